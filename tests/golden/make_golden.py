@@ -1,0 +1,181 @@
+"""Generate golden vectors from the UNMODIFIED reference NeRF branch (run in the build container).
+
+    python tests/golden/make_golden.py            # needs /root/reference (or $C3D_REFERENCE)
+
+The reference's `exp/cips3d/nerf_utils.py` and `exp/cips3d/volume_renderer.py` are imported
+as they are; two import-only third-party modules they pull in (`tl2.tl2_utils`, used for a
+`__repr__`; `pytorch3d.transforms`, used by an unrelated camera helper) are replaced by empty
+in-memory stubs.  Nothing from the reference is written into this repository except the
+numeric inputs/outputs below.
+
+Outputs (committed):
+  weights_seed0.npz   D=8 renderer state dict (torch.manual_seed(0) init, values rounded to
+                      fp16-representable numbers so they store exactly in 2 bytes; D=2 / D=6
+                      cases reuse layers 0..D-1 + views/rgb/sigma heads of the same dict)
+  case_*.npz          inputs (256-ray subsets of a 64x64 image) and reference outputs
+  camera.npz          Camera.generate_camera_params + prepare_nerf_inputs checks
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("C3D_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def import_reference():
+    tl2 = types.ModuleType("tl2")
+    tl2_utils = types.ModuleType("tl2.tl2_utils")
+    tl2_utils.get_class_repr = lambda self, prefix="": f"{prefix}.{type(self).__name__}"
+    tl2.tl2_utils = tl2_utils
+    p3d = types.ModuleType("pytorch3d")
+    p3d_tr = types.ModuleType("pytorch3d.transforms")
+    p3d.transforms = p3d_tr
+    sys.modules.update({"tl2": tl2, "tl2.tl2_utils": tl2_utils, "pytorch3d": p3d, "pytorch3d.transforms": p3d_tr})
+    sys.path.insert(0, REF)
+    import exp.cips3d.nerf_utils as nu
+    import exp.cips3d.volume_renderer as vr
+    return nu, vr
+
+
+FFHQ = dict(fov_ang=6, dist_radius=0.12)
+CARS = dict(fov_ang=15, dist_radius=0.3)
+
+
+def sub_state(sd8, D):
+    """D-layer state dict built from the first D point layers of the D=8 one."""
+    out = {}
+    for k, v in sd8.items():
+        if k.startswith("network.pts_linears."):
+            if int(k.split(".")[2]) < D:
+                out[k] = v
+        else:
+            out[k] = v
+    return out
+
+
+def main():
+    nu, vr = import_reference()
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(0)
+    R8 = vr.VolumeFeatureRenderer(N_layers_renderer=8, input_dim=3, hidden_dim=256, style_dim=256,
+                                  view_dim=3, with_sdf=True, output_features=True)
+    with torch.no_grad():
+        for p in R8.parameters():
+            p.copy_(p.half().float())
+    sd8 = {k: v.detach().clone() for k, v in R8.state_dict().items()}
+    np.savez(os.path.join(HERE, "weights_seed0.npz"),
+             **{k: v.numpy().astype(np.float16) for k, v in sd8.items()})
+
+    def renderer(D):
+        R = vr.VolumeFeatureRenderer(N_layers_renderer=D, input_dim=3, hidden_dim=256, style_dim=256,
+                                     view_dim=3, with_sdf=True, output_features=True)
+        R.load_state_dict(sub_state(sd8, D), strict=True)
+        return R.eval()
+
+    ray_idx = torch.arange(0, 4096, 16) + (torch.arange(256) // 4) % 16      # 256 rays spread over the image
+
+    def case(name, D, N, cam, locs, static_viewdirs=False, perturb=False, wplus=False, seed=1,
+             sigmoid_beta=None, grads=False):
+        g = torch.Generator().manual_seed(seed)
+        R = renderer(D)
+        if sigmoid_beta is not None:
+            with torch.no_grad():
+                R.sigmoid_beta.fill_(sigmoid_beta)
+        locs_t = torch.tensor(locs, dtype=torch.float32)
+        b = locs_t.shape[0]
+        c2w, focal, near, far, _ = nu.Camera.generate_camera_params(
+            img_size=64, device="cpu", locations=locs_t, **cam)
+        torch.manual_seed(seed + 100)         # perturb draw (torch.rand inside get_z_vals)
+        pts, rays_d, viewdirs, z_vals = nu.Render.prepare_nerf_inputs(
+            focal=focal, img_size=64, cam_poses=c2w, near=near, far=far, N_samples=N,
+            perturb=perturb, static_viewdirs=static_viewdirs)
+        pts = pts.reshape(b, 4096, N, 3)[:, ray_idx].contiguous()
+        rays_d = rays_d.reshape(b, 4096, 3)[:, ray_idx].contiguous()
+        viewdirs = viewdirs.reshape(b, 4096, 3)[:, ray_idx].contiguous()
+        z_vals = z_vals.reshape(b, 4096, N)[:, ray_idx].contiguous()
+        if wplus:
+            styles = 0.6 * torch.randn(b, D + 1, 256, generator=g)
+        else:
+            styles = (0.6 * torch.randn(b, 1, 256, generator=g)).repeat(1, D + 1, 1)
+        out = {}
+        if grads:
+            styles.requires_grad_(True)
+            pts.requires_grad_(True)
+            rays_d.requires_grad_(True)
+            viewdirs.requires_grad_(True)
+            rgb_map, feat, sdf, mask, xyz, _ = R(pts=pts, rays_d=rays_d, viewdirs=viewdirs, z_vals=z_vals,
+                                                 near=near, far=far, styles=styles)
+            cot = {k: torch.randn(v.shape, generator=g) for k, v in
+                   dict(rgb_map=rgb_map, feature_map=feat, mask=mask, xyz=xyz).items()}
+            loss = (rgb_map * cot["rgb_map"]).sum() + (feat * cot["feature_map"]).sum() * 0.05 \
+                + (mask * cot["mask"]).sum() + (xyz * cot["xyz"]).sum()
+            gs = torch.autograd.grad(loss, [styles, pts, rays_d, viewdirs])
+            out.update({"cot_" + k: v.numpy() for k, v in cot.items()})
+            out.update(g_styles=gs[0].numpy(), g_pts=gs[1].numpy(), g_rays_d=gs[2].numpy(),
+                       g_viewdirs=gs[3].numpy(), loss=np.float32(loss.item()))
+        else:
+            with torch.no_grad():
+                rgb_map, feat, sdf, mask, xyz, _ = R(pts=pts, rays_d=rays_d, viewdirs=viewdirs, z_vals=z_vals,
+                                                     near=near, far=far, styles=styles)
+        out.update(
+            D=np.int32(D), N=np.int32(N), static_viewdirs=np.int32(static_viewdirs),
+            sigmoid_beta=R.sigmoid_beta.detach().numpy(), ray_idx=ray_idx.numpy().astype(np.int32),
+            locations=locs_t.numpy(), c2w=c2w.numpy(), focal=focal.numpy(), near=near.numpy(), far=far.numpy(),
+            pts=pts.detach().numpy(), rays_d=rays_d.detach().numpy(), viewdirs=viewdirs.detach().numpy(),
+            z_vals=z_vals.numpy(), styles=styles.detach().numpy(),
+            rgb_map=rgb_map.detach().numpy(), feature_map=feat.detach().numpy(), sdf=sdf.detach().numpy(),
+            mask=mask.detach().numpy(), xyz=xyz.detach().numpy())
+        np.savez_compressed(os.path.join(HERE, f"case_{name}.npz"), **out)
+        print(name, {k: float(np.abs(out[k]).mean()) for k in ("rgb_map", "feature_map", "sdf", "mask", "xyz")})
+
+    case("ffhq_d8_n24", 8, 24, FFHQ, [[0.25, -0.1]])
+    case("ffhq_d2_n24", 2, 24, FFHQ, [[0.25, -0.1]])
+    case("ffhq_d2_n128_static", 2, 128, FFHQ, [[0.25, -0.1]], static_viewdirs=True)
+    case("cars_d6_n24", 6, 24, CARS, [[0.25, -0.1]])
+    case("ffhq_d8_n24_b2_wplus_perturb", 8, 24, FFHQ, [[-0.3, 0.12], [0.0, 0.0]], perturb=True, wplus=True)
+    case("cars_d6_n36_b2_beta", 6, 36, CARS, [[3.0, 0.16], [-1.5, 0.0]], wplus=True, sigmoid_beta=0.03)
+    case("ffhq_d2_n24_grads", 2, 24, FFHQ, [[0.2, 0.05], [-0.2, -0.05]], wplus=True, grads=True)
+    case("ffhq_d8_n24_grads_static", 8, 24, FFHQ, [[0.1, 0.1]], static_viewdirs=True, grads=True)
+
+    # survey anchors: un-rounded seed-0 weights, full image, styles = randn after camera
+    torch.manual_seed(0)
+    Rr = vr.VolumeFeatureRenderer(N_layers_renderer=8, input_dim=3, hidden_dim=256, style_dim=256,
+                                  view_dim=3, with_sdf=True, output_features=True)
+    c2w, focal, near, far, _ = nu.Camera.generate_camera_params(
+        img_size=64, device="cpu", locations=torch.zeros(1, 2), **FFHQ)
+    pts, rays_d, viewdirs, z_vals = nu.Render.prepare_nerf_inputs(
+        focal=focal, img_size=64, cam_poses=c2w, near=near, far=far, N_samples=24, perturb=False,
+        static_viewdirs=False)
+    styles = torch.randn(1, 9, 256)
+    with torch.no_grad():
+        o = Rr(pts=pts.reshape(1, 4096, 24, 3), rays_d=rays_d.reshape(1, 4096, 3),
+               viewdirs=viewdirs.reshape(1, 4096, 3), z_vals=z_vals.reshape(1, 4096, 24),
+               near=near, far=far, styles=styles)
+    print("survey anchor mean-abs:", [float(t.abs().mean()) for t in o[:5]])
+
+    # camera + ray generation goldens
+    cam = {}
+    for tag, cfg, locs in (("ffhq", FFHQ, [[0.0, 0.0], [0.25, -0.1], [-0.3, 0.15]]),
+                           ("cars", CARS, [[3.14, 0.0], [-1.2, 0.1674], [0.0, 1.5707963]])):
+        locs_t = torch.tensor(locs, dtype=torch.float32)
+        c2w, focal, near, far, vp = nu.Camera.generate_camera_params(
+            img_size=64, device="cpu", locations=locs_t, **cfg)
+        for sv in (False, True):
+            pts, rays_d, viewdirs, z_vals = nu.Render.prepare_nerf_inputs(
+                focal=focal, img_size=64, cam_poses=c2w, near=near, far=far, N_samples=24, perturb=False,
+                static_viewdirs=sv)
+            cam.update({f"{tag}_sv{int(sv)}_pts": pts[:, ::8, ::8].numpy(),
+                        f"{tag}_sv{int(sv)}_rays_d": rays_d[:, ::4, ::4].numpy(),
+                        f"{tag}_sv{int(sv)}_viewdirs": viewdirs[:, ::4, ::4].numpy(),
+                        f"{tag}_sv{int(sv)}_z_vals": z_vals[:, ::8, ::8].numpy()})
+        cam.update({f"{tag}_locations": locs_t.numpy(), f"{tag}_c2w": c2w.numpy(), f"{tag}_focal": focal.numpy(),
+                    f"{tag}_near": near.numpy(), f"{tag}_far": far.numpy()})
+    np.savez_compressed(os.path.join(HERE, "camera.npz"), **cam)
+
+
+if __name__ == "__main__":
+    main()
