@@ -1,0 +1,346 @@
+// libc3dpp.so -- C ABI entry points (see include/c3d_abi.h).  Validation + launches only; all math is in
+// the kernel headers.  Nothing here allocates device memory or synchronises.
+#include <stdlib.h>
+#include <string.h>
+
+#include "c3d_common.cuh"
+#include "kernels_aux.cuh"
+#include "mlp_fp32.cuh"
+#include "fused_bf16_sm100.cuh"
+#include "backward.cuh"
+
+namespace c3d {
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+struct FwdWs {
+  size_t film, first, view, chunk, total;
+  int chunk_imgs;
+  size_t c_feat, c_rgb, c_pts, c_rd, c_vd, c_z;   // offsets inside the fp32 chunk area
+};
+static FwdWs fwd_ws(const c3d_fwd_params* p) {
+  FwdWs w;
+  size_t o = 0;
+  const size_t b = (size_t)p->batch;
+  w.film = o;  o += align_up(b * (p->D + 1) * W * sizeof(float2), 256);
+  w.first = o; o += align_up(b * W * sizeof(float4), 256);
+  w.view = o;  o += align_up(b * W * sizeof(float4), 256);
+  w.chunk = o;
+  w.chunk_imgs = 0;
+  w.c_feat = w.c_rgb = w.c_pts = w.c_rd = w.c_vd = w.c_z = 0;
+  if (p->mode == C3D_MODE_FP32) {
+    const size_t P = (size_t)p->n_rays * p->n_samples, R = (size_t)p->n_rays;
+    const size_t per_img = align_up(P * W * 4, 256) + align_up(P * 3 * 4, 256) +
+                           (p->input_kind == C3D_INPUT_POSES ? align_up(P * 12, 256) + 2 * align_up(R * 12, 256) + align_up(P * 4, 256) : 0);
+    size_t ci = ((size_t)1 << 30) / per_img;
+    if (ci < 1) ci = 1;
+    if (ci > b) ci = b;
+    w.chunk_imgs = (int)ci;
+    size_t c = 0;
+    w.c_feat = c; c += align_up(ci * P * W * 4, 256);
+    w.c_rgb = c;  c += align_up(ci * P * 3 * 4, 256);
+    if (p->input_kind == C3D_INPUT_POSES) {
+      w.c_pts = c; c += align_up(ci * P * 12, 256);
+      w.c_rd = c;  c += align_up(ci * R * 12, 256);
+      w.c_vd = c;  c += align_up(ci * R * 12, 256);
+      w.c_z = c;   c += align_up(ci * P * 4, 256);
+    }
+    o += c;
+  }
+  w.total = o;
+  return w;
+}
+
+static int validate_fwd(const c3d_fwd_params* p) {
+  C3D_CHECK_ARG(p != nullptr, "params is NULL");
+  C3D_CHECK_ARG(p->abi_version == C3D_ABI_VERSION, "abi_version %d != library %d", p->abi_version, C3D_ABI_VERSION);
+  C3D_CHECK_ARG(p->mode == C3D_MODE_FP32 || p->mode == C3D_MODE_BF16, "bad mode %d", p->mode);
+  C3D_CHECK_ARG(p->input_kind == C3D_INPUT_POSES || p->input_kind == C3D_INPUT_POINTS, "bad input_kind %d", p->input_kind);
+  C3D_CHECK_ARG(p->batch >= 1 && p->n_rays >= 1, "batch=%d n_rays=%d must be >= 1", p->batch, p->n_rays);
+  C3D_CHECK_ARG(p->n_samples >= 2 && p->n_samples <= 256, "n_samples=%d outside [2,256]", p->n_samples);
+  C3D_CHECK_ARG(p->D >= 1 && p->D <= C3D_MAX_LAYERS, "D=%d outside [1,%d]", p->D, C3D_MAX_LAYERS);
+  C3D_CHECK_ARG((long long)p->batch * p->n_rays * p->n_samples < (1ll << 31), "batch*n_rays*n_samples overflows int32");
+  C3D_CHECK_ARG(p->packed && p->styles && p->near && p->far, "packed/styles/near/far must be non-NULL");
+  C3D_CHECK_ARG(p->rgb_map && p->feature_map && p->sdf && p->mask && p->xyz, "all five output pointers are required");
+  if (p->input_kind == C3D_INPUT_POSES) {
+    C3D_CHECK_ARG(p->cam_poses && p->focal, "POSES input needs cam_poses and focal");
+    C3D_CHECK_ARG(p->img_size >= 1 && p->n_rays == p->img_size * p->img_size, "n_rays=%d != img_size^2 (%d)", p->n_rays, p->img_size);
+  } else {
+    C3D_CHECK_ARG(p->pts && p->rays_d && p->viewdirs && p->z_vals, "POINTS input needs pts, rays_d, viewdirs, z_vals");
+  }
+  const void* ptrs[] = {p->packed, p->styles, p->cam_poses, p->pts, p->rays_d, p->viewdirs, p->z_vals, p->rgb_map,
+                        p->feature_map, p->sdf, p->mask, p->xyz, p->workspace};
+  for (const void* q : ptrs) C3D_CHECK_ARG(aligned16(q), "pointer %p is not 16-byte aligned", q);
+  C3D_CHECK_ARG(p->feat_layout == C3D_FEAT_NHWC || p->feat_layout == C3D_FEAT_NCHW, "bad feat_layout %d", p->feat_layout);
+  const FwdWs w = fwd_ws(p);
+  C3D_CHECK_ARG(p->workspace && p->workspace_bytes >= w.total, "workspace too small: %zu < %zu", p->workspace_bytes, w.total);
+  return C3D_OK;
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int hw) {
+  // in (b, hw, 256) -> out (b, 256, hw); 32x32 tiles through shared memory
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8)
+    if (r0 + i < hw) tile[i][threadIdx.x] = in[((size_t)b * hw + r0 + i) * W + c0 + threadIdx.x];
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8)
+    if (r0 + threadIdx.x < hw) out[((size_t)b * W + c0 + i) * hw + r0 + threadIdx.x] = tile[threadIdx.x][i];
+}
+
+static int launch_style_prep(const void* packed, int D, const float* styles, int batch, float* film, float* first,
+                             float* view, cudaStream_t st) {
+  const PackedLayout L = packed_layout(D);
+  dim3 grid(D + 1, (batch + SP_IMGS - 1) / SP_IMGS);
+  style_prep_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(packed), L, styles, batch,
+                                          reinterpret_cast<float2*>(film), reinterpret_cast<float4*>(first),
+                                          reinterpret_cast<float4*>(view));
+  C3D_LAUNCH_CHECK();
+  return C3D_OK;
+}
+
+static int gcd_(int a, int b) { return b ? gcd_(b, a % b) : a; }
+
+static int forward_bf16(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st) {
+  C3D_CHECK_ARG(p->n_samples >= fused::MIN_SAMPLES, "bf16 mode needs n_samples >= %d (got %d); use C3D_MODE_FP32",
+                fused::MIN_SAMPLES, p->n_samples);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(p->workspace);
+  fused::Args a;
+  memset(&a, 0, sizeof(a));
+  a.blob = reinterpret_cast<const uint8_t*>(p->packed);
+  a.L = packed_layout(p->D);
+  a.film = reinterpret_cast<const float2*>(ws + w.film);
+  a.first = reinterpret_cast<const float4*>(ws + w.first);
+  a.view = reinterpret_cast<const float4*>(ws + w.view);
+  a.batch = p->batch; a.n_rays = p->n_rays; a.n_samples = p->n_samples; a.D = p->D;
+  a.img_size = p->img_size; a.static_viewdirs = p->static_viewdirs; a.input_kind = p->input_kind;
+  // unit = whole rays whose points fill whole 128-row tiles when possible, >= 6 tiles
+  const int u0 = 128 / gcd_(p->n_samples, 128);
+  int ur = u0;
+  while (ur * p->n_samples < 6 * 128) ur += u0;
+  if (ur > p->n_rays) ur = p->n_rays;
+  a.unit_rays = ur;
+  a.units_per_img = (p->n_rays + ur - 1) / ur;
+  a.cam_poses = p->cam_poses; a.focal = p->focal; a.near = p->near; a.far = p->far; a.ray_offset = p->ray_offset;
+  a.pts = p->pts; a.rays_d = p->rays_d; a.viewdirs = p->viewdirs; a.z_vals = p->z_vals;
+  a.rgb_map = p->rgb_map; a.feature_map = p->feature_map; a.sdf = p->sdf; a.mask = p->mask; a.xyz = p->xyz;
+  a.z_vals_out = p->z_vals_out;
+
+  int dev = 0, nsm = 0;
+  C3D_CUDA(cudaGetDevice(&dev));
+  C3D_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  const char* env = getenv("C3D_CLUSTER");
+  int cluster = env ? atoi(env) : 2;
+  if (cluster != 1 && cluster != 2) cluster = 2;
+  const long long total_units = (long long)a.batch * a.units_per_img;
+  int grid = nsm;
+  if ((long long)grid * 2 > total_units) grid = (int)((total_units + 1) / 2);
+  if (grid < 1) grid = 1;
+  if (cluster == 2) grid = (grid + 1) & ~1;
+  const char* genv = getenv("C3D_GRID");
+  if (genv && atoi(genv) > 0) { grid = atoi(genv); if (cluster == 2) grid = (grid + 1) & ~1; }
+
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(fused::NTHREADS);
+  cfg.dynamicSmemBytes = fused::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (cluster == 2) {
+    C3D_CUDA(cudaFuncSetAttribute(fused::fused_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::SMEM_BYTES));
+    C3D_CUDA(cudaLaunchKernelEx(&cfg, fused::fused_forward_kernel<2>, a));
+  } else {
+    C3D_CUDA(cudaFuncSetAttribute(fused::fused_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::SMEM_BYTES));
+    C3D_CUDA(cudaLaunchKernelEx(&cfg, fused::fused_forward_kernel<1>, a));
+  }
+  C3D_LAUNCH_CHECK();
+  return C3D_OK;
+}
+
+static int forward_fp32(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st, float* feat_out) {
+  uint8_t* ws = reinterpret_cast<uint8_t*>(p->workspace);
+  uint8_t* ck = ws + w.chunk;
+  const size_t P = (size_t)p->n_rays * p->n_samples, R = (size_t)p->n_rays;
+  C3D_CUDA(cudaFuncSetAttribute(mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F32_SMEM));
+  for (int i0 = 0; i0 < p->batch; i0 += w.chunk_imgs) {
+    const int ni = (p->batch - i0 < w.chunk_imgs) ? p->batch - i0 : w.chunk_imgs;
+    const float *pts, *rays_d, *viewdirs, *z_vals;
+    if (p->input_kind == C3D_INPUT_POSES) {
+      c3d_raygen_params rg;
+      memset(&rg, 0, sizeof(rg));
+      rg.batch = ni; rg.img_size = p->img_size; rg.n_samples = p->n_samples; rg.static_viewdirs = p->static_viewdirs;
+      rg.cam_poses = p->cam_poses + (size_t)i0 * 12; rg.focal = p->focal + i0; rg.near = p->near + i0; rg.far = p->far + i0;
+      rg.ray_offset = p->ray_offset ? p->ray_offset + (size_t)i0 * R : nullptr;
+      rg.pts = reinterpret_cast<float*>(ck + w.c_pts); rg.rays_d = reinterpret_cast<float*>(ck + w.c_rd);
+      rg.viewdirs = reinterpret_cast<float*>(ck + w.c_vd); rg.z_vals = reinterpret_cast<float*>(ck + w.c_z);
+      const long long n = (long long)ni * R;
+      raygen_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(rg);
+      C3D_LAUNCH_CHECK();
+      pts = rg.pts; rays_d = rg.rays_d; viewdirs = rg.viewdirs; z_vals = rg.z_vals;
+      if (p->z_vals_out)
+        C3D_CUDA(cudaMemcpyAsync(p->z_vals_out + (size_t)i0 * P, z_vals, (size_t)ni * P * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+      pts = p->pts + (size_t)i0 * P * 3; rays_d = p->rays_d + (size_t)i0 * R * 3;
+      viewdirs = p->viewdirs + (size_t)i0 * R * 3; z_vals = p->z_vals + (size_t)i0 * P;
+    }
+    MlpF32Args m;
+    m.blob = reinterpret_cast<const uint8_t*>(p->packed);
+    m.L = packed_layout(p->D);
+    m.film = reinterpret_cast<const float2*>(ws + w.film) + (size_t)i0 * (p->D + 1) * W;
+    m.first = reinterpret_cast<const float4*>(ws + w.first) + (size_t)i0 * W;
+    m.view = reinterpret_cast<const float4*>(ws + w.view) + (size_t)i0 * W;
+    m.pts = pts; m.viewdirs = viewdirs; m.near = p->near + i0; m.far = p->far + i0;
+    m.n_samples = p->n_samples; m.pts_per_img = (int)P; m.tiles_per_img = (int)((P + F32_TP - 1) / F32_TP);
+    m.feat = reinterpret_cast<float*>(ck + w.c_feat); m.rgb = reinterpret_cast<float*>(ck + w.c_rgb);
+    m.sdf = p->sdf + (size_t)i0 * P;
+    mlp_fp32_kernel<<<(unsigned)(ni * m.tiles_per_img), 256, F32_SMEM, st>>>(m);
+    C3D_LAUNCH_CHECK();
+    c3d_composite_params c;
+    memset(&c, 0, sizeof(c));
+    c.n_rays = (int64_t)ni * R; c.n_samples = p->n_samples; c.n_feat = W;
+    c.sigmoid_beta_ptr = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p->packed) + m.L.scal) + 4;
+    c.rgb = m.rgb; c.sdf = m.sdf; c.features = m.feat; c.z_vals = z_vals; c.rays_d = rays_d; c.pts = pts;
+    c.rgb_map = p->rgb_map + (size_t)i0 * R * 3; c.feature_map = feat_out + (size_t)i0 * R * W;
+    c.xyz = p->xyz + (size_t)i0 * R * 3; c.mask = p->mask + (size_t)i0 * R * 2;
+    composite_fwd_kernel<<<(unsigned)((c.n_rays + 7) / 8), 256, 0, st>>>(c);
+    C3D_LAUNCH_CHECK();
+  }
+  return C3D_OK;
+}
+
+}  // namespace c3d
+
+using namespace c3d;
+
+extern "C" {
+
+int c3d_abi_version(void) { return C3D_ABI_VERSION; }
+const char* c3d_last_error(void) { return g_err; }
+int c3d_last_launch_count(void) { return g_launches; }
+
+size_t c3d_packed_bytes(int32_t D) {
+  if (D < 1 || D > C3D_MAX_LAYERS) return 0;
+  return packed_layout(D).total;
+}
+
+int c3d_pack_weights(const c3d_raw_params* raw, void* packed, size_t packed_bytes, c3d_stream_t stream) {
+  C3D_CHECK_ARG(raw && packed, "raw/packed is NULL");
+  C3D_CHECK_ARG(raw->D >= 1 && raw->D <= C3D_MAX_LAYERS, "D=%d outside [1,%d]", raw->D, C3D_MAX_LAYERS);
+  const PackedLayout L = packed_layout(raw->D);
+  C3D_CHECK_ARG(packed_bytes >= L.total, "packed buffer too small: %zu < %zu", packed_bytes, L.total);
+  C3D_CHECK_ARG(aligned16(packed), "packed buffer must be 16-byte aligned");
+  for (int l = 0; l < raw->D; ++l)
+    C3D_CHECK_ARG(raw->pts_weight[l] && raw->pts_bias[l] && raw->pts_gamma_weight[l] && raw->pts_gamma_bias[l] &&
+                      raw->pts_beta_weight[l] && raw->pts_beta_bias[l], "pts layer %d has a NULL tensor", l);
+  C3D_CHECK_ARG(raw->views_weight && raw->views_bias && raw->views_gamma_weight && raw->views_gamma_bias &&
+                    raw->views_beta_weight && raw->views_beta_bias && raw->rgb_weight && raw->rgb_bias &&
+                    raw->sigma_weight && raw->sigma_bias && raw->sigmoid_beta, "a head/view tensor is NULL");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  pack_small_kernel<<<1, 256, 0, st>>>(*raw, reinterpret_cast<uint8_t*>(packed), L);
+  C3D_LAUNCH_CHECK();
+  pack_matrix_kernel<<<dim3(raw->D + 1, W / 32, 3), dim3(32, 8), 0, st>>>(*raw, reinterpret_cast<uint8_t*>(packed), L);
+  C3D_LAUNCH_CHECK();
+  return C3D_OK;
+}
+
+size_t c3d_workspace_bytes(const c3d_fwd_params* p) {
+  if (!p || p->batch < 1 || p->n_rays < 1 || p->n_samples < 1 || p->D < 1) return 0;
+  FwdWs w = fwd_ws(p);
+  size_t extra = (p->feat_layout == C3D_FEAT_NCHW) ? align_up((size_t)p->batch * p->n_rays * W * 4, 256) : 0;
+  return w.total + extra;
+}
+
+int c3d_style_prep(const void* packed, int32_t D, const float* styles, int32_t batch, float* film, float* first,
+                     float* view, c3d_stream_t stream) {
+  C3D_CHECK_ARG(packed && styles && film && first && view && batch >= 1, "NULL argument or batch < 1");
+  C3D_CHECK_ARG(D >= 1 && D <= C3D_MAX_LAYERS, "D=%d outside [1,%d]", D, C3D_MAX_LAYERS);
+  return launch_style_prep(packed, D, styles, batch, film, first, view, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int c3d_nerf_forward(const c3d_fwd_params* p, c3d_stream_t stream) {
+  g_launches = 0;
+  int rc = validate_fwd(p);
+  if (rc != C3D_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const FwdWs w = fwd_ws(p);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(p->workspace);
+  rc = launch_style_prep(p->packed, p->D, p->styles, p->batch, reinterpret_cast<float*>(ws + w.film),
+                         reinterpret_cast<float*>(ws + w.first), reinterpret_cast<float*>(ws + w.view), st);
+  if (rc != C3D_OK) return rc;
+  float* feat_out = p->feature_map;
+  if (p->feat_layout == C3D_FEAT_NCHW) {
+    C3D_CHECK_ARG(p->workspace_bytes >= c3d_workspace_bytes(p), "workspace too small for NCHW staging");
+    feat_out = reinterpret_cast<float*>(ws + w.total);
+  }
+  c3d_fwd_params q = *p;
+  q.feature_map = feat_out;
+  rc = (p->mode == C3D_MODE_BF16) ? forward_bf16(&q, w, st) : forward_fp32(&q, w, st, feat_out);
+  if (rc != C3D_OK) return rc;
+  if (p->feat_layout == C3D_FEAT_NCHW) {
+    dim3 grid((p->n_rays + 31) / 32, W / 32, p->batch);
+    nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, st>>>(feat_out, p->feature_map, p->n_rays);
+    C3D_LAUNCH_CHECK();
+  }
+  return C3D_OK;
+}
+
+int c3d_raygen(const c3d_raygen_params* p, c3d_stream_t stream) {
+  C3D_CHECK_ARG(p && p->batch >= 1 && p->img_size >= 1 && p->n_samples >= 2, "bad raygen sizes");
+  C3D_CHECK_ARG(p->cam_poses && p->focal && p->near && p->far, "cam_poses/focal/near/far must be non-NULL");
+  const long long n = (long long)p->batch * p->img_size * p->img_size;
+  raygen_kernel<<<(unsigned)((n + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*p);
+  C3D_LAUNCH_CHECK();
+  return C3D_OK;
+}
+
+int c3d_composite_forward(const c3d_composite_params* p, c3d_stream_t stream) {
+  C3D_CHECK_ARG(p && p->n_rays >= 1, "n_rays must be >= 1");
+  C3D_CHECK_ARG(p->n_samples >= 1 && p->n_samples <= CMP_MAX_N, "n_samples=%d outside [1,%d]", p->n_samples, CMP_MAX_N);
+  C3D_CHECK_ARG(p->n_feat >= 0 && p->n_feat % 4 == 0, "n_feat=%d must be a multiple of 4", p->n_feat);
+  C3D_CHECK_ARG(p->rgb && p->sdf && p->z_vals && p->rays_d && p->pts, "rgb/sdf/z_vals/rays_d/pts must be non-NULL");
+  C3D_CHECK_ARG(p->rgb_map && p->xyz && p->mask, "rgb_map/xyz/mask outputs must be non-NULL");
+  C3D_CHECK_ARG(!p->features || p->feature_map, "feature_map output missing");
+  C3D_CHECK_ARG(aligned16(p->features) && aligned16(p->feature_map), "features must be 16-byte aligned");
+  C3D_CHECK_ARG(p->sigmoid_beta_ptr || p->sigmoid_beta > 0.f, "sigmoid_beta must be > 0");
+  composite_fwd_kernel<<<(unsigned)((p->n_rays + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*p);
+  C3D_LAUNCH_CHECK();
+  return C3D_OK;
+}
+
+int c3d_umma_selftest(const uint16_t* a, const uint16_t* b, float* d, int32_t N, int32_t K, int32_t variant,
+                      c3d_stream_t stream) {
+  (void)variant;
+  C3D_CHECK_ARG(a && b && d, "NULL pointer");
+  C3D_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0, "N=%d must be a multiple of 16 in [16,256]", N);
+  C3D_CHECK_ARG(K >= 64 && K <= 256 && K % 64 == 0, "K=%d must be a multiple of 64 in [64,256]", K);
+  const int smem = fused::ACT_BYTES + N * 128 * (K / 64) + 1024;
+  C3D_CUDA(cudaFuncSetAttribute(fused::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  fused::umma_selftest_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a, b, d, N, K);
+  C3D_LAUNCH_CHECK();
+  return C3D_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+size_t c3d_backward_workspace_bytes(const c3d_bwd_params* p) { (void)p; return 0; }
+int c3d_nerf_backward(const c3d_bwd_params* p, c3d_stream_t stream) {
+  (void)p; (void)stream;
+  return c3d::fail(C3D_ERR_UNSUPPORTED, "c3d_nerf_backward: not built in this revision");
+}
+int c3d_composite_backward(const c3d_composite_params* p, c3d_stream_t stream) {
+  (void)p; (void)stream;
+  return c3d::fail(C3D_ERR_UNSUPPORTED, "c3d_composite_backward: not built in this revision");
+}
+}

@@ -1,0 +1,125 @@
+// Shared definitions for libc3dpp: packed-weight blob layout, error plumbing, small device math.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/c3d_abi.h"
+
+#define C3D_MAGIC 0x43334450u  // "C3DP"
+
+namespace c3d {
+
+constexpr int W = C3D_W;            // hidden width
+constexpr int KCHUNK = 64;          // bf16 elements per 128-byte swizzle row
+constexpr int NCHUNK = W / KCHUNK;  // 4 K-chunks per layer
+
+// ------------------------------------------------------------------------------------------
+// Packed blob (device memory owned by the caller; produced by c3d_pack_weights).
+//   header   : uint32 magic, int32 D
+//   w0       : float4[256]      (W0[c][0..2], b0[c])                     volume_renderer.py:57,62
+//   wvdir    : float4[256]      (Wview[c][256..258], 0)                  volume_renderer.py:111-113
+//   bias     : float[(D+1)*256] bias of point layer l (l<D) / view layer (l==D)
+//   wsig     : float[256]       sigma_linear.weight                      volume_renderer.py:115
+//   wrgb     : float4[256]      (Wrgb[0][c], Wrgb[1][c], Wrgb[2][c], 0)  volume_renderer.py:114
+//   scal     : float[8]         bsig, brgb[0..2], sigmoid_beta
+//   film     : per layer l<=D:  GwT[256 k][256 c], BwT[256 k][256 c], gb[256], bb[256]
+//   wT32     : per layer l in 1..D: WT[256 k][256 c] fp32 (view layer: columns 0..255 only)
+//   wbf16    : per layer l in 1..D: 4 K-chunks x [256 n][64 k] bf16, rows of 128 B, 16-byte units
+//              XOR-swizzled with (n & 7)  == UMMA K-major SWIZZLE_128B image of the smem stage
+//   rgb16    : 4 K-chunks x [16 n][64 k] bf16, same swizzle (rows 0..2 = Wrgb, rest zero)
+// ------------------------------------------------------------------------------------------
+struct PackedLayout {
+  size_t w0, wvdir, bias, wsig, wrgb, scal, film, wT32, wbf16, rgb16, total;
+  int D;
+};
+constexpr size_t FILM_LAYER_FLOATS = 2 * (size_t)W * W + 2 * W;
+constexpr size_t WBF16_LAYER_BYTES = (size_t)W * W * 2;      // 131072
+constexpr size_t WBF16_CHUNK_BYTES = (size_t)W * KCHUNK * 2; // 32768
+constexpr size_t RGB16_BYTES = (size_t)16 * W * 2;           // 8192
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline PackedLayout packed_layout(int D) {
+  PackedLayout L;
+  L.D = D;
+  size_t o = 256;  // header
+  L.w0 = o;    o += sizeof(float4) * W;
+  L.wvdir = o; o += sizeof(float4) * W;
+  L.bias = o;  o += sizeof(float) * (size_t)(D + 1) * W;
+  L.wsig = o;  o += sizeof(float) * W;
+  L.wrgb = o;  o += sizeof(float4) * W;
+  L.scal = o;  o += 256;
+  L.film = o;  o += sizeof(float) * FILM_LAYER_FLOATS * (size_t)(D + 1);
+  L.wT32 = o;  o += sizeof(float) * (size_t)W * W * (size_t)D;
+  o = align_up(o, 1024);
+  L.wbf16 = o; o += WBF16_LAYER_BYTES * (size_t)D;
+  L.rgb16 = o; o += RGB16_BYTES;
+  L.total = align_up(o, 1024);
+  return L;
+}
+
+// byte offset of element (n, k) inside one K-chunk image with `rows` rows (UMMA K-major SW128)
+__host__ __device__ inline uint32_t sw128_offset(int n, int k /*0..63*/) {
+  return (uint32_t)n * 128u + ((((uint32_t)k >> 3) ^ ((uint32_t)n & 7u)) << 4) + (((uint32_t)k & 7u) << 1);
+}
+
+// ------------------------------------------------------------------------------------------
+// error plumbing (thread-local message; no exceptions across the ABI)
+// ------------------------------------------------------------------------------------------
+extern thread_local char g_err[512];
+extern thread_local int g_launches;
+int fail(int code, const char* fmt, ...);
+#define C3D_CHECK_ARG(cond, ...) do { if (!(cond)) return c3d::fail(C3D_ERR_ARG, __VA_ARGS__); } while (0)
+#define C3D_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \
+  return c3d::fail(C3D_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define C3D_LAUNCH_CHECK() do { c3d::g_launches++; C3D_CUDA(cudaGetLastError()); } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_precise(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Ray set-up shared by every kernel that generates rays in-kernel (nerf_utils.py:39-63).
+struct RayGeom {
+  float ox, oy, oz;   // origin (c2w[:, 3])
+  float dx, dy, dz;   // un-normalised world direction
+  float vx, vy, vz;   // view direction (normalised d or d_cam)
+  float dnorm;        // |d|
+};
+__device__ __forceinline__ RayGeom make_ray(const float* __restrict__ pose /*3x4*/, float focal, int img_size,
+                                            int ray, bool static_viewdirs) {
+  const int iy = ray / img_size, ix = ray - iy * img_size;
+  const float half = 0.5f * (float)img_size;
+  const float cx = ((float)ix + 0.5f - half) / focal;
+  const float cy = -((float)iy + 0.5f - half) / focal;
+  const float cz = -1.0f;
+  RayGeom r;
+  r.dx = cx * pose[0] + cy * pose[1] + cz * pose[2];
+  r.dy = cx * pose[4] + cy * pose[5] + cz * pose[6];
+  r.dz = cx * pose[8] + cy * pose[9] + cz * pose[10];
+  r.ox = pose[3]; r.oy = pose[7]; r.oz = pose[11];
+  r.dnorm = sqrtf(r.dx * r.dx + r.dy * r.dy + r.dz * r.dz);
+  float sx = static_viewdirs ? cx : r.dx, sy = static_viewdirs ? cy : r.dy, sz = static_viewdirs ? cz : r.dz;
+  float n = sqrtf(sx * sx + sy * sy + sz * sz);
+  float inv = 1.0f / fmaxf(n, 1e-12f);
+  r.vx = sx * inv; r.vy = sy * inv; r.vz = sz * inv;
+  return r;
+}
+// sample depth k of N (nerf_utils.py:97-119, offset sampling): near*(1-t)+far*t (+ u*(far-near)/N)
+__device__ __forceinline__ float sample_depth(float near, float far, int k, int N, float u) {
+  const float t = (float)k * ((1.0f - 1.0f / (float)N) / (float)(N - 1 > 0 ? N - 1 : 1));
+  const float z = near * (1.0f - t) + far * t;
+  if (u == 0.0f) return z;
+  // perturb: lower + (upper-lower)*u with upper = z_{k+1} (far for the last sample)
+  const float t1 = (float)(k + 1) * ((1.0f - 1.0f / (float)N) / (float)(N - 1 > 0 ? N - 1 : 1));
+  const float zu = (k + 1 < N) ? near * (1.0f - t1) + far * t1 : far;
+  return z + (zu - z) * u;
+}
+
+}  // namespace c3d

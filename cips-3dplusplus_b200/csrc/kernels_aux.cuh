@@ -1,0 +1,275 @@
+// Auxiliary kernels: weight packing, FiLM style preparation, ray generation, standalone compositing.
+#pragma once
+#include "c3d_common.cuh"
+
+namespace c3d {
+
+// ------------------------------------------------------------------------------------------
+// pack_weights: reference state_dict -> packed blob (layout: c3d_common.cuh)
+// ------------------------------------------------------------------------------------------
+__global__ void pack_small_kernel(c3d_raw_params raw, uint8_t* __restrict__ blob, PackedLayout L) {
+  const int c = threadIdx.x;  // 256 threads, 1 block
+  const int D = raw.D;
+  if (c == 0) {
+    reinterpret_cast<uint32_t*>(blob)[0] = C3D_MAGIC;
+    reinterpret_cast<int32_t*>(blob)[1] = D;
+    float* s = reinterpret_cast<float*>(blob + L.scal);
+    s[0] = raw.sigma_bias[0];
+    s[1] = raw.rgb_bias[0]; s[2] = raw.rgb_bias[1]; s[3] = raw.rgb_bias[2];
+    s[4] = raw.sigmoid_beta[0];
+    s[5] = s[6] = s[7] = 0.f;
+  }
+  reinterpret_cast<float4*>(blob + L.w0)[c] =
+      make_float4(raw.pts_weight[0][c * 3 + 0], raw.pts_weight[0][c * 3 + 1], raw.pts_weight[0][c * 3 + 2], raw.pts_bias[0][c]);
+  reinterpret_cast<float4*>(blob + L.wvdir)[c] =
+      make_float4(raw.views_weight[c * (W + 3) + W + 0], raw.views_weight[c * (W + 3) + W + 1],
+                  raw.views_weight[c * (W + 3) + W + 2], 0.f);
+  float* bias = reinterpret_cast<float*>(blob + L.bias);
+  for (int l = 0; l < D; ++l) bias[l * W + c] = raw.pts_bias[l][c];
+  bias[D * W + c] = raw.views_bias[c];
+  reinterpret_cast<float*>(blob + L.wsig)[c] = raw.sigma_weight[c];
+  reinterpret_cast<float4*>(blob + L.wrgb)[c] =
+      make_float4(raw.rgb_weight[c], raw.rgb_weight[W + c], raw.rgb_weight[2 * W + c], 0.f);
+  // FiLM biases
+  for (int l = 0; l <= D; ++l) {
+    float* f = reinterpret_cast<float*>(blob + L.film) + (size_t)l * FILM_LAYER_FLOATS;
+    const float* gb = l < D ? raw.pts_gamma_bias[l] : raw.views_gamma_bias;
+    const float* bb = l < D ? raw.pts_beta_bias[l] : raw.views_beta_bias;
+    f[2 * W * W + c] = gb[c];
+    f[2 * W * W + W + c] = bb[c];
+  }
+  // rgb head bf16 image: [16 n][64 k] x 4 chunks (rows >= 3 zero)
+  uint8_t* r16 = blob + L.rgb16;
+  for (int n = 0; n < 16; ++n) {
+    float v = n < 3 ? raw.rgb_weight[n * W + c] : 0.f;
+    const int ch = c >> 6, k = c & 63;
+    *reinterpret_cast<__nv_bfloat16*>(r16 + (size_t)ch * (16 * 128) + sw128_offset(n, k)) = __float2bfloat16_rn(v);
+  }
+}
+
+// grid (D+1 layers, 256/32 row tiles), block (32,8): transposes 32x32 tiles of the three 256x256
+// matrices of layer l (FiLM gamma, FiLM beta, hidden weight) and writes the bf16 swizzled image.
+__global__ void pack_matrix_kernel(c3d_raw_params raw, uint8_t* __restrict__ blob, PackedLayout L) {
+  __shared__ float tile[32][33];
+  const int l = blockIdx.x;        // 0..D
+  const int D = raw.D;
+  const int which = blockIdx.z;    // 0 gamma, 1 beta, 2 hidden weight
+  const float* src; int ld = W;
+  if (which == 0) src = l < D ? raw.pts_gamma_weight[l] : raw.views_gamma_weight;
+  else if (which == 1) src = l < D ? raw.pts_beta_weight[l] : raw.views_beta_weight;
+  else {
+    if (l == 0) return;            // layer 0 is 256x3, lives in w0
+    src = l < D ? raw.pts_weight[l] : raw.views_weight;
+    ld = l < D ? W : W + 3;
+  }
+  const int r0 = blockIdx.y * 32;  // output-channel tile
+  for (int c0 = 0; c0 < W; c0 += 32) {
+    // load src[r0+ty*4+i][c0+tx]
+    for (int i = threadIdx.y; i < 32; i += 8) tile[i][threadIdx.x] = src[(size_t)(r0 + i) * ld + c0 + threadIdx.x];
+    __syncthreads();
+    if (which < 2) {
+      float* dst = reinterpret_cast<float*>(blob + L.film) + (size_t)l * FILM_LAYER_FLOATS + (size_t)which * W * W;
+      for (int i = threadIdx.y; i < 32; i += 8) dst[(size_t)(c0 + i) * W + r0 + threadIdx.x] = tile[threadIdx.x][i];
+    } else {
+      float* dst = reinterpret_cast<float*>(blob + L.wT32) + (size_t)(l - 1) * W * W;
+      for (int i = threadIdx.y; i < 32; i += 8) dst[(size_t)(c0 + i) * W + r0 + threadIdx.x] = tile[threadIdx.x][i];
+      uint8_t* img = blob + L.wbf16 + (size_t)(l - 1) * WBF16_LAYER_BYTES;
+      for (int i = threadIdx.y; i < 32; i += 8) {
+        const int n = r0 + i, k = c0 + threadIdx.x;
+        *reinterpret_cast<__nv_bfloat16*>(img + (size_t)(k >> 6) * WBF16_CHUNK_BYTES + sw128_offset(n, k & 63)) =
+            __float2bfloat16_rn(tile[i][threadIdx.x]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// style_prep: styles (b, D+1, 256) -> FiLM tables   (volume_renderer.py:66-67, 77-83)
+//   film  (b, D+1, 256) float2 : (gamma, gamma*bias + beta)   epilogue form sin(gamma*acc + shift)
+//   first (b, 256) float4      : gamma0 * W0[c][0..2], shift0
+//   view  (b, 256) float4      : gammaD * Wview[c][256..258], 0
+// grid (D+1, ceil(b/8)), block 256 (thread = output channel), 8 images per block share the weights.
+// ------------------------------------------------------------------------------------------
+constexpr int SP_IMGS = 8;
+__global__ void __launch_bounds__(256) style_prep_kernel(const uint8_t* __restrict__ blob, PackedLayout L,
+                                                          const float* __restrict__ styles, int batch,
+                                                          float2* __restrict__ film, float4* __restrict__ first,
+                                                          float4* __restrict__ view) {
+  __shared__ float s[SP_IMGS][W];
+  const int l = blockIdx.x, D = L.D, c = threadIdx.x;
+  const int b0 = blockIdx.y * SP_IMGS;
+  for (int i = 0; i < SP_IMGS; ++i) {
+    const int b = b0 + i;
+    s[i][c] = b < batch ? styles[((size_t)b * (D + 1) + l) * W + c] : 0.f;
+  }
+  __syncthreads();
+  const float* f = reinterpret_cast<const float*>(blob + L.film) + (size_t)l * FILM_LAYER_FLOATS;
+  const float* GwT = f;
+  const float* BwT = f + (size_t)W * W;
+  float g[SP_IMGS], be[SP_IMGS];
+#pragma unroll
+  for (int i = 0; i < SP_IMGS; ++i) g[i] = be[i] = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < W; ++k) {
+    const float gw = GwT[(size_t)k * W + c], bw = BwT[(size_t)k * W + c];
+#pragma unroll
+    for (int i = 0; i < SP_IMGS; ++i) {
+      g[i] = fmaf(s[i][k], gw, g[i]);
+      be[i] = fmaf(s[i][k], bw, be[i]);
+    }
+  }
+  const float gb = f[2 * W * W + c], bb = f[2 * W * W + W + c];
+  const float bias = reinterpret_cast<const float*>(blob + L.bias)[l * W + c];
+  const float4 w0 = reinterpret_cast<const float4*>(blob + L.w0)[c];
+  const float4 wv = reinterpret_cast<const float4*>(blob + L.wvdir)[c];
+#pragma unroll
+  for (int i = 0; i < SP_IMGS; ++i) {
+    const int b = b0 + i;
+    if (b >= batch) break;
+    const float gamma = 15.0f * (g[i] + gb) + 30.0f;   // LinearLayer(std_init=15, bias_init=30)
+    const float beta = 0.25f * (be[i] + bb);           // LinearLayer(std_init=0.25)
+    const float shift = fmaf(gamma, bias, beta);
+    film[((size_t)b * (D + 1) + l) * W + c] = make_float2(gamma, shift);
+    if (l == 0) first[(size_t)b * W + c] = make_float4(gamma * w0.x, gamma * w0.y, gamma * w0.z, shift);
+    if (l == D) view[(size_t)b * W + c] = make_float4(gamma * wv.x, gamma * wv.y, gamma * wv.z, 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// raygen: Render.prepare_nerf_inputs (nerf_utils.py:172-218); thread per ray.
+// ------------------------------------------------------------------------------------------
+__global__ void raygen_kernel(c3d_raygen_params p) {
+  const int hw = p.img_size * p.img_size;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)p.batch * hw) return;
+  const int b = (int)(gid / hw), ray = (int)(gid - (long long)b * hw);
+  const RayGeom r = make_ray(p.cam_poses + (size_t)b * 12, p.focal[b], p.img_size, ray, p.static_viewdirs != 0);
+  const float near = p.near[b], far = p.far[b];
+  const float u = p.ray_offset ? p.ray_offset[gid] : 0.f;
+  if (p.rays_d) { float* o = p.rays_d + gid * 3; o[0] = r.dx; o[1] = r.dy; o[2] = r.dz; }
+  if (p.viewdirs) { float* o = p.viewdirs + gid * 3; o[0] = r.vx; o[1] = r.vy; o[2] = r.vz; }
+  const int N = p.n_samples;
+  for (int k = 0; k < N; ++k) {
+    const float z = sample_depth(near, far, k, N, u);
+    if (p.z_vals) p.z_vals[gid * N + k] = z;
+    if (p.pts) {
+      float* o = p.pts + (gid * N + k) * 3;
+      o[0] = fmaf(r.dx, z, r.ox); o[1] = fmaf(r.dy, z, r.oy); o[2] = fmaf(r.dz, z, r.oz);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// composite_forward: Render.volume_integration (nerf_utils.py:230-338), one warp per ray.
+//   lanes = samples for the density -> alpha -> transmittance scan (shuffle prefix product),
+//   lanes = channels (float4 each) for the weighted feature sum.  HBM-bound: every input byte
+//   is read exactly once (1056*N + 1152 B/ray at 256 channels).
+// ------------------------------------------------------------------------------------------
+constexpr int CMP_MAX_N = 256;
+__device__ __forceinline__ float warp_excl_prod(float v, int lane, float& total) {
+  // inclusive product scan, then shift
+  float x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x *= y;
+  }
+  total = __shfl_sync(0xffffffffu, x, 31);
+  float e = __shfl_up_sync(0xffffffffu, x, 1);
+  return lane == 0 ? 1.0f : e;
+}
+
+template <bool kPrecise>
+__device__ __forceinline__ float alpha_from_sdf(float sdf, float inv_beta, float dist) {
+  // sigma = sigmoid(-sdf/beta)/beta ; alpha = 1 - exp(-sigma*dist)      (nerf_utils.py:278,286)
+  const float sg = kPrecise ? sigmoid_precise(-sdf * inv_beta) : sigmoidf_(-sdf * inv_beta);
+  const float sigma = sg * inv_beta;
+  return 1.0f - (kPrecise ? expf(-sigma * dist) : __expf(-sigma * dist));
+}
+
+__global__ void __launch_bounds__(256) composite_fwd_kernel(c3d_composite_params p) {
+  __shared__ float s_w[8][CMP_MAX_N];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long ray = (long long)blockIdx.x * 8 + warp;
+  if (ray >= p.n_rays) return;
+  const int N = p.n_samples;
+  const float beta = p.sigmoid_beta_ptr ? *p.sigmoid_beta_ptr : p.sigmoid_beta;
+  const float inv_beta = 1.0f / beta;
+  const float* rd = p.rays_d + ray * 3;
+  const float dnorm = sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]);
+  const float* z = p.z_vals + ray * N;
+  const float* sdf = p.sdf + ray * N;
+  float carry = 1.0f;
+  float a_rgb0 = 0.f, a_rgb1 = 0.f, a_rgb2 = 0.f, a_x = 0.f, a_y = 0.f, a_z = 0.f, w_last = 0.f;
+  for (int k0 = 0; k0 < N; k0 += 32) {
+    const int k = k0 + lane;
+    float one_minus = 1.0f, w = 0.f, alpha = 0.f;
+    if (k < N) {
+      const float dist = (k + 1 < N ? z[k + 1] - z[k] : 1e10f) * dnorm;
+      alpha = alpha_from_sdf<true>(sdf[k], inv_beta, dist);
+      one_minus = 1.0f - alpha + 1e-10f;
+    }
+    float total;
+    const float T = carry * warp_excl_prod(one_minus, lane, total);
+    carry *= total;
+    if (k < N) {
+      w = alpha * T;
+      s_w[warp][k] = w;
+      if (p.weights) p.weights[ray * N + k] = w;
+      const float* c = p.rgb + (ray * N + k) * 3;
+      a_rgb0 = fmaf(w, sigmoid_precise(c[0]), a_rgb0);
+      a_rgb1 = fmaf(w, sigmoid_precise(c[1]), a_rgb1);
+      a_rgb2 = fmaf(w, sigmoid_precise(c[2]), a_rgb2);
+      const float* q = p.pts + (ray * N + k) * 3;
+      a_x = fmaf(w, q[0], a_x); a_y = fmaf(w, q[1], a_y); a_z = fmaf(w, q[2], a_z);
+      if (k == N - 1) w_last = w;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a_rgb0 += __shfl_xor_sync(0xffffffffu, a_rgb0, o);
+    a_rgb1 += __shfl_xor_sync(0xffffffffu, a_rgb1, o);
+    a_rgb2 += __shfl_xor_sync(0xffffffffu, a_rgb2, o);
+    a_x += __shfl_xor_sync(0xffffffffu, a_x, o);
+    a_y += __shfl_xor_sync(0xffffffffu, a_y, o);
+    a_z += __shfl_xor_sync(0xffffffffu, a_z, o);
+    w_last += __shfl_xor_sync(0xffffffffu, w_last, o);
+  }
+  if (lane == 0) {
+    float* o = p.rgb_map + ray * 3;
+    o[0] = -1.0f + 2.0f * a_rgb0; o[1] = -1.0f + 2.0f * a_rgb1; o[2] = -1.0f + 2.0f * a_rgb2;
+    float* x = p.xyz + ray * 3;
+    x[0] = a_x; x[1] = a_y; x[2] = a_z;
+    p.mask[ray * 2 + 0] = w_last;
+    p.mask[ray * 2 + 1] = -sqrtf(a_x * a_x + a_y * a_y + a_z * a_z);
+  }
+  __syncwarp();
+  if (p.features && p.n_feat > 0) {
+    const int C4 = p.n_feat >> 2;                    // float4 per row
+    const float4* f = reinterpret_cast<const float4*>(p.features) + (size_t)ray * N * C4;
+    for (int c = lane; c < C4; c += 32) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int k = 0;
+      for (; k + 4 <= N; k += 4) {                    // 4 independent 16-byte loads in flight per lane
+        const float4 v0 = __ldcs(f + (size_t)(k + 0) * C4 + c);
+        const float4 v1 = __ldcs(f + (size_t)(k + 1) * C4 + c);
+        const float4 v2 = __ldcs(f + (size_t)(k + 2) * C4 + c);
+        const float4 v3 = __ldcs(f + (size_t)(k + 3) * C4 + c);
+        const float w0 = s_w[warp][k], w1 = s_w[warp][k + 1], w2 = s_w[warp][k + 2], w3 = s_w[warp][k + 3];
+        acc.x = fmaf(w0, v0.x, acc.x); acc.y = fmaf(w0, v0.y, acc.y); acc.z = fmaf(w0, v0.z, acc.z); acc.w = fmaf(w0, v0.w, acc.w);
+        acc.x = fmaf(w1, v1.x, acc.x); acc.y = fmaf(w1, v1.y, acc.y); acc.z = fmaf(w1, v1.z, acc.z); acc.w = fmaf(w1, v1.w, acc.w);
+        acc.x = fmaf(w2, v2.x, acc.x); acc.y = fmaf(w2, v2.y, acc.y); acc.z = fmaf(w2, v2.z, acc.z); acc.w = fmaf(w2, v2.w, acc.w);
+        acc.x = fmaf(w3, v3.x, acc.x); acc.y = fmaf(w3, v3.y, acc.y); acc.z = fmaf(w3, v3.z, acc.z); acc.w = fmaf(w3, v3.w, acc.w);
+      }
+      for (; k < N; ++k) {
+        const float4 v = __ldcs(f + (size_t)k * C4 + c);
+        const float w = s_w[warp][k];
+        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+      }
+      reinterpret_cast<float4*>(p.feature_map)[(size_t)ray * C4 + c] = acc;
+    }
+  }
+}
+
+}  // namespace c3d

@@ -1,0 +1,316 @@
+"""NerfBranch: drop-in replacement of the reference `VolumeFeatureRenderer`
+(exp/cips3d/volume_renderer.py:163-303) whose forward runs in libc3dpp.so on a B200.
+
+Same constructor arguments, same parameter names (`sigmoid_beta`, `network.pts_linears.{i}.*`,
+`network.views_linears.*`, `network.rgb_linear.*`, `network.sigma_linear.*` -- reference checkpoints load
+with strict=True), same forward signature and return tuple.  `Generator.renderer = NerfBranch.from_reference(
+G.renderer)` is the whole integration.
+
+There is no PyTorch fallback: CPU tensors or a missing library raise.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _abi
+
+W = 256
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter containers with the reference names and init distributions
+# ---------------------------------------------------------------------------------------------
+class _Linear(nn.Module):
+    """LinearLayer parameters (volume_renderer.py:15-30). `kind`: 'style' (0.25*kaiming, a=0.2) or 'freq'."""
+
+    def __init__(self, in_dim, out_dim, kind):
+        super().__init__()
+        if kind == "freq":
+            lim = math.sqrt(6.0 / in_dim) / 25.0
+            w = torch.empty(out_dim, in_dim).uniform_(-lim, lim)
+        else:
+            w = 0.25 * nn.init.kaiming_normal_(torch.empty(out_dim, in_dim), a=0.2, mode="fan_in",
+                                               nonlinearity="leaky_relu")
+        self.weight = nn.Parameter(w)
+        lim = math.sqrt(1.0 / in_dim)
+        self.bias = nn.Parameter(torch.empty(out_dim).uniform_(-lim, lim))
+
+
+class _FiLM(nn.Module):
+    """FiLMSiren parameters (volume_renderer.py:39-67)."""
+
+    def __init__(self, in_ch, out_ch, style_dim, is_first=False):
+        super().__init__()
+        lim = 1.0 / 3.0 if is_first else math.sqrt(6.0 / in_ch) / 25.0
+        self.weight = nn.Parameter(torch.empty(out_ch, in_ch).uniform_(-lim, lim))
+        lim = math.sqrt(1.0 / in_ch)
+        self.bias = nn.Parameter(torch.empty(out_ch).uniform_(-lim, lim))
+        self.gamma = _Linear(style_dim, out_ch, "style")
+        self.beta = _Linear(style_dim, out_ch, "style")
+
+
+class _SirenParams(nn.Module):
+    """SirenGenerator parameters (volume_renderer.py:89-116)."""
+
+    def __init__(self, D, hidden, style_dim, input_ch, view_ch):
+        super().__init__()
+        self.pts_linears = nn.ModuleList(
+            [_FiLM(input_ch, hidden, style_dim, is_first=True)] +
+            [_FiLM(hidden, hidden, style_dim) for _ in range(D - 1)])
+        self.views_linears = _FiLM(view_ch + hidden, hidden, style_dim)
+        self.rgb_linear = _Linear(hidden, 3, "freq")
+        self.sigma_linear = _Linear(hidden, 1, "freq")
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# autograd bridge
+# ---------------------------------------------------------------------------------------------
+class _NerfFn(torch.autograd.Function):
+    """forward = c3d_nerf_forward, backward = c3d_nerf_backward (recomputes activations in-kernel)."""
+
+    @staticmethod
+    def forward(ctx, module, kind, meta, styles, a0, a1, a2, a3, near, far, *params):
+        # kind POINTS: a0..a3 = pts, rays_d, viewdirs, z_vals ; kind POSES: a0, a1, a2 = cam_poses, focal, ray_offset
+        outs = module._launch_forward(kind, meta, styles, a0, a1, a2, a3, near, far)
+        ctx.module, ctx.kind, ctx.meta = module, kind, meta
+        ctx.save_for_backward(styles, a0, a1, a2 if a2 is not None else styles.new_empty(0),
+                              a3 if a3 is not None else styles.new_empty(0), near, far)
+        ctx.has = (a2 is not None, a3 is not None)
+        ctx.mark_non_differentiable(outs[5]) if outs[5] is not None else None
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_feat, g_sdf, g_mask, g_xyz, g_z):
+        styles, a0, a1, a2, a3, near, far = ctx.saved_tensors
+        a2 = a2 if ctx.has[0] else None
+        a3 = a3 if ctx.has[1] else None
+        grads = ctx.module._launch_backward(ctx.kind, ctx.meta, styles, a0, a1, a2, a3, near, far,
+                                            g_rgb, g_feat, g_sdf, g_mask, g_xyz, ctx.needs_input_grad)
+        return (None, None, None) + grads
+
+
+class NerfBranch(nn.Module):
+    def __init__(self, N_layers_renderer, input_dim=3, hidden_dim=256, style_dim=256, view_dim=3, with_sdf=True,
+                 output_features=True, precision="bf16", **kwargs):
+        super().__init__()
+        if (input_dim, hidden_dim, style_dim, view_dim) != (3, W, W, 3) or not with_sdf or not output_features:
+            raise ValueError("NerfBranch supports input_dim=3, hidden_dim=256, style_dim=256, view_dim=3, "
+                             "with_sdf=True, output_features=True (the v10 configs)")
+        if not 1 <= N_layers_renderer <= _abi.MAX_LAYERS:
+            raise ValueError(f"N_layers_renderer must be in [1, {_abi.MAX_LAYERS}]")
+        self.N_layers_renderer = N_layers_renderer
+        self.input_dim, self.hidden_dim, self.style_dim, self.view_dim = input_dim, hidden_dim, style_dim, view_dim
+        self.with_sdf, self.output_features = with_sdf, output_features
+        self.precision = precision
+        self.sigmoid_beta = nn.Parameter(0.1 * torch.ones(1))
+        self.network = _SirenParams(N_layers_renderer, hidden_dim, style_dim, input_dim, view_dim)
+        self._cache = None          # (key, packed blob); never pickled / deep-copied
+
+    # -- construction helpers ------------------------------------------------------------------
+    @classmethod
+    def from_reference(cls, renderer, precision="bf16"):
+        """Build from a reference VolumeFeatureRenderer (or anything with the same state_dict)."""
+        m = cls(renderer.N_layers_renderer, precision=precision)
+        m.load_state_dict(renderer.state_dict(), strict=True)
+        p = next(renderer.parameters())
+        return m.to(p.device)
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d["_cache"] = None
+        return d
+
+    def extra_repr(self):
+        return f"N_layers_renderer={self.N_layers_renderer}, precision={self.precision}"
+
+    # -- packed weights -------------------------------------------------------------------------
+    def _ordered_params(self):
+        net = self.network
+        ps = []
+        for layer in list(net.pts_linears) + [net.views_linears]:
+            ps += [layer.weight, layer.bias, layer.gamma.weight, layer.gamma.bias, layer.beta.weight, layer.beta.bias]
+        ps += [net.rgb_linear.weight, net.rgb_linear.bias, net.sigma_linear.weight, net.sigma_linear.bias,
+               self.sigmoid_beta]
+        return ps
+
+    def packed_weights(self):
+        """Kernel-layout weight blob, rebuilt when any parameter changed (keyed on tensor versions)."""
+        ps = self._ordered_params()
+        dev = ps[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("NerfBranch parameters must live on a CUDA device (no CPU path)")
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._cache is not None and self._cache[0] == key:
+            return self._cache[1]
+        lib = _abi.load()
+        D = self.N_layers_renderer
+        keep = [_f32c(p) for p in ps]
+        raw = _abi.RawParams()
+        raw.D = D
+        it = iter(keep)
+        for l in range(D + 1):
+            w, b, gw, gb, bw, bb = (next(it) for _ in range(6))
+            if l < D:
+                raw.pts_weight[l], raw.pts_bias[l] = w.data_ptr(), b.data_ptr()
+                raw.pts_gamma_weight[l], raw.pts_gamma_bias[l] = gw.data_ptr(), gb.data_ptr()
+                raw.pts_beta_weight[l], raw.pts_beta_bias[l] = bw.data_ptr(), bb.data_ptr()
+            else:
+                raw.views_weight, raw.views_bias = w.data_ptr(), b.data_ptr()
+                raw.views_gamma_weight, raw.views_gamma_bias = gw.data_ptr(), gb.data_ptr()
+                raw.views_beta_weight, raw.views_beta_bias = bw.data_ptr(), bb.data_ptr()
+        rw, rb, sw, sb, sbeta = (next(it) for _ in range(5))
+        raw.rgb_weight, raw.rgb_bias = rw.data_ptr(), rb.data_ptr()
+        raw.sigma_weight, raw.sigma_bias, raw.sigmoid_beta = sw.data_ptr(), sb.data_ptr(), sbeta.data_ptr()
+        nbytes = lib.c3d_packed_bytes(D)
+        blob = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _abi.check(lib.c3d_pack_weights(raw, _abi.ptr(blob), nbytes, torch.cuda.current_stream().cuda_stream),
+                       "c3d_pack_weights")
+        self._cache = (key, blob, keep)
+        return blob
+
+    # -- launches ---------------------------------------------------------------------------------
+    def _mode(self):
+        if self.precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        return _abi.MODE_BF16 if self.precision == "bf16" else _abi.MODE_FP32
+
+    def _fill_common(self, P, kind, meta, styles, a0, a1, a2, a3, near, far):
+        b, n_rays, N, img_size, static_viewdirs, nchw = meta
+        P.abi_version = _abi.ABI_VERSION
+        P.mode = self._mode()
+        P.input_kind = kind
+        P.feat_layout = _abi.FEAT_NCHW if nchw else _abi.FEAT_NHWC
+        P.batch, P.n_rays, P.n_samples, P.D = b, n_rays, N, self.N_layers_renderer
+        P.img_size, P.static_viewdirs = img_size, int(static_viewdirs)
+        P.packed = self.packed_weights().data_ptr()
+        P.styles, P.near, P.far = styles.data_ptr(), near.data_ptr(), far.data_ptr()
+        if kind == _abi.INPUT_POINTS:
+            P.pts, P.rays_d, P.viewdirs, P.z_vals = a0.data_ptr(), a1.data_ptr(), a2.data_ptr(), a3.data_ptr()
+        else:
+            P.cam_poses, P.focal = a0.data_ptr(), a1.data_ptr()
+            P.ray_offset = a2.data_ptr() if a2 is not None else None
+
+    def _launch_forward(self, kind, meta, styles, a0, a1, a2, a3, near, far):
+        lib = _abi.load()
+        b, n_rays, N, img_size, static_viewdirs, nchw = meta
+        dev = styles.device
+        f = dict(dtype=torch.float32, device=dev)
+        rgb_map = torch.empty(b, n_rays, 3, **f)
+        feat = torch.empty((b, W, n_rays) if nchw else (b, n_rays, W), **f)
+        sdf = torch.empty(b, n_rays, N, 1, **f)
+        mask = torch.empty(b, n_rays, 2, **f)
+        xyz = torch.empty(b, n_rays, 3, **f)
+        z_out = torch.empty(b, n_rays, N, **f) if kind == _abi.INPUT_POSES else None
+        P = _abi.FwdParams()
+        self._fill_common(P, kind, meta, styles, a0, a1, a2, a3, near, far)
+        P.rgb_map, P.feature_map, P.sdf, P.mask, P.xyz = (t.data_ptr() for t in (rgb_map, feat, sdf, mask, xyz))
+        P.z_vals_out = z_out.data_ptr() if z_out is not None else None
+        nws = lib.c3d_workspace_bytes(P)
+        ws = torch.empty(max(nws, 16), dtype=torch.uint8, device=dev)
+        P.workspace, P.workspace_bytes = ws.data_ptr(), nws
+        with torch.cuda.device(dev):
+            _abi.check(lib.c3d_nerf_forward(P, torch.cuda.current_stream().cuda_stream), "c3d_nerf_forward")
+        self.last_launch_count = lib.c3d_last_launch_count()
+        return rgb_map, feat, sdf, mask, xyz, z_out
+
+    def _launch_backward(self, kind, meta, styles, a0, a1, a2, a3, near, far, g_rgb, g_feat, g_sdf, g_mask, g_xyz,
+                         needs):
+        lib = _abi.load()
+        dev = styles.device
+        B = _abi.BwdParams()
+        self._fill_common(B.fwd, kind, meta, styles, a0, a1, a2, a3, near, far)
+        cot = [None if g is None else g.to(torch.float32).contiguous() for g in (g_rgb, g_feat, g_mask, g_xyz, g_sdf)]
+        B.g_rgb_map, B.g_feature_map, B.g_mask, B.g_xyz, B.g_sdf = (None if g is None else g.data_ptr() for g in cot)
+        # needs_input_grad indices: module, kind, meta, styles, a0, a1, a2, a3, near, far, *params
+        g_styles = torch.zeros_like(styles) if needs[3] else None
+        g_a0 = torch.zeros_like(a0) if needs[4] else None
+        g_a1 = torch.zeros_like(a1) if needs[5] else None
+        g_a2 = torch.zeros_like(a2) if (a2 is not None and needs[6] and kind == _abi.INPUT_POINTS) else None
+        B.g_styles = None if g_styles is None else g_styles.data_ptr()
+        if kind == _abi.INPUT_POINTS:
+            B.g_pts = None if g_a0 is None else g_a0.data_ptr()
+            B.g_rays_d = None if g_a1 is None else g_a1.data_ptr()
+            B.g_viewdirs = None if g_a2 is None else g_a2.data_ptr()
+        else:
+            B.g_cam_poses = None if g_a0 is None else g_a0.data_ptr()
+            B.g_focal = None if g_a1 is None else g_a1.data_ptr()
+        n_param = len(needs) - 10
+        g_packed = None
+        if any(needs[10:]):
+            raise NotImplementedError("gradients w.r.t. renderer weights are not provided by libc3dpp "
+                                      "(inversion optimises latents/cameras; call requires_grad_(False))")
+        nws = lib.c3d_backward_workspace_bytes(B)
+        ws = torch.empty(max(nws, 16), dtype=torch.uint8, device=dev)
+        B.fwd.workspace, B.fwd.workspace_bytes = ws.data_ptr(), nws
+        with torch.cuda.device(dev):
+            _abi.check(lib.c3d_nerf_backward(B, torch.cuda.current_stream().cuda_stream), "c3d_nerf_backward")
+        return (g_styles, g_a0, g_a1, g_a2, None, None, None) + (None,) * n_param
+
+    def _run(self, kind, meta, styles, a0, a1, a2, a3, near, far):
+        tensors = [styles, a0, a1, near, far] + [t for t in (a2, a3) if t is not None]
+        for t in tensors:
+            if t.device.type != "cuda":
+                raise RuntimeError("NerfBranch needs CUDA tensors: there is no CPU fallback")
+        need_grad = torch.is_grad_enabled() and (
+            any(t.requires_grad for t in tensors) or any(p.requires_grad for p in self.parameters()))
+        if not need_grad:
+            return self._launch_forward(kind, meta, styles, a0, a1, a2, a3, near, far)
+        params = [p for p in self._ordered_params()]
+        return _NerfFn.apply(self, kind, meta, styles, a0, a1, a2, a3, near, far, *params)
+
+    # -- public API -----------------------------------------------------------------------------
+    def forward(self, pts, rays_d, viewdirs, z_vals, near, far, styles=None, return_eikonal=False,
+                N_samples_forward=None):
+        """VolumeFeatureRenderer.forward (volume_renderer.py:192-283).
+
+        pts (b,hw,N,3) or (b,h,w,N,3); rays_d, viewdirs (b,hw,3); z_vals (b,hw,N); near, far (b,1,1);
+        styles (b,D+1,256).  Returns (rgb_map, feature_map, sdf, mask, xyz, eikonal_term=None).
+        `N_samples_forward` (ray chunking to bound the unfused path's memory) is accepted and ignored:
+        the fused kernel keeps per-point activations on chip.
+        """
+        if return_eikonal:
+            raise NotImplementedError("return_eikonal=True (training-time double backward) is outside the "
+                                      "inference/inversion hot path this library covers")
+        if styles is None:
+            raise ValueError("styles is required")
+        lead = pts.shape[:-2]
+        b, N = pts.shape[0], pts.shape[-2]
+        n_rays = int(math.prod(lead[1:]))
+        c = lambda t, *s: t.to(torch.float32).reshape(*s).contiguous()
+        meta = (b, n_rays, N, 0, False, False)
+        rgb_map, feat, sdf, mask, xyz, _ = self._run(
+            _abi.INPUT_POINTS, meta, c(styles, b, self.N_layers_renderer + 1, W), c(pts, b, n_rays, N, 3),
+            c(rays_d, b, n_rays, 3), c(viewdirs, b, n_rays, 3), c(z_vals, b, n_rays, N), c(near, b), c(far, b))
+        if len(lead) > 2:
+            rgb_map, feat, mask, xyz = (t.reshape(*lead, t.shape[-1]) for t in (rgb_map, feat, mask, xyz))
+            sdf = sdf.reshape(*lead, N, 1)
+        return rgb_map, feat, sdf, mask, xyz, None
+
+    def render(self, cam_poses, focal, near, far, styles, img_size=64, N_samples=24, static_viewdirs=False,
+               perturb=False, ray_offset=None, features_nchw=False):
+        """Fused fast path = Render.prepare_nerf_inputs (nerf_utils.py:172-218) + forward, rays generated
+        in-kernel.  cam_poses (b,3,4), focal/near/far (b,1,1) or (b,).  Returns a dict of maps; `z_vals`
+        are the sample depths the kernel used."""
+        b = cam_poses.shape[0]
+        n_rays = img_size * img_size
+        c = lambda t, *s: t.to(torch.float32).reshape(*s).contiguous()
+        if perturb and ray_offset is None:
+            ray_offset = torch.rand(b, img_size, img_size, 1, device=cam_poses.device)   # nerf_utils.py:110
+        ro = None if ray_offset is None else c(ray_offset, b, n_rays)
+        meta = (b, n_rays, N_samples, img_size, bool(static_viewdirs), bool(features_nchw))
+        rgb_map, feat, sdf, mask, xyz, z = self._run(
+            _abi.INPUT_POSES, meta, c(styles, b, self.N_layers_renderer + 1, W), c(cam_poses, b, 3, 4), c(focal, b),
+            ro, None, c(near, b), c(far, b))
+        return dict(rgb_map=rgb_map, feature_map=feat, sdf=sdf, mask=mask, xyz=xyz, z_vals=z)
+
+    def mlp_init_pass(self, *args, **kwargs):
+        raise NotImplementedError("mlp_init_pass (sphere-init pre-training, volume_renderer.py:569-634) is "
+                                  "training-only and outside this library's scope")

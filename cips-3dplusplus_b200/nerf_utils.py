@@ -1,0 +1,142 @@
+"""Host-side mirrors of the reference's static helpers `nerf_utils.Render` / `nerf_utils.Camera`
+(exp/cips3d/nerf_utils.py) so callers that use them directly keep working on the new path.
+
+* `Render.prepare_nerf_inputs`      -> c3d_raygen (CUDA)
+* `Render.volume_integration`       -> c3d_composite_forward (CUDA)
+* `Camera.generate_camera_params` stays PyTorch glue on purpose: it is ~30 scalar ops per image and must
+  remain differentiable w.r.t. azimuth/elevation for flip inversion (projector_v9.py:209).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import _abi
+
+
+def _c(t, *shape):
+    return t.to(torch.float32).reshape(*shape).contiguous()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Render:
+    @staticmethod
+    def prepare_nerf_inputs(focal, img_size, cam_poses, near, far, N_samples, perturb, static_viewdirs=False,
+                            **kwargs):
+        """nerf_utils.py:172-218 -> pts (b,h,w,N,3), rays_d (b,h,w,3), viewdirs (b,h,w,3), z_vals (b,h,w,N)."""
+        if cam_poses.device.type != "cuda":
+            raise RuntimeError("Render.prepare_nerf_inputs needs CUDA tensors (no CPU fallback)")
+        lib = _abi.load()
+        b, S, N, dev = cam_poses.shape[0], int(img_size), int(N_samples), cam_poses.device
+        f = dict(dtype=torch.float32, device=dev)
+        pts = torch.empty(b, S, S, N, 3, **f)
+        rays_d = torch.empty(b, S, S, 3, **f)
+        viewdirs = torch.empty(b, S, S, 3, **f)
+        z_vals = torch.empty(b, S, S, N, **f)
+        off = _c(torch.rand(b, S, S, 1, device=dev), b, S * S) if perturb else None     # nerf_utils.py:110
+        keep = [_c(cam_poses, b, 3, 4), _c(focal, b), _c(near, b), _c(far, b)]
+        P = _abi.RaygenParams()
+        P.batch, P.img_size, P.n_samples, P.static_viewdirs = b, S, N, int(bool(static_viewdirs))
+        P.cam_poses, P.focal, P.near, P.far = (t.data_ptr() for t in keep)
+        P.ray_offset = None if off is None else off.data_ptr()
+        P.pts, P.rays_d, P.viewdirs, P.z_vals = pts.data_ptr(), rays_d.data_ptr(), viewdirs.data_ptr(), z_vals.data_ptr()
+        with torch.cuda.device(dev):
+            _abi.check(lib.c3d_raygen(P, _stream()), "c3d_raygen")
+        return pts, rays_d, viewdirs, z_vals
+
+    @staticmethod
+    def normalize_points(pts, near, far):
+        """nerf_utils.py:123-133 (one multiply; kept as a torch op because callers pass autograd tensors)."""
+        shape = [-1] + [1] * (pts.dim() - 1)
+        return pts * 2 / (far - near).view(*shape)
+
+    @staticmethod
+    def volume_integration(rgb, sdf, features, z_vals, rays_d, pts, with_sdf=True, sigmoid_beta=None,
+                           return_eikonal=False, raw_noise_std=0.0, force_background=False):
+        """nerf_utils.py:230-338 -> rgb_map, feature_map, xyz, mask, eikonal_term(None)."""
+        if not with_sdf or return_eikonal or raw_noise_std > 0 or force_background:
+            raise NotImplementedError("only the with_sdf=True inference branch used by the v10 configs is provided")
+        if rgb.device.type != "cuda":
+            raise RuntimeError("Render.volume_integration needs CUDA tensors (no CPU fallback)")
+        lib = _abi.load()
+        lead, N, dev = rgb.shape[:-2], rgb.shape[-2], rgb.device
+        R = int(math.prod(lead))
+        f = dict(dtype=torch.float32, device=dev)
+        C = 0 if features is None else features.shape[-1]
+        keep = [_c(rgb, R, N, 3), _c(sdf, R, N), _c(z_vals, R, N), _c(rays_d, R, 3), _c(pts, R, N, 3)]
+        feats = None if features is None else _c(features, R, N, C)
+        rgb_map, xyz, mask = torch.empty(R, 3, **f), torch.empty(R, 3, **f), torch.empty(R, 2, **f)
+        feature_map = None if features is None else torch.empty(R, C, **f)
+        P = _abi.CompositeParams()
+        P.n_rays, P.n_samples, P.n_feat = R, N, C
+        if torch.is_tensor(sigmoid_beta):
+            sb = _c(sigmoid_beta, 1)
+            keep.append(sb)
+            P.sigmoid_beta_ptr = sb.data_ptr()
+        else:
+            P.sigmoid_beta = float(sigmoid_beta)
+        P.rgb, P.sdf, P.z_vals, P.rays_d, P.pts = (t.data_ptr() for t in keep[:5])
+        P.features = None if feats is None else feats.data_ptr()
+        P.rgb_map, P.xyz, P.mask = rgb_map.data_ptr(), xyz.data_ptr(), mask.data_ptr()
+        P.feature_map = None if feature_map is None else feature_map.data_ptr()
+        with torch.cuda.device(dev):
+            _abi.check(lib.c3d_composite_forward(P, _stream()), "c3d_composite_forward")
+        rs = lambda t: None if t is None else t.reshape(*lead, t.shape[-1])
+        return rs(rgb_map), rs(feature_map), rs(xyz), rs(mask), None
+
+
+class Camera:
+    @staticmethod
+    def generate_camera_params(img_size, device, batch=1, locations=None, sweep=False, uniform=False,
+                               azim_range=0.3, elev_range=0.15, fov_ang=6, dist_radius=0.12):
+        """nerf_utils.py:343-436: camera on the unit sphere looking at the origin.
+
+        Returns extrinsics (b,3,4), focal (b,1,1), near (b,1,1), far (b,1,1), viewpoint (b,2).
+        """
+        def rng(r):
+            return (r[0], r[1]) if isinstance(r, (list, tuple)) else (-r, r)
+
+        if locations is not None:
+            azim, elev = locations[:, 0:1], locations[:, 1:2]
+            n = azim.shape[0]
+        elif sweep:
+            (a0, a1), (e0, e1) = rng(azim_range), rng(elev_range)
+            azim = (a0 + (a1 - a0) / 7 * torch.arange(8, device=device)).view(-1, 1).repeat(batch, 1)
+            elev = e0 + (e1 - e0) * torch.rand(batch, 1, device=device).repeat(1, 8).view(-1, 1)
+            n = batch * 8
+        else:
+            if uniform:
+                (a0, a1), (e0, e1) = rng(azim_range), rng(elev_range)
+                azim = a0 + (a1 - a0) * torch.rand(batch, 1, device=device)
+                elev = e0 + (e1 - e0) * torch.rand(batch, 1, device=device)
+            else:
+                azim = azim_range * torch.randn(batch, 1, device=device)
+                elev = elev_range * torch.randn(batch, 1, device=device)
+            n = batch
+        dist = torch.ones(n, 1, device=device)
+        near, far = (dist - dist_radius).unsqueeze(-1), (dist + dist_radius).unsqueeze(-1)
+        if torch.is_tensor(fov_ang):
+            fov = fov_ang.to(device).reshape(-1, 1) * torch.ones(n, 1, device=device)
+        else:
+            fov = fov_ang * torch.ones(n, 1, device=device)
+        focal = 0.5 * img_size / torch.tan(fov * math.pi / 180).unsqueeze(-1)
+        viewpoint = torch.cat([azim, elev], 1)
+
+        cam_dir = torch.stack([torch.cos(elev) * torch.sin(azim), torch.sin(elev), torch.cos(elev) * torch.cos(azim)],
+                              dim=1).view(-1, 3)
+        cam_loc = dist * cam_dir
+        up = torch.tensor([[0.0, 1.0, 0.0]], device=device) * torch.ones_like(dist)
+        z_ax = F.normalize(cam_dir, eps=1e-5)
+        x_ax = F.normalize(torch.cross(up, z_ax, dim=1), eps=1e-5)
+        y_ax = F.normalize(torch.cross(z_ax, x_ax, dim=1), eps=1e-5)
+        degenerate = torch.isclose(x_ax, torch.tensor(0.0, device=device), atol=5e-3).all(dim=1, keepdim=True)
+        if degenerate.any():
+            x_ax = torch.where(degenerate, F.normalize(torch.cross(y_ax, z_ax, dim=1), eps=1e-5), x_ax)
+        rot = torch.stack([x_ax, y_ax, z_ax], dim=2)              # columns are the camera axes
+        extrinsics = torch.cat([rot, cam_loc[:, :, None]], dim=-1)
+        return extrinsics, focal, near, far, viewpoint

@@ -1,0 +1,189 @@
+/* c3d_abi.h -- C ABI of libc3dpp.so: the B200-native NeRF branch of CIPS-3D++.
+ *
+ * The reference has NO native code / FFI on this path (it is ~60 ATen calls issued from
+ * Python); the entry points below replace these reference interfaces:
+ *
+ *   c3d_nerf_forward      VolumeFeatureRenderer.forward        exp/cips3d/volume_renderer.py:192-283
+ *                         (+ Render.prepare_nerf_inputs        exp/cips3d/nerf_utils.py:172-218 when
+ *                            input_kind == C3D_INPUT_POSES)
+ *   c3d_nerf_backward     autograd of the same forward (flip inversion, projector_v9.py:1143)
+ *   c3d_raygen            Render.prepare_nerf_inputs           exp/cips3d/nerf_utils.py:172-218
+ *   c3d_style_prep        FiLMSiren.gamma / .beta LinearLayers exp/cips3d/volume_renderer.py:66-67,77-81
+ *   c3d_composite_forward Render.volume_integration            exp/cips3d/nerf_utils.py:230-338
+ *   c3d_composite_backward autograd of volume_integration
+ *   c3d_pack_weights      (new) re-lays the reference state_dict (volume_renderer.py:107-115,183)
+ *                         into the kernel's packed blob; re-derivable from the fp32 state dict
+ *
+ * Conventions
+ *   - plain C, no C++ / torch types; every pointer is a DEVICE pointer to fp32 data unless noted
+ *   - ownership: all buffers (inputs, outputs, packed weights, workspace) are allocated and
+ *     owned by the caller; the library never allocates, frees or retains a pointer
+ *   - errors: 0 = success, negative = failure; text via c3d_last_error() (thread-local)
+ *   - streams: work is enqueued on the given CUDA stream; the library never synchronises
+ *   - alignment: all pointers 16-byte aligned; W (hidden width) is fixed at 256
+ */
+#ifndef C3D_ABI_H_
+#define C3D_ABI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C3D_ABI_VERSION 3
+#define C3D_MAX_LAYERS 16
+#define C3D_W 256
+
+typedef struct CUstream_st* c3d_stream_t; /* == cudaStream_t */
+
+enum { C3D_OK = 0, C3D_ERR_ARG = -1, C3D_ERR_CUDA = -2, C3D_ERR_UNSUPPORTED = -3 };
+enum { C3D_MODE_FP32 = 0, C3D_MODE_BF16 = 1 };          /* arithmetic of the point MLP */
+enum { C3D_INPUT_POSES = 0, C3D_INPUT_POINTS = 1 };
+enum { C3D_FEAT_NHWC = 0, C3D_FEAT_NCHW = 1 };          /* feature_map (b,hw,256) or (b,256,hw) */
+
+/* Reference state_dict tensors (names: SURVEY.md 3.4), fp32, contiguous, row-major (out,in). */
+typedef struct c3d_raw_params {
+  int32_t D;                                        /* N_layers_renderer, 1..C3D_MAX_LAYERS */
+  int32_t _pad;
+  const float* pts_weight[C3D_MAX_LAYERS];          /* [0]:(256,3)  [i>0]:(256,256) */
+  const float* pts_bias[C3D_MAX_LAYERS];            /* (256) */
+  const float* pts_gamma_weight[C3D_MAX_LAYERS];    /* (256,256) */
+  const float* pts_gamma_bias[C3D_MAX_LAYERS];      /* (256) */
+  const float* pts_beta_weight[C3D_MAX_LAYERS];     /* (256,256) */
+  const float* pts_beta_bias[C3D_MAX_LAYERS];       /* (256) */
+  const float* views_weight;                        /* (256,259) */
+  const float* views_bias;
+  const float* views_gamma_weight;
+  const float* views_gamma_bias;
+  const float* views_beta_weight;
+  const float* views_beta_bias;
+  const float* rgb_weight;                          /* (3,256) */
+  const float* rgb_bias;                            /* (3) */
+  const float* sigma_weight;                        /* (1,256) */
+  const float* sigma_bias;                          /* (1) */
+  const float* sigmoid_beta;                        /* (1) */
+} c3d_raw_params;
+
+typedef struct c3d_fwd_params {
+  int32_t abi_version;       /* C3D_ABI_VERSION */
+  int32_t mode;              /* C3D_MODE_* */
+  int32_t input_kind;        /* C3D_INPUT_* */
+  int32_t feat_layout;       /* C3D_FEAT_* */
+  int32_t batch;             /* images (latent, pose) pairs */
+  int32_t n_rays;            /* rays per image (hw; any count >= 1 for C3D_INPUT_POINTS) */
+  int32_t n_samples;         /* N, 2..256 */
+  int32_t D;                 /* must equal the packed blob's D */
+  int32_t img_size;          /* POSES: n_rays == img_size^2 */
+  int32_t static_viewdirs;   /* POSES: nerf_utils.py:58-61 */
+  const void* packed;        /* c3d_pack_weights output */
+  const float* styles;       /* (batch, D+1, 256) */
+  /* C3D_INPUT_POSES */
+  const float* cam_poses;    /* (batch,3,4) camera-to-world */
+  const float* focal;        /* (batch) */
+  const float* near;         /* (batch)  also used by C3D_INPUT_POINTS for normalisation */
+  const float* far;          /* (batch) */
+  const float* ray_offset;   /* NULL (eval) or (batch,n_rays) U[0,1) draws: perturb (nerf_utils.py:105-119) */
+  /* C3D_INPUT_POINTS (reference layouts, contiguous) */
+  const float* pts;          /* (batch,n_rays,N,3) world space */
+  const float* rays_d;       /* (batch,n_rays,3) */
+  const float* viewdirs;     /* (batch,n_rays,3) */
+  const float* z_vals;       /* (batch,n_rays,N) */
+  /* outputs */
+  float* rgb_map;            /* (batch,n_rays,3) */
+  float* feature_map;        /* (batch,n_rays,256) or (batch,256,n_rays) */
+  float* sdf;                /* (batch,n_rays,N)  [reference shape (b,hw,N,1)] */
+  float* mask;               /* (batch,n_rays,2): background weight, depth = -|xyz| */
+  float* xyz;                /* (batch,n_rays,3) */
+  float* z_vals_out;         /* optional (POSES): (batch,n_rays,N) sample depths, or NULL */
+  void* workspace;           /* >= c3d_workspace_bytes() */
+  size_t workspace_bytes;
+} c3d_fwd_params;
+
+/* Cotangents in, gradients out. Any gradient pointer may be NULL (not computed). */
+typedef struct c3d_bwd_params {
+  c3d_fwd_params fwd;        /* same inputs as the forward call (outputs unused; recomputed) */
+  const float* g_rgb_map;    /* (batch,n_rays,3) or NULL (= zero) */
+  const float* g_feature_map;/* layout as fwd.feat_layout, or NULL */
+  const float* g_mask;       /* (batch,n_rays,2) or NULL */
+  const float* g_xyz;        /* (batch,n_rays,3) or NULL */
+  const float* g_sdf;        /* (batch,n_rays,N) or NULL */
+  float* g_styles;           /* (batch,D+1,256) */
+  float* g_pts;              /* POINTS: (batch,n_rays,N,3) */
+  float* g_rays_d;           /* POINTS: (batch,n_rays,3) */
+  float* g_viewdirs;         /* POINTS: (batch,n_rays,3) */
+  float* g_cam_poses;        /* POSES: (batch,3,4) */
+  float* g_focal;            /* POSES: (batch) */
+  float* g_packed_fp32;      /* optional: gradients of the fp32 section of the packed blob, or NULL */
+} c3d_bwd_params;
+
+typedef struct c3d_raygen_params {
+  int32_t batch, img_size, n_samples, static_viewdirs;
+  const float* cam_poses;    /* (batch,3,4) */
+  const float* focal;        /* (batch) */
+  const float* near;         /* (batch) */
+  const float* far;          /* (batch) */
+  const float* ray_offset;   /* NULL or (batch,img_size^2) */
+  float* pts;                /* (batch,hw,N,3) */
+  float* rays_d;             /* (batch,hw,3) */
+  float* viewdirs;           /* (batch,hw,3) */
+  float* z_vals;             /* (batch,hw,N) */
+} c3d_raygen_params;
+
+typedef struct c3d_composite_params {
+  int64_t n_rays;            /* total rays (batch*hw) */
+  int32_t n_samples;
+  int32_t n_feat;            /* feature channels, multiple of 4, <= 256 (0: no features) */
+  float sigmoid_beta;        /* used when sigmoid_beta_ptr == NULL */
+  int32_t _pad;
+  const float* sigmoid_beta_ptr; /* device scalar or NULL */
+  const float* rgb;          /* (n_rays,N,3) raw rgb head output */
+  const float* sdf;          /* (n_rays,N) */
+  const float* features;     /* (n_rays,N,n_feat) or NULL */
+  const float* z_vals;       /* (n_rays,N) */
+  const float* rays_d;       /* (n_rays,3) */
+  const float* pts;          /* (n_rays,N,3) */
+  float* rgb_map;            /* (n_rays,3) */
+  float* feature_map;        /* (n_rays,n_feat) */
+  float* xyz;                /* (n_rays,3) */
+  float* mask;               /* (n_rays,2) */
+  float* weights;            /* optional (n_rays,N) or NULL */
+  /* backward only */
+  const float* g_rgb_map; const float* g_feature_map; const float* g_xyz; const float* g_mask;
+  float* g_rgb; float* g_sdf; float* g_features; float* g_pts; float* g_rays_d; float* g_sigmoid_beta;
+} c3d_composite_params;
+
+int c3d_abi_version(void);
+const char* c3d_last_error(void);
+
+size_t c3d_packed_bytes(int32_t D);
+int c3d_pack_weights(const c3d_raw_params* raw, void* packed, size_t packed_bytes, c3d_stream_t stream);
+
+size_t c3d_workspace_bytes(const c3d_fwd_params* p);
+int c3d_nerf_forward(const c3d_fwd_params* p, c3d_stream_t stream);
+
+size_t c3d_backward_workspace_bytes(const c3d_bwd_params* p);
+int c3d_nerf_backward(const c3d_bwd_params* p, c3d_stream_t stream);
+
+int c3d_raygen(const c3d_raygen_params* p, c3d_stream_t stream);
+/* film: (batch, D+1, 256, 2) = (gamma, gamma*bias+beta); first: (batch,256,4); view: (batch,256,4) */
+int c3d_style_prep(const void* packed, int32_t D, const float* styles, int32_t batch, float* film, float* first,
+                   float* view, c3d_stream_t stream);
+int c3d_composite_forward(const c3d_composite_params* p, c3d_stream_t stream);
+int c3d_composite_backward(const c3d_composite_params* p, c3d_stream_t stream);
+
+/* Launch statistics of the most recent c3d_nerf_forward on this thread (kernel launches it made). */
+int c3d_last_launch_count(void);
+
+/* Self-test hook: one 128x{N}x{K} tcgen05 tile product through the library's own shared-memory
+ * layouts; a: (128,K) bf16 bits row-major, b: (N,K) bf16 bits row-major, d: (128,N) fp32.
+ * variant selects the operand roles exercised by the fused kernel (0: layer tile, 1: transposed
+ * view-layer tile, 2: rgb-head tile). */
+int c3d_umma_selftest(const uint16_t* a, const uint16_t* b, float* d, int32_t N, int32_t K,
+                      int32_t variant, c3d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C3D_ABI_H_ */

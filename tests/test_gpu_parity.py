@@ -1,0 +1,239 @@
+"""GPU parity tests (run on the B200 box): every call goes through the C ABI of libc3dpp.so and is checked
+against the CPU oracle (oracle/nerf_oracle.py) and the committed reference vectors (tests/golden).
+
+Tolerances (BASELINE.json north_star / SURVEY.md 8d):
+  fp32 mode: depths (z_vals, mask[...,1]) max-abs <= 1e-4; rgb/feature/xyz/sdf rel-L2 <= 1e-3
+  bf16 mode: rel-L2 <= 2e-2 on rgb_map and feature_map
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import CASES, load_case, load_weights, rel_l2
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_REL, BF16_REL, DEPTH_ABS = 1e-3, 2e-2, 1e-4
+
+
+def _dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _module(D, precision, sigmoid_beta=None):
+    import cips3dpp_b200 as c3d
+    m = c3d.NerfBranch(D, precision=precision)
+    sd = {k: torch.from_numpy(v) for k, v in load_weights(D).items()}
+    if sigmoid_beta is not None:
+        sd["sigmoid_beta"] = torch.from_numpy(np.asarray(sigmoid_beta, np.float32).reshape(1))
+    m.load_state_dict(sd, strict=True)
+    return m.to(_dev()).eval().requires_grad_(False)
+
+
+def _t(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(_dev())
+
+
+# ------------------------------------------------------------------------------------------------
+def test_library_loaded_is_in_tree():
+    import cips3dpp_b200 as c3d
+    lib = c3d._abi.load()
+    assert lib.c3d_abi_version() == c3d._abi.ABI_VERSION
+    assert os.path.dirname(c3d._abi.LIB_PATH).endswith("cips-3dplusplus_b200")
+
+
+@pytest.mark.parametrize("N,K", [(256, 256), (128, 256), (16, 256), (256, 64), (64, 128)])
+def test_umma_tile_product(N, K):
+    """tcgen05 descriptors / swizzled layouts of the fused kernel against an exact integer-valued product."""
+    import cips3dpp_b200 as c3d
+    lib = c3d._abi.load()
+    rng = np.random.default_rng(N * 1000 + K)
+    a = rng.integers(-4, 5, size=(128, K)).astype(np.float32)
+    b = rng.integers(-4, 5, size=(N, K)).astype(np.float32)
+    ta = _t(a).to(torch.bfloat16).view(torch.int16)
+    tb = _t(b).to(torch.bfloat16).view(torch.int16)
+    d = torch.full((128, N), float("nan"), device=_dev())
+    c3d._abi.check(lib.c3d_umma_selftest(ta.data_ptr(), tb.data_ptr(), d.data_ptr(), N, K, 0,
+                                         torch.cuda.current_stream().cuda_stream), "c3d_umma_selftest")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d.cpu().numpy(), a @ b.T)      # small integers: exact in bf16 x bf16 -> fp32
+
+
+def test_style_prep_matches_oracle():
+    import cips3dpp_b200 as c3d
+    lib = c3d._abi.load()
+    D, b = 6, 11
+    m = _module(D, "fp32")
+    params = load_weights(D)
+    rng = np.random.default_rng(3)
+    styles = (0.6 * rng.standard_normal((b, D + 1, 256))).astype(np.float32)
+    film = torch.empty(b, D + 1, 256, 2, device=_dev())
+    first = torch.empty(b, 256, 4, device=_dev())
+    view = torch.empty(b, 256, 4, device=_dev())
+    c3d._abi.check(lib.c3d_style_prep(m.packed_weights().data_ptr(), D, _t(styles).data_ptr(), b, film.data_ptr(),
+                                      first.data_ptr(), view.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                   "c3d_style_prep")
+    film, first, view = film.cpu().numpy(), first.cpu().numpy(), view.cpu().numpy()
+    for l in range(D + 1):
+        pre = f"network.pts_linears.{l}." if l < D else "network.views_linears."
+        p = {k[len(pre):]: v for k, v in params.items() if k.startswith(pre)}
+        gamma, beta = O.film_params(styles[:, l], p)
+        np.testing.assert_allclose(film[:, l, :, 0], gamma, rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(film[:, l, :, 1], gamma * p["bias"] + beta, rtol=2e-5, atol=2e-4)
+        if l == 0:
+            np.testing.assert_allclose(first[:, :, :3], gamma[:, :, None] * p["weight"][None], rtol=2e-5, atol=2e-5)
+        if l == D:
+            np.testing.assert_allclose(view[:, :, :3], gamma[:, :, None] * p["weight"][None, :, 256:], rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("static_viewdirs,perturb", [(False, False), (True, True)])
+def test_raygen_matches_oracle(static_viewdirs, perturb):
+    import cips3dpp_b200 as c3d
+    locs = np.array([[0.25, -0.1], [-0.3, 0.15], [3.0, 0.1]], np.float32)
+    c2w, focal, near, far, _ = O.generate_camera_params(locs, 64, 15, 0.3)
+    torch.manual_seed(5)
+    pts, rays_d, viewdirs, z_vals = c3d.Render.prepare_nerf_inputs(
+        focal=_t(focal), img_size=64, cam_poses=_t(c2w), near=_t(near), far=_t(far), N_samples=24,
+        perturb=perturb, static_viewdirs=static_viewdirs)
+    t_rand = None
+    if perturb:
+        torch.manual_seed(5)
+        t_rand = torch.rand(3, 64, 64, 1, device=_dev()).cpu().numpy()
+    o_pts, o_rd, o_vd, o_z = O.prepare_nerf_inputs(focal, 64, c2w, near, far, 24, t_rand, static_viewdirs)
+    assert np.abs(z_vals.cpu().numpy() - o_z).max() < 1e-6
+    assert np.abs(pts.cpu().numpy() - o_pts).max() < 2e-6
+    assert np.abs(rays_d.cpu().numpy() - o_rd).max() < 1e-6
+    assert np.abs(viewdirs.cpu().numpy() - o_vd).max() < 1e-6
+
+
+def test_camera_params_match_oracle():
+    import cips3dpp_b200 as c3d
+    locs = np.array([[0.0, 0.0], [0.25, -0.1], [3.14, 0.0], [0.0, 1.5707963]], np.float32)
+    out = c3d.Camera.generate_camera_params(64, _dev(), locations=_t(locs), fov_ang=15, dist_radius=0.3)
+    ref = O.generate_camera_params(locs, 64, 15, 0.3)
+    for a, b in zip(out, ref):
+        np.testing.assert_allclose(a.cpu().numpy(), b, atol=2e-6, rtol=1e-6)
+
+
+@pytest.mark.parametrize("R,N,C", [(1000, 24, 256), (37, 128, 256), (5, 200, 64), (64, 2, 0)])
+def test_composite_matches_oracle(R, N, C):
+    """Standalone volume_integration kernel (nerf_utils.py:230-338) on random inputs, ragged sizes."""
+    import cips3dpp_b200 as c3d
+    rng = np.random.default_rng(R + N)
+    rgb = rng.standard_normal((R, N, 3)).astype(np.float32)
+    sdf = (0.1 * rng.standard_normal((R, N, 1))).astype(np.float32)
+    feat = rng.standard_normal((R, N, C)).astype(np.float32) if C else None
+    z = np.sort(rng.uniform(0.88, 1.12, (R, N)).astype(np.float32), axis=-1)
+    rd = rng.standard_normal((R, 3)).astype(np.float32)
+    pts = rng.standard_normal((R, N, 3)).astype(np.float32)
+    out = c3d.Render.volume_integration(_t(rgb), _t(sdf), None if feat is None else _t(feat), _t(z), _t(rd), _t(pts),
+                                        sigmoid_beta=torch.tensor([0.1], device=_dev()))
+    o_rgb, o_feat, o_xyz, o_mask, _ = O.volume_integration(rgb, sdf, feat, z, rd, pts, np.float32(0.1))
+    assert rel_l2(out[0].cpu().numpy(), o_rgb) < 1e-5
+    if C:
+        assert rel_l2(out[1].cpu().numpy(), o_feat) < 1e-5
+    else:
+        assert out[1] is None
+    assert rel_l2(out[2].cpu().numpy(), o_xyz) < 1e-5
+    np.testing.assert_allclose(out[3].cpu().numpy(), o_mask, atol=2e-6, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+def _run_points(case, precision):
+    c = load_case(case)
+    m = _module(int(c["D"]), precision, c["sigmoid_beta"])
+    with torch.no_grad():
+        out = m(pts=_t(c["pts"]), rays_d=_t(c["rays_d"]), viewdirs=_t(c["viewdirs"]), z_vals=_t(c["z_vals"]),
+                near=_t(c["near"]), far=_t(c["far"]), styles=_t(c["styles"]))
+    torch.cuda.synchronize()
+    assert out[5] is None
+    return c, [o.cpu().numpy() for o in out[:5]], m
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_forward_fp32_matches_reference_golden(case):
+    c, (rgb_map, feat, sdf, mask, xyz), m = _run_points(case, "fp32")
+    assert sdf.shape == c["sdf"].shape and feat.shape == c["feature_map"].shape
+    assert rel_l2(feat, c["feature_map"]) < FP32_REL
+    assert rel_l2(rgb_map, c["rgb_map"]) < FP32_REL
+    assert rel_l2(sdf, c["sdf"]) < FP32_REL
+    assert rel_l2(xyz, c["xyz"]) < FP32_REL
+    assert np.abs(mask[..., 1] - c["mask"][..., 1]).max() < DEPTH_ABS
+    assert np.abs(mask[..., 0] - c["mask"][..., 0]).max() < 1e-3
+    assert m.last_launch_count >= 3
+
+
+@pytest.mark.parametrize("cluster", ["1", "2"])
+@pytest.mark.parametrize("case", CASES)
+def test_forward_bf16_matches_reference_golden(case, cluster, monkeypatch):
+    monkeypatch.setenv("C3D_CLUSTER", cluster)
+    c, (rgb_map, feat, sdf, mask, xyz), m = _run_points(case, "bf16")
+    errs = dict(feat=rel_l2(feat, c["feature_map"]), rgb=rel_l2(rgb_map, c["rgb_map"]), sdf=rel_l2(sdf, c["sdf"]),
+                xyz=rel_l2(xyz, c["xyz"]), depth=float(np.abs(mask[..., 1] - c["mask"][..., 1]).max()))
+    print(case, cluster, errs)
+    assert errs["feat"] < BF16_REL and errs["rgb"] < BF16_REL, errs
+    assert errs["xyz"] < BF16_REL and errs["sdf"] < 5e-2, errs
+    assert errs["depth"] < 2e-3, errs
+    assert m.last_launch_count == 2          # style_prep + the fused kernel
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", ["ffhq_d8_n24", "ffhq_d2_n128_static", "cars_d6_n24"])
+def test_render_from_poses_matches_reference_golden(case, precision):
+    """Fused entry (rays generated in-kernel) on the full 64x64 image, compared at the golden ray subset."""
+    c = load_case(case)
+    m = _module(int(c["D"]), precision, c["sigmoid_beta"])
+    with torch.no_grad():
+        out = m.render(_t(c["c2w"]), _t(c["focal"]), _t(c["near"]), _t(c["far"]), _t(c["styles"]), img_size=64,
+                       N_samples=int(c["N"]), static_viewdirs=bool(c["static_viewdirs"]))
+    idx = torch.from_numpy(c["ray_idx"].astype(np.int64)).to(_dev())
+    g = lambda k: out[k][:, idx].cpu().numpy()
+    assert np.abs(g("z_vals") - c["z_vals"]).max() < DEPTH_ABS
+    tol = FP32_REL if precision == "fp32" else BF16_REL
+    assert rel_l2(g("feature_map"), c["feature_map"]) < tol
+    assert rel_l2(g("rgb_map"), c["rgb_map"]) < tol
+    assert rel_l2(g("xyz"), c["xyz"]) < tol
+    assert np.abs(g("mask")[..., 1] - c["mask"][..., 1]).max() < (DEPTH_ABS if precision == "fp32" else 2e-3)
+
+
+def test_render_nchw_and_perturb_consistency():
+    """features_nchw is the transpose of the default layout; perturbed sampling equals POINTS mode fed with
+    the depths the kernel reports."""
+    import cips3dpp_b200 as c3d
+    c = load_case("ffhq_d2_n24")
+    m = _module(2, "fp32")
+    args = (_t(c["c2w"]), _t(c["focal"]), _t(c["near"]), _t(c["far"]), _t(c["styles"]))
+    with torch.no_grad():
+        a = m.render(*args, img_size=16, N_samples=24)
+        b = m.render(*args, img_size=16, N_samples=24, features_nchw=True)
+        torch.manual_seed(11)
+        p = m.render(*args, img_size=16, N_samples=24, perturb=True)
+        torch.manual_seed(11)
+        pts, rays_d, viewdirs, z_vals = c3d.Render.prepare_nerf_inputs(
+            focal=args[1], img_size=16, cam_poses=args[0], near=args[2], far=args[3], N_samples=24, perturb=True)
+        q = m(pts=pts.reshape(1, 256, 24, 3), rays_d=rays_d.reshape(1, 256, 3), viewdirs=viewdirs.reshape(1, 256, 3),
+              z_vals=z_vals.reshape(1, 256, 24), near=args[2], far=args[3], styles=args[4])
+    assert torch.equal(a["feature_map"].transpose(1, 2), b["feature_map"])
+    assert (p["z_vals"] - z_vals.reshape(1, 256, 24)).abs().max().item() < 1e-6
+    assert (p["z_vals"] - a["z_vals"]).abs().max().item() > 1e-4
+    assert rel_l2(p["feature_map"].cpu().numpy(), q[1].cpu().numpy()) < 1e-4
+
+
+def test_argument_errors_are_reported():
+    import cips3dpp_b200 as c3d
+    m = _module(2, "bf16")
+    c = load_case("ffhq_d2_n24")
+    with pytest.raises(RuntimeError):           # CPU tensors: no fallback
+        m(pts=torch.from_numpy(c["pts"]), rays_d=torch.from_numpy(c["rays_d"]), viewdirs=torch.from_numpy(c["viewdirs"]),
+          z_vals=torch.from_numpy(c["z_vals"]), near=torch.from_numpy(c["near"]), far=torch.from_numpy(c["far"]),
+          styles=torch.from_numpy(c["styles"]))
+    with pytest.raises(NotImplementedError):
+        m(pts=_t(c["pts"]), rays_d=_t(c["rays_d"]), viewdirs=_t(c["viewdirs"]), z_vals=_t(c["z_vals"]),
+          near=_t(c["near"]), far=_t(c["far"]), styles=_t(c["styles"]), return_eikonal=True)
+    with pytest.raises(c3d._abi.C3DError, match="n_samples"):      # bf16 path needs N >= 8
+        m(pts=_t(c["pts"][:, :, :4]), rays_d=_t(c["rays_d"]), viewdirs=_t(c["viewdirs"]), z_vals=_t(c["z_vals"][:, :, :4]),
+          near=_t(c["near"]), far=_t(c["far"]), styles=_t(c["styles"]))
