@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""Benchmark of the NeRF-branch hot path (BASELINE.json metric: rays/s & images/s at 64x64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c4|c1]
+
+One "step" = one pass of the hot path over one batch: BASELINE.json configs[1] -- FFHQ v10 NeRF branch
+(D=8, N=24 samples, 64x64 rays), 32 latents x 8-pose yaw sweep = 256 images, bf16, random-init weights,
+synthetic latents.  N>1: launched by torchrun, every rank renders its own 256 images (weak scaling, no
+data-path collective), time = max over ranks.
+
+Prints ONE JSON line (see the keys at the bottom).  `--impl reference` times the CPU restatement of the
+reference path (oracle/nerf_oracle.c, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (D, N, latents, poses/latent, cam cfg, description)
+    "c2": dict(D=8, N=24, latents=32, sweep=8, fov=6.0, radius=0.12, azim=0.3, elev=0.15,
+               desc="FFHQ v10 NeRF branch 64x64, D=8, N=24, 32 latents x 8-pose yaw sweep (BASELINE configs[1])"),
+    "c4": dict(D=6, N=24, latents=32, sweep=1, fov=15.0, radius=0.3, azim=3.14, elev=0.0837,
+               desc="CompCars v10 NeRF branch 64x64, D=6, N=24, batch 32 (BASELINE configs[3])"),
+    "c1": dict(D=8, N=24, latents=1, sweep=1, fov=6.0, radius=0.12, azim=0.0, elev=0.0,
+               desc="FFHQ v10 NeRF branch 64x64, D=8, N=24, batch 1 (BASELINE configs[0])"),
+}
+IMG = 64
+
+
+def workload(cfg, seed_latent=1, seed_pose=2):
+    """Synthetic inputs of the configured shape (numpy, host): poses, focal, near, far, styles."""
+    from oracle import nerf_oracle as O
+    rng_l, rng_p = np.random.default_rng(seed_latent), np.random.default_rng(seed_pose)
+    L, S = cfg["latents"], cfg["sweep"]
+    if S == 8:
+        locs = O.sweep_locations(L, cfg["azim"], cfg["elev"], rng_p.uniform(size=L))
+    else:
+        locs = np.stack([rng_p.uniform(-cfg["azim"], cfg["azim"], L * S),
+                         rng_p.uniform(-cfg["elev"], cfg["elev"], L * S)], 1).astype(np.float32)
+    c2w, focal, near, far, _ = O.generate_camera_params(locs, IMG, cfg["fov"], cfg["radius"])
+    w = (0.6 * rng_l.standard_normal((L, 1, 256))).astype(np.float32)           # one latent per identity
+    styles = np.repeat(np.repeat(w, cfg["D"] + 1, axis=1), S, axis=0)            # (L*S, D+1, 256)
+    return c2w, focal.reshape(-1), near.reshape(-1), far.reshape(-1), np.ascontiguousarray(styles)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as e:                                    # noqa: BLE001
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_baseline(cfg, n_images, reps=1):
+    """oracle/nerf_oracle.c (kind 'port': the reference path is Python, nothing to compile) on host cores."""
+    from oracle import c_oracle, nerf_oracle as O
+    c2w, focal, near, far, styles = workload(cfg)
+    params = O.init_params(cfg["D"], seed=0)
+    packed = c_oracle.pack_params(params)
+    sl = slice(0, n_images)
+    times = []
+    for _ in range(reps + 1):                                      # first pass = warm-up
+        t0 = time.perf_counter()
+        pts, rd, vd, z = c_oracle.prepare_inputs(c2w[sl], focal[sl], near[sl], far[sl], IMG, cfg["N"])
+        c_oracle.renderer_forward(params, pts, rd, vd, z, near[sl], far[sl], styles[sl], packed=packed)
+        times.append(time.perf_counter() - t0)
+    t = min(times[1:])
+    return dict(value=n_images * IMG * IMG / t, unit="rays/s", cores=c_oracle.num_threads(), kind="port",
+                sample=f"{n_images} of {c2w.shape[0]} images of the step ({t:.2f} s, best of {reps})",
+                images_per_s=n_images / t, host_cpus=os.cpu_count()), t
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    n_img = max(1, min(cfg["latents"] * cfg["sweep"], 4))
+    cb, _ = cpu_baseline(cfg, n_img, reps=1)                        # sizes the sample
+    times = []
+    from oracle import c_oracle, nerf_oracle as O
+    c2w, focal, near, far, styles = workload(cfg)
+    params = O.init_params(cfg["D"], seed=0)
+    packed = c_oracle.pack_params(params)
+    sl = slice(0, n_img)
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        pts, rd, vd, z = c_oracle.prepare_inputs(c2w[sl], focal[sl], near[sl], far[sl], IMG, cfg["N"])
+        c_oracle.renderer_forward(params, pts, rd, vd, z, near[sl], far[sl], styles[sl], packed=packed)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    t = float(np.mean(times))
+    v = n_img * IMG * IMG / t
+    cb.update(value=v, sample=f"each step = {n_img} of {c2w.shape[0]} images of the workload")
+    print(json.dumps({
+        "impl": "reference", "metric": "nerf_branch_rays_per_s", "value": v, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "images_per_s": n_img / t,
+        "config": {"workload": cfg["desc"], "sample_images_per_step": n_img, "img_size": IMG},
+        "cpu_baseline": cb,
+        "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import cips3dpp_b200 as c3d
+    from oracle import nerf_oracle as O
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    c3d._abi.load()
+
+    D, N = cfg["D"], cfg["N"]
+    params = O.init_params(D, seed=0)
+    m = c3d.NerfBranch(D, precision=args.precision)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    m = m.to(dev).eval().requires_grad_(False)
+    c2w, focal, near, far, styles = workload(cfg, seed_latent=1 + rank, seed_pose=2 + rank)
+    B = c2w.shape[0]
+    host = [torch.from_numpy(x).pin_memory() for x in (c2w, focal, near, far, styles)]
+    devt = [h.to(dev) for h in host]
+    m.packed_weights()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_resident():
+        return m.render(devt[0], devt[1], devt[2], devt[3], devt[4], img_size=IMG, N_samples=N)
+
+    out_host = {k: torch.empty(s, dtype=torch.float32).pin_memory()
+                for k, s in (("rgb_map", (B, IMG * IMG, 3)), ("mask", (B, IMG * IMG, 2)), ("xyz", (B, IMG * IMG, 3)))}
+
+    def step_e2e():
+        d = [h.to(dev, non_blocking=True) for h in host]
+        out = m.render(d[0], d[1], d[2], d[3], d[4], img_size=IMG, N_samples=N)
+        for k, hbuf in out_host.items():
+            hbuf.copy_(out[k], non_blocking=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        evs = []
+        barrier()
+        t_wall = time.perf_counter()
+        for _ in range(steps):
+            flush.fill_(1)                                            # L2 flush, outside the event pair
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            evs.append((e0, e1))
+        barrier()
+        wall = time.perf_counter() - t_wall
+        ms = [a.elapsed_time(b) for a, b in evs]
+        return float(np.mean(ms)), float(np.min(ms)), wall
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_step, ms_min, wall = timed(step_resident, args.steps, max(args.warmup, 3))
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    launches_per_step = m.last_launch_count
+    ms_e2e, _, _ = timed(step_e2e, args.steps, 2)
+
+    # the dominant kernel alone: step minus the (tiny) FiLM style_prep launch, measured live
+    film = torch.empty(B, D + 1, 256, 2, device=dev)
+    first = torch.empty(B, 256, 4, device=dev)
+    view = torch.empty(B, 256, 4, device=dev)
+    lib = c3d._abi.load()
+
+    def sp():
+        c3d._abi.check(lib.c3d_style_prep(m.packed_weights().data_ptr(), D, devt[4].data_ptr(), B, film.data_ptr(),
+                                          first.data_ptr(), view.data_ptr(), stream.cuda_stream), "c3d_style_prep")
+    ms_sp, _, _ = timed(sp, args.steps, 2)
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_step, ms_e2e, ms_sp_m = maxr(ms_step), maxr(ms_e2e), maxr(ms_sp)
+    rays_step = B * IMG * IMG
+    value = world * rays_step / (ms_step * 1e-3)
+    e2e_value = world * rays_step / (ms_e2e * 1e-3)
+
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured sustained (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md sustained)"
+    flops_launch = O.flops_per_point(D) * rays_step * N
+    ms_kernel = max(ms_step - ms_sp_m, 1e-6)
+    achieved = flops_launch / (ms_kernel * 1e-3) / 1e12
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tf):
+        traffic = json.load(open(tf)).get(f"{args.config}_{args.precision}")
+
+    if rank == 0:
+        line = {
+            "metric": "nerf_branch_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "images_per_s": world * B / (ms_step * 1e-3), "ms_per_step_min": ms_min,
+            "config": {"workload": cfg["desc"], "images_per_gpu": B, "rays_per_image": IMG * IMG, "samples_per_ray": N,
+                       "layers": D, "weights": "random-init (reference distributions)", "sampling": "eval (unperturbed)",
+                       "l2": "flushed (256 MiB write) between timed steps, outside the event pair",
+                       "d2h": "rgb_map+mask+xyz to pinned host (feature_map stays on device for the decoder)"},
+            "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(sum(h.numel() * 4 for h in host)),
+                    "d2h_bytes_per_step": int(sum(h.numel() * 4 for h in out_host.values()))},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tf, "traffic": traffic, "kernel": "fused_forward_kernel",
+                         "peak_source": peak_src, "kernel_ms": ms_kernel, "flops_per_launch": flops_launch,
+                         "frac_of_nominal_2250": achieved / 2250.0,
+                         "frac_of_burst": achieved / peaks.get("bf16_tflops", 1590.0)},
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _ = cpu_baseline(cfg, min(B, 8), reps=2)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
