@@ -7,6 +7,7 @@
 #include "kernels_aux.cuh"
 #include "mlp_fp32.cuh"
 #include "fused_bf16_sm100.cuh"
+#include "fused2_bf16_sm100.cuh"
 #include "backward.cuh"
 
 namespace c3d {
@@ -147,23 +148,23 @@ static int forward_bf16(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
   const char* genv = getenv("C3D_GRID");
   if (genv && atoi(genv) > 0) { grid = atoi(genv); if (cluster == 2) grid = (grid + 1) & ~1; }
 
+  const char* venv = getenv("C3D_FUSED");
+  const int version = (venv && atoi(venv) == 1) ? 1 : 2;     // 1: rows = points (first version, kept for A/B runs)
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(fused::NTHREADS);
-  cfg.dynamicSmemBytes = fused::SMEM_BYTES;
+  cfg.dynamicSmemBytes = version == 1 ? fused::SMEM_BYTES : fused2::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (cluster == 2) {
-    C3D_CUDA(cudaFuncSetAttribute(fused::fused_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::SMEM_BYTES));
-    C3D_CUDA(cudaLaunchKernelEx(&cfg, fused::fused_forward_kernel<2>, a));
-  } else {
-    C3D_CUDA(cudaFuncSetAttribute(fused::fused_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::SMEM_BYTES));
-    C3D_CUDA(cudaLaunchKernelEx(&cfg, fused::fused_forward_kernel<1>, a));
-  }
+  void (*kern)(const fused::Args) =
+      version == 1 ? (cluster == 2 ? fused::fused_forward_kernel<2> : fused::fused_forward_kernel<1>)
+                   : (cluster == 2 ? fused2::fused_forward_kernel<2> : fused2::fused_forward_kernel<1>);
+  C3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
+  C3D_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   C3D_LAUNCH_CHECK();
   return C3D_OK;
 }
@@ -320,13 +321,19 @@ int c3d_composite_forward(const c3d_composite_params* p, c3d_stream_t stream) {
 
 int c3d_umma_selftest(const uint16_t* a, const uint16_t* b, float* d, int32_t N, int32_t K, int32_t variant,
                       c3d_stream_t stream) {
-  (void)variant;
   C3D_CHECK_ARG(a && b && d, "NULL pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (K == 16) {       // layer-0 operand layout (K-major, no swizzle); variant 1 swaps LBO/SBO (diagnostic)
+    C3D_CHECK_ARG(N == 128, "K=16 self-test needs N=128 (got %d)", N);
+    fused2::umma_k16_selftest_kernel<<<1, 128, 0, st>>>(a, b, d, variant);
+    C3D_LAUNCH_CHECK();
+    return C3D_OK;
+  }
   C3D_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0, "N=%d must be a multiple of 16 in [16,256]", N);
-  C3D_CHECK_ARG(K >= 64 && K <= 256 && K % 64 == 0, "K=%d must be a multiple of 64 in [64,256]", K);
+  C3D_CHECK_ARG(K >= 64 && K <= 256 && K % 64 == 0, "K=%d must be 16 or a multiple of 64 in [64,256]", K);
   const int smem = fused::ACT_BYTES + N * 128 * (K / 64) + 1024;
   C3D_CUDA(cudaFuncSetAttribute(fused::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  fused::umma_selftest_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a, b, d, N, K);
+  fused::umma_selftest_kernel<<<1, 128, smem, st>>>(a, b, d, N, K);
   C3D_LAUNCH_CHECK();
   return C3D_OK;
 }

@@ -29,16 +29,22 @@ constexpr int NCHUNK = W / KCHUNK;  // 4 K-chunks per layer
 //   wT32     : per layer l in 1..D: WT[256 k][256 c] fp32 (view layer: columns 0..255 only)
 //   wbf16    : per layer l in 1..D: 4 K-chunks x [256 n][64 k] bf16, rows of 128 B, 16-byte units
 //              XOR-swizzled with (n & 7)  == UMMA K-major SWIZZLE_128B image of the smem stage
-//   rgb16    : 4 K-chunks x [16 n][64 k] bf16, same swizzle (rows 0..2 = Wrgb, rest zero)
+//   heads16  : 4 K-chunks x [16 n][64 k] bf16, same swizzle: rows 0..2 = Wrgb, row 4 / 5 = hi / lo bf16 split
+//              of sigma_linear.weight, other rows zero (one N=16 MMA serves the rgb and the sdf head)
+//   w0img    : [256 n][16 k] bf16, UMMA K-major no-swizzle (8x8 core matrices: 16 B per row, 128 B per K-block,
+//              256 B per 8 rows); layer-0 weights split for a K=16 tensor-core product that is exact to ~2^-17:
+//              per coordinate j, k-slots 5j..5j+4 = (hi, hi, hi, lo, lo) of W0[n][j]; the point tile carries
+//              (hi, mid, lo, hi, mid) of the normalised coordinate; slot 15 is zero
 // ------------------------------------------------------------------------------------------
 struct PackedLayout {
-  size_t w0, wvdir, bias, wsig, wrgb, scal, film, wT32, wbf16, rgb16, total;
+  size_t w0, wvdir, bias, wsig, wrgb, scal, film, wT32, wbf16, rgb16, w0img, total;
   int D;
 };
 constexpr size_t FILM_LAYER_FLOATS = 2 * (size_t)W * W + 2 * W;
 constexpr size_t WBF16_LAYER_BYTES = (size_t)W * W * 2;      // 131072
 constexpr size_t WBF16_CHUNK_BYTES = (size_t)W * KCHUNK * 2; // 32768
-constexpr size_t RGB16_BYTES = (size_t)16 * W * 2;           // 8192
+constexpr size_t RGB16_BYTES = (size_t)16 * W * 2;           // 8192 (heads16)
+constexpr size_t W0IMG_BYTES = (size_t)W * 16 * 2;           // 8192
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -57,6 +63,7 @@ __host__ __device__ inline PackedLayout packed_layout(int D) {
   o = align_up(o, 1024);
   L.wbf16 = o; o += WBF16_LAYER_BYTES * (size_t)D;
   L.rgb16 = o; o += RGB16_BYTES;
+  L.w0img = o; o += W0IMG_BYTES;
   L.total = align_up(o, 1024);
   return L;
 }
@@ -64,6 +71,11 @@ __host__ __device__ inline PackedLayout packed_layout(int D) {
 // byte offset of element (n, k) inside one K-chunk image with `rows` rows (UMMA K-major SW128)
 __host__ __device__ inline uint32_t sw128_offset(int n, int k /*0..63*/) {
   return (uint32_t)n * 128u + ((((uint32_t)k >> 3) ^ ((uint32_t)n & 7u)) << 4) + (((uint32_t)k & 7u) << 1);
+}
+
+// byte offset of element (r, k<16) of a K=16 operand in the UMMA K-major no-swizzle ("interleave") layout
+__host__ __device__ inline uint32_t k16_offset(int r, int k) {
+  return ((uint32_t)r >> 3) * 256u + ((uint32_t)k >> 3) * 128u + ((uint32_t)r & 7u) * 16u + ((uint32_t)k & 7u) * 2u;
 }
 
 // ------------------------------------------------------------------------------------------

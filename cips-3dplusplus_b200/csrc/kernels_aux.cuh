@@ -38,13 +38,25 @@ __global__ void pack_small_kernel(c3d_raw_params raw, uint8_t* __restrict__ blob
     f[2 * W * W + c] = gb[c];
     f[2 * W * W + W + c] = bb[c];
   }
-  // rgb head bf16 image: [16 n][64 k] x 4 chunks (rows >= 3 zero)
+  // heads16 bf16 image: [16 n][64 k] x 4 chunks; rows 0..2 rgb head, rows 4/5 = hi/lo split of the sdf head
   uint8_t* r16 = blob + L.rgb16;
+  const float ws = raw.sigma_weight[c];
+  const float ws_hi = __bfloat162float(__float2bfloat16_rn(ws));
   for (int n = 0; n < 16; ++n) {
-    float v = n < 3 ? raw.rgb_weight[n * W + c] : 0.f;
+    float v = n < 3 ? raw.rgb_weight[n * W + c] : (n == 4 ? ws_hi : (n == 5 ? ws - ws_hi : 0.f));
     const int ch = c >> 6, k = c & 63;
     *reinterpret_cast<__nv_bfloat16*>(r16 + (size_t)ch * (16 * 128) + sw128_offset(n, k)) = __float2bfloat16_rn(v);
   }
+  // layer-0 split image: row c, k-slots 5j..5j+4 = (hi, hi, hi, lo, lo) of W0[c][j]
+  uint8_t* w0i = blob + L.w0img;
+  for (int j = 0; j < 3; ++j) {
+    const float w = raw.pts_weight[0][c * 3 + j];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+    for (int q = 0; q < 5; ++q)
+      *reinterpret_cast<__nv_bfloat16*>(w0i + k16_offset(c, 5 * j + q)) = q < 3 ? hi : lo;
+  }
+  *reinterpret_cast<__nv_bfloat16*>(w0i + k16_offset(c, 15)) = __float2bfloat16_rn(0.f);
 }
 
 // grid (D+1 layers, 256/32 row tiles), block (32,8): transposes 32x32 tiles of the three 256x256

@@ -109,6 +109,16 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                              // layout type: SWIZZLE_128B
   return d;
 }
+// K-major operand with K = 16 in the no-swizzle ("interleave") layout: 8x8 core matrices of 128 B (8 rows x 16 B),
+// the two K-blocks of a row group 128 B apart (leading byte offset), 8-row groups 256 B apart (stride byte offset).
+__device__ __forceinline__ uint64_t umma_desc_kmajor_k16(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(128u >> 4) << 16;                    // leading byte offset: next K-block (8 elements)
+  d |= (uint64_t)(256u >> 4) << 32;                    // stride byte offset : next 8 rows
+  d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell); layout type 0 = no swizzle
+  return d;
+}
 // Instruction descriptor, kind::f16: BF16 x BF16 -> FP32, both operands K-major.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4)            // c_format  = F32

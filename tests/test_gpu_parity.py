@@ -63,6 +63,22 @@ def test_umma_tile_product(N, K):
     np.testing.assert_array_equal(d.cpu().numpy(), a @ b.T)      # small integers: exact in bf16 x bf16 -> fp32
 
 
+def test_umma_k16_operand_layout():
+    """K=16 no-swizzle operand layout used by the layer-0 split product (fused v2)."""
+    import cips3dpp_b200 as c3d
+    lib = c3d._abi.load()
+    rng = np.random.default_rng(16)
+    a = rng.integers(-4, 5, size=(128, 16)).astype(np.float32)
+    b = rng.integers(-4, 5, size=(128, 16)).astype(np.float32)
+    ta = _t(a).to(torch.bfloat16).view(torch.int16)
+    tb = _t(b).to(torch.bfloat16).view(torch.int16)
+    d = torch.full((128, 128), float("nan"), device=_dev())
+    c3d._abi.check(lib.c3d_umma_selftest(ta.data_ptr(), tb.data_ptr(), d.data_ptr(), 128, 16, 0,
+                                         torch.cuda.current_stream().cuda_stream), "c3d_umma_selftest")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d.cpu().numpy(), a @ b.T)
+
+
 def test_style_prep_matches_oracle():
     import cips3dpp_b200 as c3d
     lib = c3d._abi.load()
@@ -171,6 +187,7 @@ def test_forward_fp32_matches_reference_golden(case):
 @pytest.mark.parametrize("case", CASES)
 def test_forward_bf16_matches_reference_golden(case, cluster, monkeypatch):
     monkeypatch.setenv("C3D_CLUSTER", cluster)
+    monkeypatch.delenv("C3D_FUSED", raising=False)
     c, (rgb_map, feat, sdf, mask, xyz), m = _run_points(case, "bf16")
     errs = dict(feat=rel_l2(feat, c["feature_map"]), rgb=rel_l2(rgb_map, c["rgb_map"]), sdf=rel_l2(sdf, c["sdf"]),
                 xyz=rel_l2(xyz, c["xyz"]), depth=float(np.abs(mask[..., 1] - c["mask"][..., 1]).max()))
