@@ -133,6 +133,7 @@ static int forward_bf16(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
   a.pts = p->pts; a.rays_d = p->rays_d; a.viewdirs = p->viewdirs; a.z_vals = p->z_vals;
   a.rgb_map = p->rgb_map; a.feature_map = p->feature_map; a.sdf = p->sdf; a.mask = p->mask; a.xyz = p->xyz;
   a.z_vals_out = p->z_vals_out;
+  { const char* d = getenv("C3D_DEBUG"); a.debug = d ? atoi(d) : 0; }
 
   int dev = 0, nsm = 0;
   C3D_CUDA(cudaGetDevice(&dev));

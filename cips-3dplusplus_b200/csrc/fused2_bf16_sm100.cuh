@@ -56,6 +56,13 @@ struct Misc {
   float carry[2];
 };
 
+// bf16(x) -> 2-byte shared-memory store (F2FP + STS.U16, no repacking)
+__device__ __forceinline__ void st_bf16(uint32_t smem_addr, float x) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(x));
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(smem_addr), "h"((unsigned short)r) : "memory");
+}
+
 // packed weight-layer index streamed by job j of a tile (-1: the job uses resident operands only)
 __device__ __forceinline__ int job_layer(int j, int D) {
   if (j >= 1 && j <= D - 1) return j - 1;   // hidden layer l = j  -> wbf16[l-1]
@@ -119,6 +126,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_kernel(const Args a
           mbar_wait(&misc->empty[st], ph ^ 1u);
           uint8_t* dst = smem + SM_STAGE + st * STAGE_BYTES;
           const uint8_t* src = wsrc + (size_t)layer * WBF16_LAYER_BYTES + (size_t)c * WBF16_CHUNK_BYTES;
+          if (a.debug & 1) { mbar_arrive(&misc->full[st]); continue; }     // timing experiment: no weight traffic
           mbar_arrive_expect_tx(&misc->full[st], STAGE_BYTES);
           if (kCluster == 1) {
             bulk_g2s(dst, src, STAGE_BYTES, &misc->full[st]);
@@ -206,7 +214,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_kernel(const Args a
     uint32_t xoroff[8];
 #pragma unroll
     for (int jx = 0; jx < 8; ++jx) xoroff[jx] = (uint32_t)((((t & 63) >> 3) ^ jx) << 4) + (uint32_t)((t & 7) << 1);
-    uint8_t* abase[2] = {act + (t >> 6) * ACT_CHUNK, act + ((t + TILE) >> 6) * ACT_CHUNK};
+    const uint32_t abase_u32[2] = {smem_u32(act + (t >> 6) * ACT_CHUNK), smem_u32(act + ((t + TILE) >> 6) * ACT_CHUNK)};
     float cur[2] = {0.f, 0.f}, shift_ray[2] = {0.f, 0.f};
     uint32_t jobcnt = 0;
     const int total_units = a.batch * a.units_per_img;
@@ -282,23 +290,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_kernel(const Args a
           mbar_wait(&misc->acc_full[s], jobcnt & 1u);
           jobcnt++;
           tc_fence_after();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const float scale = h ? f1.x : f0.x, shift = h ? f1.y : f0.y;
-            uint8_t* ab = abase[h];
-            uint32_t v[2][32];
-            tmem_ld_32x32(tacc + h * 128, v[0]);
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
+          {
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32(tacc, v0);
+#pragma unroll 1
+            for (int hc = 0; hc < 4; ++hc) {               // 64 points of one channel half per iteration
+              const int h = hc >> 1, p0 = (hc & 1) * 64;
+              const float scale = h ? f1.x : f0.x, shift = h ? f1.y : f0.y;
+              const uint32_t ab = abase_u32[h] + (uint32_t)p0 * 128u;
               tmem_ld_wait();
-              if (cc + 1 < 4) tmem_ld_32x32(tacc + h * 128 + (cc + 1) * 32, v[(cc + 1) & 1]);
-              const uint32_t(&vv)[32] = v[cc & 1];
+              tmem_ld_32x32(tacc + h * 128 + p0 + 32, v1);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const int p = cc * 32 + i;
-                const float o = __sinf(fmaf(__uint_as_float(vv[i]), scale, shift));
-                *reinterpret_cast<__nv_bfloat16*>(ab + p * 128 + xoroff[p & 7]) = __float2bfloat16_rn(o);
-              }
+              for (int i = 0; i < 32; ++i)
+                st_bf16(ab + i * 128 + xoroff[i & 7], __sinf(fmaf(__uint_as_float(v0[i]), scale, shift)));
+              tmem_ld_wait();
+              if (hc < 3) tmem_ld_32x32(tacc + ((hc + 1) >> 1) * 128 + ((hc + 1) & 1) * 64, v0);
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                st_bf16(ab + (32 + i) * 128 + xoroff[i & 7], __sinf(fmaf(__uint_as_float(v1[i]), scale, shift)));
             }
           }
           tc_fence_before();
@@ -340,33 +349,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_kernel(const Args a
           mbar_wait(&misc->acc_full[s], jobcnt & 1u);
           jobcnt++;
           tc_fence_after();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const float scale = h ? f1.x : f0.x, shift0 = h ? f1.y : f0.y;
-            const float4 tv = h ? tv1 : tv0;
-            float cu = cur[h], sr = shift_ray[h];
-            float* fout = a.feature_map + ((size_t)img * a.n_rays + r0) * W + t + h * TILE;
-            uint8_t* ab = abase[h];
-            uint32_t v[2][32];
-            tmem_ld_32x32(tacc + h * 128, v[0]);
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
+          {
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32(tacc, v0);
+            float* const fbase = a.feature_map + ((size_t)img * a.n_rays + r0) * W + t;
+#pragma unroll 1
+            for (int hc = 0; hc < 4; ++hc) {
+              const int h = hc >> 1, p0 = (hc & 1) * 64;
+              const float scale = h ? f1.x : f0.x, shift0 = h ? f1.y : f0.y;
+              const float4 tv = h ? tv1 : tv0;
+              float cu = cur[h], sr = shift_ray[h];
+              float* fout = fbase + h * TILE;
+              const uint32_t ab = abase_u32[h] + (uint32_t)p0 * 128u;
               tmem_ld_wait();
-              if (cc + 1 < 4) tmem_ld_32x32(tacc + h * 128 + (cc + 1) * 32, v[(cc + 1) & 1]);
-              const uint32_t(&vv)[32] = v[cc & 1];
+              tmem_ld_32x32(tacc + h * 128 + p0 + 32, v1);
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                const int p = cc * 32 + i;
-                const float4 pw = ptS[p];
-                const int fl = flagS[p];
+                const float4 pw = ptS[p0 + i];
+                const int fl = flagS[p0 + i];
                 if (fl & 1) sr = fmaf(tv.x, pw.y, fmaf(tv.y, pw.z, fmaf(tv.z, pw.w, shift0)));
-                const float feat = __sinf(fmaf(__uint_as_float(vv[i]), scale, sr));
+                const float feat = __sinf(fmaf(__uint_as_float(v0[i]), scale, sr));
                 cu = fmaf(pw.x, feat, cu);
-                *reinterpret_cast<__nv_bfloat16*>(ab + p * 128 + xoroff[p & 7]) = __float2bfloat16_rn(feat);
+                st_bf16(ab + i * 128 + xoroff[i & 7], feat);
                 if (fl & 2) { fout[(size_t)(fl >> 3) * W] = cu; cu = 0.f; }
               }
+              tmem_ld_wait();
+              if (hc < 3) tmem_ld_32x32(tacc + ((hc + 1) >> 1) * 128 + ((hc + 1) & 1) * 64, v0);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float4 pw = ptS[p0 + 32 + i];
+                const int fl = flagS[p0 + 32 + i];
+                if (fl & 1) sr = fmaf(tv.x, pw.y, fmaf(tv.y, pw.z, fmaf(tv.z, pw.w, shift0)));
+                const float feat = __sinf(fmaf(__uint_as_float(v1[i]), scale, sr));
+                cu = fmaf(pw.x, feat, cu);
+                st_bf16(ab + (32 + i) * 128 + xoroff[i & 7], feat);
+                if (fl & 2) { fout[(size_t)(fl >> 3) * W] = cu; cu = 0.f; }
+              }
+              cur[h] = cu; shift_ray[h] = sr;
             }
-            cur[h] = cu; shift_ray[h] = sr;
           }
           tc_fence_before();
           fence_proxy_async_smem();

@@ -57,6 +57,7 @@ struct Args {
   const float* cam_poses; const float* focal; const float* near; const float* far; const float* ray_offset;
   const float* pts; const float* rays_d; const float* viewdirs; const float* z_vals;
   float* rgb_map; float* feature_map; float* sdf; float* mask; float* xyz; float* z_vals_out;
+  int debug;   // bit 0: producer skips the weight copies (timing experiments only; results are garbage)
 };
 
 struct Misc {
