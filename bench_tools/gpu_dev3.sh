@@ -5,11 +5,11 @@ for cs in ffhq_d2_n24 ffhq_d8_n24 ffhq_d2_n128_static cars_d6_n36_b2_beta; do
   run dbg_${cs} python bench_tools/debug_fused.py $cs bf16 points
 done
 run bench_v2 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
-C3D_DEBUG=1 run bench_v2_noweights python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+C3D_DEBUG=1 run bench_noweights python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 C3D_CLUSTER=1 run bench_v2_cl1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 run pytest_gpu python -m pytest tests -q -m gpu --timeout 300
 run ncu_full ncu --set full --clock-control none --import-source on -k regex:fused_forward -s 2 -c 1 -f -o gpurun_out/prof_fused_v2b python bench.py --steps 1 --warmup 3 --no-cpu-baseline
 cat gpurun_out/summary.txt
 tail -q -n 1 gpurun_out/dbg_*.log | cut -c 1-250
-for f in bench_v2 bench_v2_noweights bench_v2_cl1; do tail -n 1 gpurun_out/$f.log | cut -c 1-330; done
+for f in bench_v2 bench_noweights bench_v2_cl1; do tail -n 1 gpurun_out/$f.log | cut -c 1-330; done
 tail -n 3 gpurun_out/pytest_gpu.log

@@ -8,6 +8,7 @@
 #include "mlp_fp32.cuh"
 #include "fused_bf16_sm100.cuh"
 #include "fused2_bf16_sm100.cuh"
+#include "fused3_bf16_sm100.cuh"
 #include "backward.cuh"
 
 namespace c3d {
@@ -150,20 +151,22 @@ static int forward_bf16(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
   if (genv && atoi(genv) > 0) { grid = atoi(genv); if (cluster == 2) grid = (grid + 1) & ~1; }
 
   const char* venv = getenv("C3D_FUSED");
-  const int version = (venv && atoi(venv) == 1) ? 1 : 2;     // 1: rows = points (first version, kept for A/B runs)
+  int version = venv ? atoi(venv) : 3;     // 1: rows = points; 2: lanes = channels, [point][channel] tile; 3: H^T tile
+  if (version < 1 || version > 3) version = 3;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(fused::NTHREADS);
-  cfg.dynamicSmemBytes = version == 1 ? fused::SMEM_BYTES : fused2::SMEM_BYTES;
+  cfg.dynamicSmemBytes = version == 1 ? fused::SMEM_BYTES : (version == 2 ? fused2::SMEM_BYTES : fused3::SMEM_BYTES);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  void (*kern)(const fused::Args) =
-      version == 1 ? (cluster == 2 ? fused::fused_forward_kernel<2> : fused::fused_forward_kernel<1>)
-                   : (cluster == 2 ? fused2::fused_forward_kernel<2> : fused2::fused_forward_kernel<1>);
+  void (*kern)(const fused::Args);
+  if (version == 1) kern = cluster == 2 ? fused::fused_forward_kernel<2> : fused::fused_forward_kernel<1>;
+  else if (version == 2) kern = cluster == 2 ? fused2::fused_forward_kernel<2> : fused2::fused_forward_kernel<1>;
+  else kern = cluster == 2 ? fused3::fused_forward_kernel<2> : fused3::fused_forward_kernel<1>;
   C3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
   C3D_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   C3D_LAUNCH_CHECK();
@@ -332,6 +335,14 @@ int c3d_umma_selftest(const uint16_t* a, const uint16_t* b, float* d, int32_t N,
   }
   C3D_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0, "N=%d must be a multiple of 16 in [16,256]", N);
   C3D_CHECK_ARG(K >= 64 && K <= 256 && K % 64 == 0, "K=%d must be 16 or a multiple of 64 in [64,256]", K);
+  if (variant != 0) {  // MN-major operand layouts (bit 0: A, bit 1: B, bit 2: diagnostic LBO/SBO exchange)
+    C3D_CHECK_ARG(N % 64 == 0, "MN-major self-test needs N %% 64 == 0 (got %d)", N);
+    const int smem_mn = 2 * 65536 + 1024;
+    C3D_CUDA(cudaFuncSetAttribute(fused2::umma_mn_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_mn));
+    fused2::umma_mn_selftest_kernel<<<1, 128, smem_mn, st>>>(a, b, d, N, K, variant);
+    C3D_LAUNCH_CHECK();
+    return C3D_OK;
+  }
   const int smem = fused::ACT_BYTES + N * 128 * (K / 64) + 1024;
   C3D_CUDA(cudaFuncSetAttribute(fused::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   fused::umma_selftest_kernel<<<1, 128, smem, st>>>(a, b, d, N, K);

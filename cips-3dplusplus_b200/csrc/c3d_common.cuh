@@ -31,10 +31,11 @@ constexpr int NCHUNK = W / KCHUNK;  // 4 K-chunks per layer
 //              XOR-swizzled with (n & 7)  == UMMA K-major SWIZZLE_128B image of the smem stage
 //   heads16  : 4 K-chunks x [16 n][64 k] bf16, same swizzle: rows 0..2 = Wrgb, row 4 / 5 = hi / lo bf16 split
 //              of sigma_linear.weight, other rows zero (one N=16 MMA serves the rgb and the sdf head)
-//   w0img    : [256 n][16 k] bf16, UMMA K-major no-swizzle (8x8 core matrices: 16 B per row, 128 B per K-block,
-//              256 B per 8 rows); layer-0 weights split for a K=16 tensor-core product that is exact to ~2^-17:
-//              per coordinate j, k-slots 5j..5j+4 = (hi, hi, hi, lo, lo) of W0[n][j]; the point tile carries
-//              (hi, mid, lo, hi, mid) of the normalised coordinate; slot 15 is zero
+//   w0img    : "wk16" [256 n][16 k] bf16, UMMA K-major no-swizzle (8x8 core matrices: 16 B per row, 128 B per
+//              K-block, 256 B per 8 rows): the K=16 side operand of the layer-0 and view-layer MMAs.
+//              k-slots 4j..4j+3 (j = x,y,z) = (hi, hi, lo, hi) of W0[n][j]  x  point tile (hi, mid, hi, lo) of the
+//              normalised coordinate (split product exact to ~2^-18); slots 12..14 = bf16(Wview[n][256+j]) x
+//              view-direction tile; slot 15 zero.  The point tile zeroes 12..15, the view tile zeroes 0..11.
 // ------------------------------------------------------------------------------------------
 struct PackedLayout {
   size_t w0, wvdir, bias, wsig, wrgb, scal, film, wT32, wbf16, rgb16, w0img, total;

@@ -268,9 +268,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_kernel(const Args a
             const float r1 = pn[jx] - hi;
             const float mid = __bfloat162float(__float2bfloat16_rn(r1));
             const float lo = __bfloat162float(__float2bfloat16_rn(r1 - mid));
-            e[5 * jx + 0] = hi; e[5 * jx + 1] = mid; e[5 * jx + 2] = lo; e[5 * jx + 3] = hi; e[5 * jx + 4] = mid;
+            e[4 * jx + 0] = hi; e[4 * jx + 1] = mid; e[4 * jx + 2] = hi; e[4 * jx + 3] = lo;
           }
-          e[15] = 0.f;
+          e[12] = e[13] = e[14] = e[15] = 0.f;
           uint4 lo8, hi8;                       // values are bf16-exact: the packing below does not round
           lo8.x = pack_bf16x2(e[0], e[1]); lo8.y = pack_bf16x2(e[2], e[3]);
           lo8.z = pack_bf16x2(e[4], e[5]); lo8.w = pack_bf16x2(e[6], e[7]);
@@ -491,6 +491,71 @@ __global__ void __launch_bounds__(128, 1) umma_k16_selftest_kernel(const uint16_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tb, 128); }
+}
+
+
+// Self-test of MN-major SWIZZLE_128B operands:  D[128][N] = A[128][K] * B[N][K]^T with A and/or B stored [k][mn].
+// variant bit 0: A MN-major, bit 1: B MN-major, bit 2: exchange the LBO / SBO fields (diagnostic).
+__global__ void __launch_bounds__(128, 1) umma_mn_selftest_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B,
+                                                                   float* __restrict__ Dout, int N, int K, int variant) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 65536;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tbase;
+  const int warp = threadIdx.x >> 5;
+  const bool a_mn = variant & 1, b_mn = variant & 2;
+  const uint32_t blk = (uint32_t)K * 128u;                   // bytes of one 64-wide mn block: K rows of 128 B
+  for (int idx = threadIdx.x; idx < 128 * K; idx += 128) {
+    const int r = idx / K, k = idx - r * K;
+    const uint32_t off = a_mn ? (uint32_t)(r >> 6) * blk + (uint32_t)k * 128u + (uint32_t)((((r & 63) >> 3) ^ (k & 7)) << 4) + (uint32_t)(r & 7) * 2u
+                              : (uint32_t)(k >> 6) * ACT_CHUNK + sw128_offset(r, k & 63);
+    *reinterpret_cast<uint16_t*>(sA + off) = A[idx];
+  }
+  for (int idx = threadIdx.x; idx < N * K; idx += 128) {
+    const int r = idx / K, k = idx - r * K;
+    const uint32_t off = b_mn ? (uint32_t)(r >> 6) * blk + (uint32_t)k * 128u + (uint32_t)((((r & 63) >> 3) ^ (k & 7)) << 4) + (uint32_t)(r & 7) * 2u
+                              : (uint32_t)(k >> 6) * (uint32_t)(N * 128) + sw128_offset(r, k & 63);
+    *reinterpret_cast<uint16_t*>(sB + off) = B[idx];
+  }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 1) { tmem_alloc(&tbase, 256); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tbase;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)N, a_mn ? 1u : 0u, b_mn ? 1u : 0u);
+    for (int ks = 0; ks < K / 16; ++ks) {
+      uint64_t ad, bd;
+      if (a_mn) ad = umma_desc_mnmajor_sw128(smem_u32(sA) + ks * 2048, blk);
+      else ad = umma_desc_kmajor_sw128(smem_u32(sA + (ks >> 2) * ACT_CHUNK)) + 2 * (ks & 3);
+      if (b_mn) bd = umma_desc_mnmajor_sw128(smem_u32(sB) + ks * 2048, blk);
+      else bd = umma_desc_kmajor_sw128(smem_u32(sB + (ks >> 2) * (N * 128))) + 2 * (ks & 3);
+      if (variant & 4) {
+        const uint64_t m = ((uint64_t)0x3FFF << 16) | ((uint64_t)0x3FFF << 32);
+        const uint64_t sw = ((uint64_t)(1024u >> 4) << 16) | ((uint64_t)((blk >> 4) & 0x3FFF) << 32);
+        if (a_mn) ad = (ad & ~m) | sw;
+        if (b_mn) bd = (bd & ~m) | sw;
+      }
+      umma_bf16_ss(tb, ad, bd, idesc, ks != 0);
+    }
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  const uint32_t taddr = tb + ((uint32_t)(warp * 32) << 16);
+  for (int c0 = 0; c0 < N; c0 += 4) {
+    uint32_t v4[4];
+    tmem_ld_32x4(taddr + c0, v4);
+    tmem_ld_wait();
+    for (int jx = 0; jx < 4; ++jx) Dout[(size_t)threadIdx.x * N + c0 + jx] = __uint_as_float(v4[jx]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tb, 256); }
 }
 
 }}  // namespace c3d::fused2

@@ -1,0 +1,450 @@
+// Fused NeRF-branch forward for sm_100a, version 3.
+//
+// Reference semantics: exp/cips3d/volume_renderer.py:133-160,192-283, exp/cips3d/nerf_utils.py:17-218,230-338.
+//
+// Orientation: every layer computes D^T[channel][point] = W * H^T, so TMEM lanes are channels (the FiLM scale /
+// shift of an epilogue thread are two registers) and TMEM columns are the 128 points of the tile.
+//
+// Activation tile (64 KB per slot): H^T stored [channel][point] in bf16, two 64-point blocks of [256 rows][128 B],
+// 16-byte units XOR-swizzled with (channel & 7).  One buffer, three operand views:
+//   * B operand, MN-major SWIZZLE_128B (N = points, K = channels)      -> hidden / view layer MMAs
+//   * A operand, MN-major SWIZZLE_128B (M = points, K = channels)      -> sdf / rgb head MMAs (N = 16)
+//   * A operand, K-major  SWIZZLE_128B (M = channels, K = points)      -> compositing MMA  F^T = feat^T * Wgt^T
+// The epilogue therefore writes 8 consecutive points of its channel with one 16-byte store.
+//
+// Per 128-point tile the MMA issuer runs D+3 jobs ("wait a_ready -> MMAs -> commit acc_full"), the slot's
+// epilogue group answers each ("wait acc_full -> epilogue -> arrive a_ready"):
+//   job 0       layer 0    : K = 16 split product, A = wk16 (W0 hi/lo), B = point tile (hi/mid/lo)
+//   job 1..D-1  hidden l   : 2 halves x 16 x (128x128x16), A = weight ring stage, B = H^T
+//   job D       sdf head   : 16 x (128x16x16), A = H^T (rows = points), B = heads16
+//   job D+1     view layer : hidden-style + one K = 16 MMA per half adding W_view[:,256:259] * viewdir
+//   job D+2     post       : compositing MMAs (features summed per ray on the tensor core) + rgb head MMA
+#pragma once
+#include "c3d_common.cuh"
+#include "sm100_ptx.cuh"
+#include "fused_bf16_sm100.cuh"   // Args, slot/unit helpers
+
+namespace c3d { namespace fused3 {
+
+using namespace c3d::ptx;
+using fused::Args;
+using fused::slot_tiles;
+
+constexpr int NTHREADS = 384;
+constexpr int TILE = 128;
+constexpr int ACT_BYTES = 65536;               // H^T tile: 2 point blocks x [256][128 B]
+constexpr int ACT_PBLOCK = 32768;
+constexpr int STAGE_BYTES = W * 128;           // 32768: [256 rows][64 k]
+constexpr int NSTAGE = 2;
+constexpr int RAYS = 16;                       // rays touching one tile (n_samples >= 8)
+constexpr int AUX_BYTES = 4096;                // per slot: point tile / view tile ([128][16] k16) or Wgt ([16][128] sw128)
+
+constexpr int SM_ACT = 0;
+constexpr int SM_STAGE = SM_ACT + 2 * ACT_BYTES;                 // 131072
+constexpr int SM_HEADS = SM_STAGE + NSTAGE * STAGE_BYTES;        // 196608
+constexpr int SM_WK16 = SM_HEADS + (int)RGB16_BYTES;             // 204800
+constexpr int SM_AUX = SM_WK16 + (int)W0IMG_BYTES;               // 212992  [slot][4096]
+constexpr int SM_OM = SM_AUX + 2 * AUX_BYTES;                    // 221184  [slot][128] float
+constexpr int SM_RAYACC = SM_OM + 2 * TILE * 4;                  // 222208  [slot][RAYS*2][8] float
+constexpr int SM_MISC = SM_RAYACC + 2 * RAYS * 2 * 8 * 4;        // 224256
+constexpr int SM_TOTAL = SM_MISC + 256;
+constexpr int SMEM_BYTES = SM_TOTAL + 1024;
+
+struct Misc {
+  uint64_t full[NSTAGE], empty[NSTAGE], a_ready[2], acc_full[2];
+  uint32_t tmem_base;
+  float carry[2];
+};
+
+__device__ __forceinline__ int job_layer(int j, int D) {
+  if (j >= 1 && j <= D - 1) return j - 1;
+  if (j == D + 1) return D - 1;
+  return -1;
+}
+
+__device__ __forceinline__ void st_bf16(uint32_t smem_addr, float x) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(x));
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(smem_addr), "h"((unsigned short)r) : "memory");
+}
+__device__ __forceinline__ void st_v4(uint32_t smem_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// sin(acc * scale + shift) for 32 consecutive points of one channel -> bf16 -> four 16-byte stores into H^T.
+// row_addr = tile + block(p0) + channel*128 (shared address), u0 = unit index of p0 inside its 64-point block.
+__device__ __forceinline__ void epilogue32(const uint32_t (&v)[32], float scale, float shift, uint32_t row_addr,
+                                           int u0, int c7) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = __sinf(fmaf(__uint_as_float(v[g * 8 + i]), scale, shift));
+    st_v4(row_addr + (uint32_t)(((u0 + g) ^ c7) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+          pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  }
+}
+
+template <int kCluster>
+__global__ void __launch_bounds__(NTHREADS, 1) fused_forward_kernel(const Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  Misc* misc = reinterpret_cast<Misc*>(smem + SM_MISC);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = a.D, N = a.n_samples;
+  const int JOBS = D + 3;
+  const int nslots = 2 * gridDim.x;
+  const uint32_t cta_rank = kCluster > 1 ? cluster_ctarank() : 0u;
+
+  if (threadIdx.x == 32) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], kCluster); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&misc->a_ready[i], TILE); mbar_init(&misc->acc_full[i], 1); }
+    misc->carry[0] = misc->carry[1] = 1.0f;
+    fence_mbar_init();
+  }
+  if (warp == 2) { tmem_alloc(&misc->tmem_base, 512); tmem_relinquish(); }
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.blob + a.L.rgb16);      // heads16 + wk16 are adjacent
+    uint4* dst = reinterpret_cast<uint4*>(smem + SM_HEADS);
+    for (int i = threadIdx.x; i < (int)(RGB16_BYTES + W0IMG_BYTES) / 16; i += NTHREADS) dst[i] = src[i];
+    float* ra = reinterpret_cast<float*>(smem + SM_RAYACC);
+    for (int i = threadIdx.x; i < 2 * RAYS * 2 * 8; i += NTHREADS) ra[i] = 0.f;
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (kCluster > 1) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = misc->tmem_base;
+
+  int my_tiles[2];
+  my_tiles[0] = slot_tiles(a, 2 * blockIdx.x + 0, nslots);
+  my_tiles[1] = slot_tiles(a, 2 * blockIdx.x + 1, nslots);
+  int max_tiles = max(my_tiles[0], my_tiles[1]);
+  if (kCluster > 1) {
+    const int peer = blockIdx.x ^ 1;
+    max_tiles = max(max_tiles, max(slot_tiles(a, 2 * peer, nslots), slot_tiles(a, 2 * peer + 1, nslots)));
+  }
+  const int rounds = max_tiles * JOBS;
+
+  if (warp == 0 && lane == 0) {
+    // ============================================================ weight producer
+    const uint8_t* wsrc = a.blob + a.L.wbf16;
+    uint32_t n = 0;
+    for (int g = 0; g < rounds; ++g) {
+      const int layer = job_layer(g % JOBS, D);
+      if (layer < 0) continue;
+      for (int s = 0; s < 2; ++s) {
+        for (int c = 0; c < NCHUNK; ++c, ++n) {
+          const uint32_t st = n & 1u, ph = (n >> 1) & 1u;
+          mbar_wait(&misc->empty[st], ph ^ 1u);
+          uint8_t* dst = smem + SM_STAGE + st * STAGE_BYTES;
+          const uint8_t* src = wsrc + (size_t)layer * WBF16_LAYER_BYTES + (size_t)c * WBF16_CHUNK_BYTES;
+          if (a.debug & 1) { mbar_arrive(&misc->full[st]); continue; }
+          mbar_arrive_expect_tx(&misc->full[st], STAGE_BYTES);
+          if (kCluster == 1) {
+            bulk_g2s(dst, src, STAGE_BYTES, &misc->full[st]);
+          } else {
+            const uint32_t half = STAGE_BYTES / 2;
+            bulk_g2s_multicast(dst + cta_rank * half, src + cta_rank * half, half, &misc->full[st], (uint16_t)0x3);
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ============================================================ MMA issuer
+    const uint32_t idesc_kk = umma_idesc_bf16(128, 128, 0, 0);     // both K-major (K = 16 side products)
+    const uint32_t idesc_l = umma_idesc_bf16(128, 128, 0, 1);      // layers: A = weights K-major, B = H^T MN-major
+    const uint32_t idesc_h = umma_idesc_bf16(128, 16, 1, 0);       // heads : A = H^T MN-major (rows = points)
+    const uint32_t idesc_c = umma_idesc_bf16(128, 16, 0, 0);       // composite: A = feat^T K-major, B = Wgt K-major
+    const uint32_t act_addr[2] = {smem_u32(smem + SM_ACT), smem_u32(smem + SM_ACT + ACT_BYTES)};
+    const uint32_t stage_addr[2] = {smem_u32(smem + SM_STAGE), smem_u32(smem + SM_STAGE + STAGE_BYTES)};
+    const uint32_t aux_addr[2] = {smem_u32(smem + SM_AUX), smem_u32(smem + SM_AUX + AUX_BYTES)};
+    const uint32_t heads_addr = smem_u32(smem + SM_HEADS), wk_addr = smem_u32(smem + SM_WK16);
+    uint32_t n = 0, jobcnt[2] = {0u, 0u};
+    for (int g = 0; g < rounds; ++g) {
+      const int j = g % JOBS, tile_idx = g / JOBS;
+      const int layer = job_layer(j, D);
+      for (int s = 0; s < 2; ++s) {
+        const bool real = tile_idx < my_tiles[s];
+        const uint32_t tacc = tmem_base + (uint32_t)s * 256u;
+        if (layer >= 0) {
+          if (real) {
+            mbar_wait(&misc->a_ready[s], jobcnt[s] & 1u);
+            tc_fence_after();
+            if (j == D + 1) {             // view layer: W_view[:,256:259] * viewdir first (K = 16), then accumulate
+              const uint64_t bd = umma_desc_kmajor_k16(aux_addr[s]);
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+                umma_bf16_ss(tacc + (uint32_t)h * 128u, umma_desc_kmajor_k16(wk_addr + h * 4096), bd, idesc_kk, 0u);
+            }
+          }
+          const uint32_t acc0 = (j == D + 1) ? 1u : 0u;
+          for (int c = 0; c < NCHUNK; ++c, ++n) {
+            const uint32_t st = n & 1u, ph = (n >> 1) & 1u;
+            mbar_wait(&misc->full[st], ph);
+            tc_fence_after();
+            if (real) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const uint64_t ad = umma_desc_kmajor_sw128(stage_addr[st] + h * (STAGE_BYTES / 2));
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_bf16_ss(tacc + (uint32_t)h * 128u, ad + 2 * kk,
+                               umma_desc_mnmajor_sw128(act_addr[s] + c * 8192 + kk * 2048, ACT_PBLOCK), idesc_l,
+                               acc0 | (uint32_t)((c | kk) != 0));
+              }
+            }
+            if (kCluster == 1) umma_commit(&misc->empty[st]);
+            else umma_commit_multicast(&misc->empty[st], (uint16_t)0x3);
+          }
+          if (real) { umma_commit(&misc->acc_full[s]); jobcnt[s]++; }
+        } else if (real) {
+          mbar_wait(&misc->a_ready[s], jobcnt[s] & 1u);
+          tc_fence_after();
+          if (j == 0) {                     // layer 0
+            const uint64_t bd = umma_desc_kmajor_k16(aux_addr[s]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              umma_bf16_ss(tacc + (uint32_t)h * 128u, umma_desc_kmajor_k16(wk_addr + h * 4096), bd, idesc_kk, 0u);
+          } else {
+            if (j == D + 2) {               // compositing: F^T[c][ray] = sum_p feat^T[c][p] * Wgt[ray][p]
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                  umma_bf16_ss(tacc + (uint32_t)h * 16u,
+                               umma_desc_kmajor_sw128(act_addr[s] + (ks >> 2) * ACT_PBLOCK + h * 16384) + 2 * (ks & 3),
+                               umma_desc_kmajor_sw128(aux_addr[s] + (ks >> 2) * 2048) + 2 * (ks & 3), idesc_c, ks != 0);
+            }
+            const uint32_t dcol = (j == D + 2) ? 32u : 0u;    // heads: sdf (job D) / rgb (job D+2)
+#pragma unroll
+            for (int ks = 0; ks < 16; ++ks)
+              umma_bf16_ss(tacc + dcol, umma_desc_mnmajor_sw128(act_addr[s] + ks * 2048, ACT_PBLOCK),
+                           umma_desc_kmajor_sw128(heads_addr + (ks >> 2) * 2048) + 2 * (ks & 3), idesc_h, ks != 0);
+          }
+          umma_commit(&misc->acc_full[s]);
+          jobcnt[s]++;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================================================ epilogue groups
+    const int s = (warp - 4) >> 2;
+    const int t = threadIdx.x - 128 - s * TILE;          // point row (point stages) / channel t, t+128 (layer stages)
+    const int quad = warp & 3;
+    const uint32_t bar_id = 1u + (uint32_t)s;
+    const int slot = 2 * blockIdx.x + s;
+    uint8_t* aux = smem + SM_AUX + s * AUX_BYTES;
+    const uint32_t aux_u32 = smem_u32(aux);
+    float* omS = reinterpret_cast<float*>(smem + SM_OM) + s * TILE;
+    float* rayacc = reinterpret_cast<float*>(smem + SM_RAYACC) + s * RAYS * 2 * 8;
+    const uint32_t tacc = tmem_base + (uint32_t)s * 256u + ((uint32_t)(quad * 32) << 16);
+    const float* scal = reinterpret_cast<const float*>(a.blob + a.L.scal);
+    const float bsig = scal[0], brgb0 = scal[1], brgb1 = scal[2], brgb2 = scal[3];
+    const float inv_beta = 1.0f / scal[4];
+    const uint32_t act_u32 = smem_u32(smem + SM_ACT + s * ACT_BYTES);
+    const uint32_t row_u32[2] = {act_u32 + (uint32_t)t * 128u, act_u32 + (uint32_t)(t + TILE) * 128u};
+    const int c7 = t & 7;
+    float carry_f[2] = {0.f, 0.f};                       // partial feature sums of a ray continuing into the next tile
+    uint32_t jobcnt = 0;
+    const int total_units = a.batch * a.units_per_img;
+
+    for (int u = slot; u < total_units; u += nslots) {
+      const int img = u / a.units_per_img;
+      const int r0 = (u - img * a.units_per_img) * a.unit_rays;
+      const int nr = min(a.unit_rays, a.n_rays - r0);
+      const int npts = nr * N;
+      const int ntiles = (npts + TILE - 1) / TILE;
+      const float near = a.near[img], far = a.far[img];
+      const float nscale = 2.0f / (far - near);
+      const float2* film_img = a.film + (size_t)img * (D + 1) * W;
+      carry_f[0] = carry_f[1] = 0.f;
+
+      for (int tile = 0; tile < ntiles; ++tile) {
+        // ------------------------------------------------ geometry of my point (nerf_utils.py:17-170)
+        const int q = tile * TILE + t;
+        const bool valid = q < npts;
+        const int qc = valid ? q : npts - 1;
+        const int rl = qc / N, k = qc - rl * N;
+        const int rl0 = (tile * TILE) / N;                // first ray touching this tile
+        const size_t gray = (size_t)img * a.n_rays + r0 + rl;
+        float px, py, pz, vx, vy, vz, dist, zk;
+        if (a.input_kind == C3D_INPUT_POSES) {
+          const RayGeom rg = make_ray(a.cam_poses + (size_t)img * 12, a.focal[img], a.img_size, r0 + rl, a.static_viewdirs != 0);
+          const float uo = a.ray_offset ? a.ray_offset[gray] : 0.f;
+          zk = sample_depth(near, far, k, N, uo);
+          const float z1 = (k + 1 < N) ? sample_depth(near, far, k + 1, N, uo) : 0.f;
+          px = fmaf(rg.dx, zk, rg.ox); py = fmaf(rg.dy, zk, rg.oy); pz = fmaf(rg.dz, zk, rg.oz);
+          vx = rg.vx; vy = rg.vy; vz = rg.vz;
+          dist = ((k + 1 < N) ? (z1 - zk) : 1e10f) * rg.dnorm;
+        } else {
+          const float* pp = a.pts + (gray * N + k) * 3;
+          px = pp[0]; py = pp[1]; pz = pp[2];
+          const float* vv = a.viewdirs + gray * 3;
+          vx = vv[0]; vy = vv[1]; vz = vv[2];
+          const float* rd = a.rays_d + gray * 3;
+          const float dn = sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]);
+          zk = a.z_vals[gray * N + k];
+          dist = ((k + 1 < N) ? (a.z_vals[gray * N + k + 1] - zk) : 1e10f) * dn;
+        }
+        if (a.z_vals_out && valid) a.z_vals_out[gray * N + k] = zk;
+        const uint32_t aux_row = aux_u32 + (uint32_t)((t >> 3) * 256 + (t & 7) * 16);
+        {
+          // point tile of the layer-0 MMA: per coordinate (hi, mid, hi, lo); k-slots 12..15 zero
+          const float pn[3] = {px * nscale, py * nscale, pz * nscale};
+          float e[12];
+#pragma unroll
+          for (int jx = 0; jx < 3; ++jx) {
+            const float hi = __bfloat162float(__float2bfloat16_rn(pn[jx]));
+            const float r1 = pn[jx] - hi;
+            const float mid = __bfloat162float(__float2bfloat16_rn(r1));
+            const float lo = __bfloat162float(__float2bfloat16_rn(r1 - mid));
+            e[4 * jx + 0] = hi; e[4 * jx + 1] = mid; e[4 * jx + 2] = hi; e[4 * jx + 3] = lo;
+          }
+          st_v4(aux_row, pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+          st_v4(aux_row + 128, pack_bf16x2(e[8], e[9]), pack_bf16x2(e[10], e[11]), 0u, 0u);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&misc->a_ready[s]);
+
+        float sdf = 0.f, wgt = 0.f;
+        // ------------------------------------------------ layers 0..D (D = view layer): thread = channel t and t+128
+        for (int l = 0; l <= D; ++l) {
+          const float2 f0 = film_img[l * W + t], f1 = film_img[l * W + t + TILE];
+          if (l == D) {
+            // ---------------------------------------------- sdf head (thread = point) -> alpha -> transmittance
+            mbar_wait(&misc->acc_full[s], jobcnt & 1u);
+            jobcnt++;
+            tc_fence_after();
+            {
+              uint32_t v4[4];
+              tmem_ld_32x4(tacc + 4, v4);          // heads16 rows 4, 5: hi / lo part of sigma_linear.weight
+              tmem_ld_wait();
+              tc_fence_before();
+              sdf = __uint_as_float(v4[0]) + __uint_as_float(v4[1]) + bsig;
+            }
+            if (valid) a.sdf[gray * N + k] = sdf;
+            const float sigma = sigmoid_precise(-sdf * inv_beta) * inv_beta;
+            const float alpha = 1.0f - expf(-sigma * dist);
+            const float om = 1.0f - alpha + 1e-10f;
+            omS[t] = valid ? om : 1.0f;
+            // view-direction tile for the view-layer MMA (k-slots 12..14), reuses the point-tile buffer
+            st_v4(aux_row, 0u, 0u, 0u, 0u);
+            st_v4(aux_row + 128, 0u, 0u, pack_bf16x2(vx, vy), pack_bf16x2(vz, 0.f));
+            named_bar_sync(bar_id, TILE);
+            const int first_row = t - k;
+            float T = first_row < 0 ? misc->carry[s] : 1.0f;
+            for (int m = max(first_row, 0); m < t; ++m) T *= omS[m];
+            wgt = valid ? alpha * T : 0.f;
+            named_bar_sync(bar_id, TILE);
+            if (t == TILE - 1) misc->carry[s] = (k == N - 1) ? 1.0f : T * om;
+            fence_proxy_async_smem();
+            mbar_arrive(&misc->a_ready[s]);
+          }
+          mbar_wait(&misc->acc_full[s], jobcnt & 1u);
+          jobcnt++;
+          tc_fence_after();
+          if (l == D) {
+            // the view-direction tile has been consumed: build Wgt[ray slot][point] (bf16, K-major SW128) in its place
+            const int myslot = rl - rl0;
+#pragma unroll
+            for (int jx = 0; jx < RAYS; ++jx)
+              st_bf16(aux_u32 + (uint32_t)((t >> 6) * 2048) + sw128_offset(jx, t & 63), jx == myslot ? wgt : 0.f);
+          }
+          {
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32(tacc, v0);
+#pragma unroll 1
+            for (int hc = 0; hc < 4; ++hc) {               // 64 points (= one point block) of one channel half
+              const int h = hc >> 1, pb = hc & 1;
+              const float scale = h ? f1.x : f0.x, shift = h ? f1.y : f0.y;
+              const uint32_t row = (h ? row_u32[1] : row_u32[0]) + (uint32_t)pb * ACT_PBLOCK;
+              tmem_ld_wait();
+              tmem_ld_32x32(tacc + h * 128 + pb * 64 + 32, v1);
+              epilogue32(v0, scale, shift, row, 0, c7);
+              tmem_ld_wait();
+              if (hc < 3) tmem_ld_32x32(tacc + ((hc + 1) >> 1) * 128 + ((hc + 1) & 1) * 64, v0);
+              epilogue32(v1, scale, shift, row, 4, c7);
+            }
+          }
+          tc_fence_before();
+          fence_proxy_async_smem();
+          mbar_arrive(&misc->a_ready[s]);
+        }
+
+        // ------------------------------------------------ post job: composited features (thread = channel) + rgb (thread = point)
+        {
+          mbar_wait(&misc->acc_full[s], jobcnt & 1u);
+          jobcnt++;
+          tc_fence_after();
+          uint32_t fv[32], v4[4];
+          tmem_ld_32x32(tacc, fv);               // cols 0..15: channel t, cols 16..31: channel t+128; column = ray slot
+          tmem_ld_32x4(tacc + 32, v4);           // raw rgb of my point
+          tmem_ld_wait();
+          tc_fence_before();
+          float* fbase = a.feature_map + ((size_t)img * a.n_rays + r0 + rl0) * W + t;
+          const int tile_end = min((tile + 1) * TILE, npts);      // first point index beyond this tile
+#pragma unroll
+          for (int jx = 0; jx < RAYS; ++jx) {
+            const int rbeg = (rl0 + jx) * N, rend = rbeg + N;      // point range of ray slot jx inside the unit
+            if (rbeg < tile_end) {                                  // uniform: the slot is in use
+              float f0v = __uint_as_float(fv[jx]), f1v = __uint_as_float(fv[16 + jx]);
+              if (jx == 0) { f0v += carry_f[0]; f1v += carry_f[1]; }
+              if (rend <= tile_end) {                               // ray complete
+                fbase[(size_t)jx * W] = f0v;
+                fbase[(size_t)jx * W + TILE] = f1v;
+              }
+              if (rend >= tile_end) {                               // last slot of the tile: carry (0 if it ended here)
+                carry_f[0] = rend > tile_end ? f0v : 0.f;
+                carry_f[1] = rend > tile_end ? f1v : 0.f;
+              }
+            }
+          }
+          // rgb / xyz / mask sums of my ray (nerf_utils.py:315,329-336)
+          float vals[6];
+          vals[0] = wgt * sigmoid_precise(__uint_as_float(v4[0]) + brgb0);
+          vals[1] = wgt * sigmoid_precise(__uint_as_float(v4[1]) + brgb1);
+          vals[2] = wgt * sigmoid_precise(__uint_as_float(v4[2]) + brgb2);
+          vals[3] = wgt * px; vals[4] = wgt * py; vals[5] = wgt * pz;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int rid = __shfl_down_sync(0xffffffffu, rl, o);
+            const bool same = (lane + o < 32) && (rid == rl);
+#pragma unroll
+            for (int jx = 0; jx < 6; ++jx) {
+              const float y = __shfl_down_sync(0xffffffffu, vals[jx], o);
+              if (same) vals[jx] += y;
+            }
+          }
+          const int rprev = __shfl_up_sync(0xffffffffu, rl, 1);
+          float* racc = rayacc + (rl & (2 * RAYS - 1)) * 8;
+          if (valid && (lane == 0 || rprev != rl)) {
+#pragma unroll
+            for (int jx = 0; jx < 6; ++jx) atomicAdd(racc + jx, vals[jx]);
+          }
+          named_bar_sync(bar_id, TILE);
+          if (valid && k == N - 1) {
+            const float x = racc[3], y = racc[4], z = racc[5];
+            float* o3 = a.rgb_map + gray * 3;
+            o3[0] = -1.0f + 2.0f * racc[0]; o3[1] = -1.0f + 2.0f * racc[1]; o3[2] = -1.0f + 2.0f * racc[2];
+            float* x3 = a.xyz + gray * 3;
+            x3[0] = x; x3[1] = y; x3[2] = z;
+            a.mask[gray * 2 + 0] = wgt;
+            a.mask[gray * 2 + 1] = -sqrtf(x * x + y * y + z * z);
+#pragma unroll
+            for (int jx = 0; jx < 6; ++jx) racc[jx] = 0.f;
+          }
+        }
+      }  // tiles
+    }    // units
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (kCluster > 1) cluster_sync_all();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+}}  // namespace c3d::fused3

@@ -47,14 +47,17 @@ __global__ void pack_small_kernel(c3d_raw_params raw, uint8_t* __restrict__ blob
     const int ch = c >> 6, k = c & 63;
     *reinterpret_cast<__nv_bfloat16*>(r16 + (size_t)ch * (16 * 128) + sw128_offset(n, k)) = __float2bfloat16_rn(v);
   }
-  // layer-0 split image: row c, k-slots 5j..5j+4 = (hi, hi, hi, lo, lo) of W0[c][j]
+  // wk16 image (see c3d_common.cuh): W0 split in slots 0..11, view-direction weights in 12..14
   uint8_t* w0i = blob + L.w0img;
   for (int j = 0; j < 3; ++j) {
     const float w = raw.pts_weight[0][c * 3 + j];
     const __nv_bfloat16 hi = __float2bfloat16_rn(w);
     const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-    for (int q = 0; q < 5; ++q)
-      *reinterpret_cast<__nv_bfloat16*>(w0i + k16_offset(c, 5 * j + q)) = q < 3 ? hi : lo;
+    *reinterpret_cast<__nv_bfloat16*>(w0i + k16_offset(c, 4 * j + 0)) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(w0i + k16_offset(c, 4 * j + 1)) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(w0i + k16_offset(c, 4 * j + 2)) = lo;
+    *reinterpret_cast<__nv_bfloat16*>(w0i + k16_offset(c, 4 * j + 3)) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(w0i + k16_offset(c, 12 + j)) = __float2bfloat16_rn(raw.views_weight[c * (W + 3) + W + j]);
   }
   *reinterpret_cast<__nv_bfloat16*>(w0i + k16_offset(c, 15)) = __float2bfloat16_rn(0.f);
 }

@@ -119,11 +119,25 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_k16(uint32_t smem_addr) {
   d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell); layout type 0 = no swizzle
   return d;
 }
-// Instruction descriptor, kind::f16: BF16 x BF16 -> FP32, both operands K-major.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
+// MN-major operand (memory is [k][mn], mn contiguous), SWIZZLE_128B: 64 mn-elements (128 B) per row, one row per k,
+// 8-row (k) atoms of 1024 B (stride byte offset); the next 64 mn-elements live `mn_block_bytes` further
+// (leading byte offset).  Advance the start address by 16 rows (2048 B) per K=16 step.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t mn_block_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((mn_block_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: BF16 x BF16 -> FP32; a_mn / b_mn select MN-major operands (default K-major).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn = 0, uint32_t b_mn = 0) {
   return (1u << 4)            // c_format  = F32
          | (1u << 7)          // a_format  = BF16
          | (1u << 10)         // b_format  = BF16
+         | (a_mn << 15)       // a_major
+         | (b_mn << 16)       // b_major
          | ((N >> 3) << 17)   // n_dim
          | ((M >> 4) << 24);  // m_dim
 }
