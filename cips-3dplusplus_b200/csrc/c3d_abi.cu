@@ -6,9 +6,8 @@
 #include "c3d_common.cuh"
 #include "kernels_aux.cuh"
 #include "mlp_fp32.cuh"
+#include "fused_common.cuh"
 #include "fused_bf16_sm100.cuh"
-#include "fused2_bf16_sm100.cuh"
-#include "fused3_bf16_sm100.cuh"
 #include "backward.cuh"
 
 namespace c3d {
@@ -150,23 +149,21 @@ static int forward_bf16(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
   const char* genv = getenv("C3D_GRID");
   if (genv && atoi(genv) > 0) { grid = atoi(genv); if (cluster == 2) grid = (grid + 1) & ~1; }
 
-  const char* venv = getenv("C3D_FUSED");
-  int version = venv ? atoi(venv) : 3;     // 1: rows = points; 2: lanes = channels, [point][channel] tile; 3: H^T tile
-  if (version < 1 || version > 3) version = 3;
+  const char* eenv = getenv("C3D_EGW");
+  const int egw = (eenv && atoi(eenv) == 8) ? 8 : 4;      // epilogue warps per slot (tuning knob; 4 measured best)
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(fused::NTHREADS);
-  cfg.dynamicSmemBytes = version == 1 ? fused::SMEM_BYTES : (version == 2 ? fused2::SMEM_BYTES : fused3::SMEM_BYTES);
+  cfg.blockDim = dim3(fused::nthreads(egw));
+  cfg.dynamicSmemBytes = fused::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   void (*kern)(const fused::Args);
-  if (version == 1) kern = cluster == 2 ? fused::fused_forward_kernel<2> : fused::fused_forward_kernel<1>;
-  else if (version == 2) kern = cluster == 2 ? fused2::fused_forward_kernel<2> : fused2::fused_forward_kernel<1>;
-  else kern = cluster == 2 ? fused3::fused_forward_kernel<2> : fused3::fused_forward_kernel<1>;
+  if (egw == 8) kern = cluster == 2 ? fused::fused_forward_kernel<2, 8> : fused::fused_forward_kernel<1, 8>;
+  else kern = cluster == 2 ? fused::fused_forward_kernel<2, 4> : fused::fused_forward_kernel<1, 4>;
   C3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
   C3D_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   C3D_LAUNCH_CHECK();
@@ -329,7 +326,7 @@ int c3d_umma_selftest(const uint16_t* a, const uint16_t* b, float* d, int32_t N,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (K == 16) {       // layer-0 operand layout (K-major, no swizzle); variant 1 swaps LBO/SBO (diagnostic)
     C3D_CHECK_ARG(N == 128, "K=16 self-test needs N=128 (got %d)", N);
-    fused2::umma_k16_selftest_kernel<<<1, 128, 0, st>>>(a, b, d, variant);
+    fused::umma_k16_selftest_kernel<<<1, 128, 0, st>>>(a, b, d, variant);
     C3D_LAUNCH_CHECK();
     return C3D_OK;
   }
@@ -338,8 +335,8 @@ int c3d_umma_selftest(const uint16_t* a, const uint16_t* b, float* d, int32_t N,
   if (variant != 0) {  // MN-major operand layouts (bit 0: A, bit 1: B, bit 2: diagnostic LBO/SBO exchange)
     C3D_CHECK_ARG(N % 64 == 0, "MN-major self-test needs N %% 64 == 0 (got %d)", N);
     const int smem_mn = 2 * 65536 + 1024;
-    C3D_CUDA(cudaFuncSetAttribute(fused2::umma_mn_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_mn));
-    fused2::umma_mn_selftest_kernel<<<1, 128, smem_mn, st>>>(a, b, d, N, K, variant);
+    C3D_CUDA(cudaFuncSetAttribute(fused::umma_mn_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_mn));
+    fused::umma_mn_selftest_kernel<<<1, 128, smem_mn, st>>>(a, b, d, N, K, variant);
     C3D_LAUNCH_CHECK();
     return C3D_OK;
   }

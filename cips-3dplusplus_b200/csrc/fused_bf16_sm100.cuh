@@ -1,64 +1,51 @@
-// Fused NeRF-branch forward for sm_100a: rays -> samples -> FiLM-SIREN point MLP on tcgen05 tensor
-// cores (bf16 operands, fp32 TMEM accumulators) -> SDF compositing -> (rgb, feature, sdf, mask, xyz)
-// maps.  Per-point activations never leave the SM.
+// Fused NeRF-branch forward for sm_100a (third structure tried this round; profiles/r01_fused.md has the history).
 //
-// Reference semantics: exp/cips3d/volume_renderer.py:133-160,192-283 and
-// exp/cips3d/nerf_utils.py:17-218,230-338 (see DESIGN.md for the math and the data layout).
+// Reference semantics: exp/cips3d/volume_renderer.py:133-160,192-283, exp/cips3d/nerf_utils.py:17-218,230-338.
 //
-// One persistent CTA per SM, 12 warps:
-//   warp 0  (1 lane)  weight producer : cp.async.bulk (TMA engine) of pre-swizzled 32 KB K-chunks of
-//                                        the layer's bf16 weights into a 2-stage shared-memory ring
-//                                        (multicast to the 2 CTAs of a cluster when kCluster == 2)
-//   warp 1  (1 lane)  MMA issuer      : tcgen05.mma 128x256x16 (hidden layers), 2 x 128x128x16 with the
-//                                        operand roles swapped (view layer -> channels on TMEM lanes),
-//                                        128x16x16 (rgb head); tcgen05.commit -> mbarriers
-//   warp 2            TMEM allocator (512 columns = two 128x256 fp32 accumulators)
-//   warps 4-7 / 8-11  epilogue group 0 / 1: each owns one 128-point tile "slot" (activations 64 KB in
-//                                        shared memory as the K-major SWIZZLE_128B A operand, one
-//                                        accumulator).  While the tensor core runs slot X's layer, slot
-//                                        Y's warps apply sin(gamma*acc+shift) and rewrite its A tile.
+// Orientation: every layer computes D^T[channel][point] = W * H^T, so TMEM lanes are channels (the FiLM scale /
+// shift of an epilogue thread are two registers) and TMEM columns are the 128 points of the tile.
+//
+// Activation tile (64 KB per slot): H^T stored [channel][point] in bf16, two 64-point blocks of [256 rows][128 B],
+// 16-byte units XOR-swizzled with (channel & 7).  One buffer, three operand views:
+//   * B operand, MN-major SWIZZLE_128B (N = points, K = channels)      -> hidden / view layer MMAs
+//   * A operand, MN-major SWIZZLE_128B (M = points, K = channels)      -> sdf / rgb head MMAs (N = 16)
+//   * A operand, K-major  SWIZZLE_128B (M = channels, K = points)      -> compositing MMA  F^T = feat^T * Wgt^T
+// The epilogue therefore writes 8 consecutive points of its channel with one 16-byte store.
+//
+// Per 128-point tile the MMA issuer runs D+3 jobs ("wait a_ready -> MMAs -> commit acc_full"), the slot's
+// epilogue group answers each ("wait acc_full -> epilogue -> arrive a_ready"):
+//   job 0       layer 0    : K = 16 split product, A = wk16 (W0 hi/lo), B = point tile (hi/mid/lo)
+//   job 1..D-1  hidden l   : 2 halves x 16 x (128x128x16), A = weight ring stage, B = H^T
+//   job D       sdf head   : 16 x (128x16x16), A = H^T (rows = points), B = heads16
+//   job D+1     view layer : hidden-style + one K = 16 MMA per half adding W_view[:,256:259] * viewdir
+//   job D+2     post       : compositing MMAs (features summed per ray on the tensor core) + rgb head MMA
 #pragma once
 #include "c3d_common.cuh"
 #include "sm100_ptx.cuh"
+#include "fused_common.cuh"
 
 namespace c3d { namespace fused {
 
-using namespace c3d::ptx;
 
-constexpr int NTHREADS = 384;
-constexpr int TILE = 128;
-constexpr int ACT_CHUNK = TILE * 128;          // 16384 B: [128 rows][64 bf16]
-constexpr int ACT_BYTES = NCHUNK * ACT_CHUNK;  // 65536
-constexpr int STAGE_BYTES = W * 128;           // 32768: [256 rows][64 bf16]
-constexpr int NSTAGE = 2;
-constexpr int RSLOTS = 32;                     // per-slot ray accumulators (rays per tile <= 128/N + 2)
-constexpr int MIN_SAMPLES = 8;
+// epilogue warps per slot (template parameter kEgw): 4 -> each thread owns channels t and t+128;
+// 8 -> warps 0-3 own channel half 0, warps 4-7 half 1 (and only warps 0-3 run the per-point stages)
+__host__ __device__ constexpr int nthreads(int egw) { return 128 + 2 * egw * 32; }
+constexpr int ACT_PBLOCK = 32768;
+constexpr int STAGE_BYTES = 128 * 128;         // 16384: one channel half of a K-chunk, [128 rows][64 k]
+constexpr int NSTAGE = 4;
+constexpr int RAYS = 16;                       // rays touching one tile (n_samples >= 8)
+constexpr int AUX_BYTES = 4096;                // per slot: point tile / view tile ([128][16] k16) or Wgt ([16][128] sw128)
 
-// shared memory map (bytes from a 1024-aligned base)
 constexpr int SM_ACT = 0;
 constexpr int SM_STAGE = SM_ACT + 2 * ACT_BYTES;                 // 131072
-constexpr int SM_RGB16 = SM_STAGE + NSTAGE * STAGE_BYTES;        // 196608
-constexpr int SM_FILM = SM_RGB16 + (int)RGB16_BYTES;             // 204800  [slot][buf][256] float2
-constexpr int SM_TAB0 = SM_FILM + 2 * 2 * W * 8;                 // 212992  [slot][256] float4
-constexpr int SM_PT = SM_TAB0 + 2 * W * 16;                      // 221184  [slot][128] float4 (w, vx, vy, vz)
-constexpr int SM_WSIG = SM_PT + 2 * TILE * 16;                   // 225280  [256] float
-constexpr int SM_OM = SM_WSIG + W * 4;                           // 226304  [slot][128] float
-constexpr int SM_FLAG = SM_OM + 2 * TILE * 4;                    // 227328  [slot][128] int
-constexpr int SM_RAYACC = SM_FLAG + 2 * TILE * 4;                // 228352  [slot][RSLOTS][8] float
-constexpr int SM_MISC = SM_RAYACC + 2 * RSLOTS * 8 * 4;          // 230400  barriers, tmem ptr, carries
-constexpr int SM_TOTAL = SM_MISC + 256;                          // 230656
-constexpr int SMEM_BYTES = SM_TOTAL + 1024;                      // + alignment slack
-
-struct Args {
-  const uint8_t* blob; PackedLayout L;
-  const float2* film; const float4* first; const float4* view;   // style_prep tables, indexed by image
-  int batch, n_rays, n_samples, D, img_size, static_viewdirs, input_kind;
-  int unit_rays, units_per_img;
-  const float* cam_poses; const float* focal; const float* near; const float* far; const float* ray_offset;
-  const float* pts; const float* rays_d; const float* viewdirs; const float* z_vals;
-  float* rgb_map; float* feature_map; float* sdf; float* mask; float* xyz; float* z_vals_out;
-  int debug;   // bit 0: producer skips the weight copies (timing experiments only; results are garbage)
-};
+constexpr int SM_HEADS = SM_STAGE + NSTAGE * STAGE_BYTES;        // 196608
+constexpr int SM_WK16 = SM_HEADS + (int)RGB16_BYTES;             // 204800
+constexpr int SM_AUX = SM_WK16 + (int)W0IMG_BYTES;               // 212992  [slot][4096]
+constexpr int SM_OM = SM_AUX + 2 * AUX_BYTES;                    // 221184  [slot][128] float
+constexpr int SM_RAYACC = SM_OM + 2 * TILE * 4;                  // 222208  [slot][RAYS*2][8] float
+constexpr int SM_MISC = SM_RAYACC + 2 * RAYS * 2 * 8 * 4;        // 224256
+constexpr int SM_TOTAL = SM_MISC + 256;
+constexpr int SMEM_BYTES = SM_TOTAL + 1024;
 
 struct Misc {
   uint64_t full[NSTAGE], empty[NSTAGE], a_ready[2], acc_full[2];
@@ -66,55 +53,85 @@ struct Misc {
   float carry[2];
 };
 
-__device__ __forceinline__ int unit_tiles(const Args& a, int u) {
-  const int r0 = (u % a.units_per_img) * a.unit_rays;
-  const int nr = min(a.unit_rays, a.n_rays - r0);
-  return (nr * a.n_samples + TILE - 1) / TILE;
-}
-__device__ __forceinline__ int slot_tiles(const Args& a, int slot, int nslots) {
-  int t = 0;
-  const int total = a.batch * a.units_per_img;
-  for (int u = slot; u < total; u += nslots) t += unit_tiles(a, u);
-  return t;
+__device__ __forceinline__ int job_layer(int j, int D) {
+  if (j >= 1 && j <= D - 1) return j - 1;
+  if (j == D + 1) return D - 1;
+  return -1;
 }
 
-// 8 activations -> bf16 -> one 16-byte store into the K-major SWIZZLE_128B A tile (row = point)
-__device__ __forceinline__ void store8(uint8_t* act_row /*act + row*128*/, int row7, int c8 /*0..31*/, const float (&o)[8]) {
-  uint4 pk;
-  pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
-  pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
-  *reinterpret_cast<uint4*>(act_row + (c8 >> 3) * ACT_CHUNK + (((c8 & 7) ^ row7) << 4)) = pk;
+__device__ __forceinline__ void st_bf16(uint32_t smem_addr, float x) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(x));
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(smem_addr), "h"((unsigned short)r) : "memory");
+}
+__device__ __forceinline__ void st_v4(uint32_t smem_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <int kCluster>
-__global__ void __launch_bounds__(NTHREADS, 1) fused_forward_kernel(const Args a) {
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// sin(acc * scale + shift) for 16 consecutive points of one channel -> bf16 -> two 16-byte stores into H^T.
+__device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], float scale, float shift, uint32_t row_addr,
+                                           int u0, int c7) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = __sinf(fmaf(__uint_as_float(v[g * 8 + i]), scale, shift));
+    st_v4(row_addr + (uint32_t)(((u0 + g) ^ c7) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+          pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  }
+}
+
+// sin(acc * scale + shift) for 32 consecutive points of one channel -> bf16 -> four 16-byte stores into H^T.
+// row_addr = tile + block(p0) + channel*128 (shared address), u0 = unit index of p0 inside its 64-point block.
+__device__ __forceinline__ void epilogue32(const uint32_t (&v)[32], float scale, float shift, uint32_t row_addr,
+                                           int u0, int c7) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = __sinf(fmaf(__uint_as_float(v[g * 8 + i]), scale, shift));
+    st_v4(row_addr + (uint32_t)(((u0 + g) ^ c7) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+          pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  }
+}
+
+template <int kCluster, int kEgw>
+__global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const Args a) {
+  constexpr int EG_THREADS = kEgw * 32;
+  constexpr int NTHREADS = nthreads(kEgw);
+  constexpr int HPT = kEgw == 8 ? 1 : 2;               // channel halves per epilogue thread
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   Misc* misc = reinterpret_cast<Misc*>(smem + SM_MISC);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform role index
+  const int lane = threadIdx.x & 31;
   const int D = a.D, N = a.n_samples;
-  const int JOBS = D + 1;                           // MMA jobs per tile: D-1 hidden, view, rgb
+  const int JOBS = D + 3;
   const int nslots = 2 * gridDim.x;
   const uint32_t cta_rank = kCluster > 1 ? cluster_ctarank() : 0u;
 
-  // ---------------------------------------------------------------- one-time setup
   if (threadIdx.x == 32) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], kCluster); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&misc->a_ready[i], TILE); mbar_init(&misc->acc_full[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&misc->a_ready[i], EG_THREADS); mbar_init(&misc->acc_full[i], 1); }
     misc->carry[0] = misc->carry[1] = 1.0f;
     fence_mbar_init();
   }
   if (warp == 2) { tmem_alloc(&misc->tmem_base, 512); tmem_relinquish(); }
   {
-    // resident tables: rgb-head bf16 image, sigma weights; zero the ray accumulators
-    const uint4* src = reinterpret_cast<const uint4*>(a.blob + a.L.rgb16);
-    uint4* dst = reinterpret_cast<uint4*>(smem + SM_RGB16);
-    for (int i = threadIdx.x; i < (int)RGB16_BYTES / 16; i += NTHREADS) dst[i] = src[i];
-    const float* ws = reinterpret_cast<const float*>(a.blob + a.L.wsig);
-    float* wd = reinterpret_cast<float*>(smem + SM_WSIG);
-    for (int i = threadIdx.x; i < W; i += NTHREADS) wd[i] = ws[i];
+    const uint4* src = reinterpret_cast<const uint4*>(a.blob + a.L.rgb16);      // heads16 + wk16 are adjacent
+    uint4* dst = reinterpret_cast<uint4*>(smem + SM_HEADS);
+    for (int i = threadIdx.x; i < (int)(RGB16_BYTES + W0IMG_BYTES) / 16; i += NTHREADS) dst[i] = src[i];
     float* ra = reinterpret_cast<float*>(smem + SM_RAYACC);
-    for (int i = threadIdx.x; i < 2 * RSLOTS * 8; i += NTHREADS) ra[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * RAYS * 2 * 8; i += NTHREADS) ra[i] = 0.f;
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -123,7 +140,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_kernel(const Args a
   tc_fence_after();
   const uint32_t tmem_base = misc->tmem_base;
 
-  // rounds of the merged job sequence; identical for every CTA of a cluster (weight ring is shared)
   int my_tiles[2];
   my_tiles[0] = slot_tiles(a, 2 * blockIdx.x + 0, nslots);
   my_tiles[1] = slot_tiles(a, 2 * blockIdx.x + 1, nslots);
@@ -134,19 +150,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_kernel(const Args a
   }
   const int rounds = max_tiles * JOBS;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
+   if (elect_one()) {
     // ============================================================ weight producer
     const uint8_t* wsrc = a.blob + a.L.wbf16;
     uint32_t n = 0;
     for (int g = 0; g < rounds; ++g) {
-      const int j = g % JOBS;
-      if (j >= D) continue;
+      const int layer = job_layer(g % JOBS, D);
+      if (layer < 0) continue;
       for (int s = 0; s < 2; ++s) {
-        for (int c = 0; c < NCHUNK; ++c, ++n) {
-          const uint32_t st = n & 1u, ph = (n >> 1) & 1u;
+        for (int c = 0; c < 2 * NCHUNK; ++c, ++n) {          // stage = (K-chunk c>>1, channel half c&1): 16 KB contiguous
+          const uint32_t st = n % NSTAGE, ph = (n / NSTAGE) & 1u;
           mbar_wait(&misc->empty[st], ph ^ 1u);
           uint8_t* dst = smem + SM_STAGE + st * STAGE_BYTES;
-          const uint8_t* src = wsrc + (size_t)j * WBF16_LAYER_BYTES + (size_t)c * WBF16_CHUNK_BYTES;
+          const uint8_t* src = wsrc + (size_t)layer * WBF16_LAYER_BYTES + (size_t)c * STAGE_BYTES;
+          if (a.debug & 1) { mbar_arrive(&misc->full[st]); continue; }
           mbar_arrive_expect_tx(&misc->full[st], STAGE_BYTES);
           if (kCluster == 1) {
             bulk_g2s(dst, src, STAGE_BYTES, &misc->full[st]);
@@ -157,88 +175,132 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_kernel(const Args a
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+   }
+  } else if (warp == 1) {
+   if (elect_one()) {
     // ============================================================ MMA issuer
-    const uint32_t idesc_l = umma_idesc_bf16(128, 256), idesc_t = umma_idesc_bf16(128, 128), idesc_r = umma_idesc_bf16(128, 16);
+    const uint32_t idesc_kk = umma_idesc_bf16(128, 128, 0, 0);     // both K-major (K = 16 side products)
+    const uint32_t idesc_l = umma_idesc_bf16(128, 128, 0, 1);      // layers: A = weights K-major, B = H^T MN-major
+    const uint32_t idesc_h = umma_idesc_bf16(128, 16, 1, 0);       // heads : A = H^T MN-major (rows = points)
+    const uint32_t idesc_c = umma_idesc_bf16(128, 16, 0, 0);       // composite: A = feat^T K-major, B = Wgt K-major
     const uint32_t act_addr[2] = {smem_u32(smem + SM_ACT), smem_u32(smem + SM_ACT + ACT_BYTES)};
-    const uint32_t stage_addr[2] = {smem_u32(smem + SM_STAGE), smem_u32(smem + SM_STAGE + STAGE_BYTES)};
-    const uint32_t rgb_addr = smem_u32(smem + SM_RGB16);
+    const uint32_t stage_base = smem_u32(smem + SM_STAGE);
+    const uint32_t aux_addr[2] = {smem_u32(smem + SM_AUX), smem_u32(smem + SM_AUX + AUX_BYTES)};
+    const uint32_t heads_addr = smem_u32(smem + SM_HEADS), wk_addr = smem_u32(smem + SM_WK16);
     uint32_t n = 0, jobcnt[2] = {0u, 0u};
+#ifdef C3D_KERNEL_PROF
+    const bool prof = (a.debug & 2) != 0;
+#else
+    constexpr bool prof = false;
+#endif
+    long long t_ready = 0, t_full = 0, t_issue = 0, t_mark = clock64(), t_begin = t_mark;
+#define C3D_PROF_ADD(acc) do { if (prof) { const long long now_ = clock64(); acc += now_ - t_mark; t_mark = now_; } } while (0)
     for (int g = 0; g < rounds; ++g) {
       const int j = g % JOBS, tile_idx = g / JOBS;
+      const int layer = job_layer(j, D);
       for (int s = 0; s < 2; ++s) {
         const bool real = tile_idx < my_tiles[s];
         const uint32_t tacc = tmem_base + (uint32_t)s * 256u;
-        if (j < D) {
-          if (real) { mbar_wait(&misc->a_ready[s], jobcnt[s] & 1u); tc_fence_after(); }
-          for (int c = 0; c < NCHUNK; ++c, ++n) {
-            const uint32_t st = n & 1u, ph = (n >> 1) & 1u;
+        if (layer >= 0) {
+          if (real) {
+            C3D_PROF_ADD(t_issue);
+            mbar_wait(&misc->a_ready[s], jobcnt[s] & 1u);
+            C3D_PROF_ADD(t_ready);
+            tc_fence_after();
+            if (j == D + 1) {             // view layer: W_view[:,256:259] * viewdir first (K = 16), then accumulate
+              const uint64_t bd = umma_desc_kmajor_k16(aux_addr[s]);
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+                umma_bf16_ss(tacc + (uint32_t)h * 128u, umma_desc_kmajor_k16(wk_addr + h * 4096), bd, idesc_kk, 0u);
+            }
+          }
+          const uint32_t acc0 = (j == D + 1) ? 1u : 0u;
+          for (int c = 0; c < 2 * NCHUNK; ++c, ++n) {
+            const uint32_t st = n % NSTAGE, ph = (n / NSTAGE) & 1u;
+            C3D_PROF_ADD(t_issue);
             mbar_wait(&misc->full[st], ph);
+            C3D_PROF_ADD(t_full);
             tc_fence_after();
             if (real) {
-              if (j < D - 1) {            // hidden layer: rows = points (A = activations), N = 256 channels
-                const uint64_t ad = umma_desc_kmajor_sw128(act_addr[s] + c * ACT_CHUNK);
-                const uint64_t bd = umma_desc_kmajor_sw128(stage_addr[st]);
+              const int kc = c >> 1, h = c & 1;
+              const uint64_t ad = umma_desc_kmajor_sw128(stage_base + st * STAGE_BYTES);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tacc, ad + 2 * kk, bd + 2 * kk, idesc_l, (c | kk) != 0);
-              } else {                    // view layer, operand roles swapped: rows = channels, N = 128 points
-                const uint64_t bd = umma_desc_kmajor_sw128(act_addr[s] + c * ACT_CHUNK);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  const uint64_t ad = umma_desc_kmajor_sw128(stage_addr[st] + h * (STAGE_BYTES / 2));
-#pragma unroll
-                  for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16_ss(tacc + (uint32_t)h * 128u, ad + 2 * kk, bd + 2 * kk, idesc_t, (c | kk) != 0);
-                }
-              }
+              for (int kk = 0; kk < 4; ++kk)
+                umma_bf16_ss(tacc + (uint32_t)h * 128u, ad + 2 * kk,
+                             umma_desc_mnmajor_sw128(act_addr[s] + kc * 8192 + kk * 2048, ACT_PBLOCK), idesc_l,
+                             acc0 | (uint32_t)((kc | kk) != 0));
             }
             if (kCluster == 1) umma_commit(&misc->empty[st]);
             else umma_commit_multicast(&misc->empty[st], (uint16_t)0x3);
           }
           if (real) { umma_commit(&misc->acc_full[s]); jobcnt[s]++; }
-        } else if (real) {                // rgb head: rows = points, N = 16 (3 used)
+        } else if (real) {
+          C3D_PROF_ADD(t_issue);
           mbar_wait(&misc->a_ready[s], jobcnt[s] & 1u);
+          C3D_PROF_ADD(t_ready);
           tc_fence_after();
+          if (j == 0) {                     // layer 0
+            const uint64_t bd = umma_desc_kmajor_k16(aux_addr[s]);
 #pragma unroll
-          for (int c = 0; c < NCHUNK; ++c) {
-            const uint64_t ad = umma_desc_kmajor_sw128(act_addr[s] + c * ACT_CHUNK);
-            const uint64_t bd = umma_desc_kmajor_sw128(rgb_addr + c * 2048);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tacc, ad + 2 * kk, bd + 2 * kk, idesc_r, (c | kk) != 0);
+            for (int h = 0; h < 2; ++h)
+              umma_bf16_ss(tacc + (uint32_t)h * 128u, umma_desc_kmajor_k16(wk_addr + h * 4096), bd, idesc_kk, 0u);
+          } else {
+            if (j == D + 2) {               // compositing: F^T[c][ray] = sum_p feat^T[c][p] * Wgt[ray][p]
+#pragma unroll 1
+              for (int h = 0; h < 2; ++h)
+#pragma unroll 2
+                for (int ks = 0; ks < 8; ++ks)
+                  umma_bf16_ss(tacc + (uint32_t)h * 16u,
+                               umma_desc_kmajor_sw128(act_addr[s] + (ks >> 2) * ACT_PBLOCK + h * 16384) + 2 * (ks & 3),
+                               umma_desc_kmajor_sw128(aux_addr[s] + (ks >> 2) * 2048) + 2 * (ks & 3), idesc_c, ks != 0);
+            }
+            const uint32_t dcol = (j == D + 2) ? 32u : 0u;    // heads: sdf (job D) / rgb (job D+2)
+#pragma unroll 2
+            for (int ks = 0; ks < 16; ++ks)
+              umma_bf16_ss(tacc + dcol, umma_desc_mnmajor_sw128(act_addr[s] + ks * 2048, ACT_PBLOCK),
+                           umma_desc_kmajor_sw128(heads_addr + (ks >> 2) * 2048) + 2 * (ks & 3), idesc_h, ks != 0);
           }
           umma_commit(&misc->acc_full[s]);
           jobcnt[s]++;
         }
       }
     }
+    if (prof && (blockIdx.x % 21 == 0 || blockIdx.x == 1)) {
+      C3D_PROF_ADD(t_issue);
+      printf("c3d prof mma[blk %d]: total %lld  wait_a_ready %lld  wait_full %lld  issue %lld  rounds %d\n", (int)blockIdx.x, clock64() - t_begin,
+             t_ready, t_full, t_issue, rounds);
+    }
+   }
   } else if (warp >= 4) {
-    // ============================================================ epilogue groups (thread = point row / channel)
-    const int s = (warp - 4) >> 2;
-    const int t = threadIdx.x - 128 - s * TILE;          // 0..127
+    // ============================================================ epilogue groups
+    const int s = (warp - 4) / kEgw;
+    const int te = threadIdx.x - 128 - s * EG_THREADS;   // 0..EG_THREADS-1
+    const int t = te & 127;                              // point row of the point stages; channel t (+128) of the layer stages
+    const bool pt_role = te < TILE;                      // the per-point stages run on the first four warps of the slot
     const int quad = warp & 3;
     const uint32_t bar_id = 1u + (uint32_t)s;
     const int slot = 2 * blockIdx.x + s;
-    uint8_t* act = smem + SM_ACT + s * ACT_BYTES;
-    uint8_t* act_row = act + t * 128;
-    const int row7 = t & 7;
-    float2* filmS = reinterpret_cast<float2*>(smem + SM_FILM) + s * 2 * W;
-    float4* tab0S = reinterpret_cast<float4*>(smem + SM_TAB0) + s * W;
-    float4* ptS = reinterpret_cast<float4*>(smem + SM_PT) + s * TILE;
-    const float* wsigS = reinterpret_cast<const float*>(smem + SM_WSIG);
+    uint8_t* aux = smem + SM_AUX + s * AUX_BYTES;
+    const uint32_t aux_u32 = smem_u32(aux);
     float* omS = reinterpret_cast<float*>(smem + SM_OM) + s * TILE;
-    int* flagS = reinterpret_cast<int*>(smem + SM_FLAG) + s * TILE;
-    float* rayacc = reinterpret_cast<float*>(smem + SM_RAYACC) + s * RSLOTS * 8;
+    float* rayacc = reinterpret_cast<float*>(smem + SM_RAYACC) + s * RAYS * 2 * 8;
     const uint32_t tacc = tmem_base + (uint32_t)s * 256u + ((uint32_t)(quad * 32) << 16);
     const float* scal = reinterpret_cast<const float*>(a.blob + a.L.scal);
     const float bsig = scal[0], brgb0 = scal[1], brgb1 = scal[2], brgb2 = scal[3];
     const float inv_beta = 1.0f / scal[4];
-    // view-layer state (thread = channel t and t+128)
-    uint32_t xoroff[8];
+    const uint32_t act_u32 = smem_u32(smem + SM_ACT + s * ACT_BYTES);
+    const int c7 = t & 7;
+    float carry_f[HPT];                                  // partial feature sums of a ray continuing into the next tile
 #pragma unroll
-    for (int jx = 0; jx < 8; ++jx) xoroff[jx] = (uint32_t)((((t & 63) >> 3) ^ jx) << 4) + (uint32_t)((t & 7) << 1);
-    float cur[2] = {0.f, 0.f}, shift_ray[2] = {0.f, 0.f};
+    for (int hh = 0; hh < HPT; ++hh) carry_f[hh] = 0.f;
+#ifdef C3D_KERNEL_PROF
+    const bool eprof = (a.debug & 2) != 0 && blockIdx.x == 0 && te == 0;
+#else
+    constexpr bool eprof = false;
+#endif
+    long long e_wait = 0, e_epi = 0, e_pt = 0, e_mark = clock64(), e_begin = e_mark;
+#define C3D_EPROF(acc) do { if (eprof) { const long long now_ = clock64(); acc += now_ - e_mark; e_mark = now_; } } while (0)
     uint32_t jobcnt = 0;
-    int cur_img = -1;
     const int total_units = a.batch * a.units_per_img;
 
     for (int u = slot; u < total_units; u += nslots) {
@@ -249,15 +311,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_kernel(const Args a
       const int ntiles = (npts + TILE - 1) / TILE;
       const float near = a.near[img], far = a.far[img];
       const float nscale = 2.0f / (far - near);
-      if (img != cur_img) {                        // layer-0 table of this image
-        named_bar_sync(bar_id, TILE);              // all readers of the previous table are done
-        tab0S[t] = a.first[(size_t)img * W + t];
-        tab0S[t + TILE] = a.first[(size_t)img * W + t + TILE];
-        cur_img = img;
-        named_bar_sync(bar_id, TILE);
-      }
       const float2* film_img = a.film + (size_t)img * (D + 1) * W;
-      cur[0] = cur[1] = 0.f;
+#pragma unroll
+      for (int hh = 0; hh < HPT; ++hh) carry_f[hh] = 0.f;
 
       for (int tile = 0; tile < ntiles; ++tile) {
         // ------------------------------------------------ geometry of my point (nerf_utils.py:17-170)
@@ -265,9 +321,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_kernel(const Args a
         const bool valid = q < npts;
         const int qc = valid ? q : npts - 1;
         const int rl = qc / N, k = qc - rl * N;
+        const int rl0 = (tile * TILE) / N;                // first ray touching this tile
         const size_t gray = (size_t)img * a.n_rays + r0 + rl;
-        float px, py, pz, vx, vy, vz, dist, zk;
-        if (a.input_kind == C3D_INPUT_POSES) {
+        float px = 0.f, py = 0.f, pz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, dist = 0.f, zk = 0.f;
+        if (!pt_role) {
+        } else if (a.input_kind == C3D_INPUT_POSES) {
           const RayGeom rg = make_ray(a.cam_poses + (size_t)img * 12, a.focal[img], a.img_size, r0 + rl, a.static_viewdirs != 0);
           const float uo = a.ray_offset ? a.ray_offset[gray] : 0.f;
           zk = sample_depth(near, far, k, N, uo);
@@ -285,129 +343,131 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_kernel(const Args a
           zk = a.z_vals[gray * N + k];
           dist = ((k + 1 < N) ? (a.z_vals[gray * N + k + 1] - zk) : 1e10f) * dn;
         }
-        if (a.z_vals_out && valid) a.z_vals_out[gray * N + k] = zk;
-        const float nx = px * nscale, ny = py * nscale, nz = pz * nscale;
-        float sdf = 0.f;
-
-        // ------------------------------------------------ layer 0 on the FP32 pipe (K = 3)
-#pragma unroll 4
-        for (int c8 = 0; c8 < 32; ++c8) {
-          float o[8];
+        if (pt_role && a.z_vals_out && valid) a.z_vals_out[gray * N + k] = zk;
+        const uint32_t aux_row = aux_u32 + (uint32_t)((t >> 3) * 256 + (t & 7) * 16);
+        if (pt_role) {
+          // point tile of the layer-0 MMA: per coordinate (hi, mid, hi, lo); k-slots 12..15 zero
+          const float pn[3] = {px * nscale, py * nscale, pz * nscale};
+          float e[12];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 tt = tab0S[c8 * 8 + i];
-            o[i] = __sinf(fmaf(tt.x, nx, fmaf(tt.y, ny, fmaf(tt.z, nz, tt.w))));
-            if (D == 1) sdf = fmaf(wsigS[c8 * 8 + i], o[i], sdf);
+          for (int jx = 0; jx < 3; ++jx) {
+            const float hi = __bfloat162float(__float2bfloat16_rn(pn[jx]));
+            const float r1 = pn[jx] - hi;
+            const float mid = __bfloat162float(__float2bfloat16_rn(r1));
+            const float lo = __bfloat162float(__float2bfloat16_rn(r1 - mid));
+            e[4 * jx + 0] = hi; e[4 * jx + 1] = mid; e[4 * jx + 2] = hi; e[4 * jx + 3] = lo;
           }
-          store8(act_row, row7, c8, o);
+          st_v4(aux_row, pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+          st_v4(aux_row + 128, pack_bf16x2(e[8], e[9]), pack_bf16x2(e[10], e[11]), 0u, 0u);
         }
-        // film table of the first MMA layer (hidden l=1, or the view layer when D == 1) is fetched below
-        fence_proxy_async_smem();
+        if (pt_role) fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&misc->a_ready[s]);
 
-        // ------------------------------------------------ hidden layers 1..D-1 (thread = point)
-        for (int l = 1; l < D; ++l) {
-          float2* fS = filmS + (l & 1) * W;
-          fS[t] = film_img[l * W + t];
-          fS[t + TILE] = film_img[l * W + t + TILE];
-          named_bar_sync(bar_id, TILE);
-          mbar_wait(&misc->acc_full[s], jobcnt & 1u);
-          jobcnt++;
-          tc_fence_after();
-          const bool last = (l == D - 1);
-          uint32_t v[2][32];
-          tmem_ld_32x32(tacc, v[0]);
-#pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
-            tmem_ld_wait();
-            if (cc + 1 < 8) tmem_ld_32x32(tacc + (cc + 1) * 32, v[(cc + 1) & 1]);
-            const uint32_t(&vv)[32] = v[cc & 1];
-#pragma unroll
-            for (int i8 = 0; i8 < 4; ++i8) {
-              float o[8];
-#pragma unroll
-              for (int i = 0; i < 8; i += 2) {
-                const int c = cc * 32 + i8 * 8 + i;
-                const float4 f = *reinterpret_cast<const float4*>(fS + c);   // (scale,shift) of c and c+1
-                o[i] = __sinf(fmaf(__uint_as_float(vv[i8 * 8 + i]), f.x, f.y));
-                o[i + 1] = __sinf(fmaf(__uint_as_float(vv[i8 * 8 + i + 1]), f.z, f.w));
-                if (last) sdf = fmaf(wsigS[c], o[i], fmaf(wsigS[c + 1], o[i + 1], sdf));
+        float sdf = 0.f, wgt = 0.f;
+        // ------------------------------------------------ layers 0..D (D = view layer): thread = channel t and t+128
+        for (int l = 0; l <= D; ++l) {
+          const float2 fa = film_img[l * W + t + (kEgw == 8 ? TILE * (te >> 7) : 0)];
+          const float2 fb = kEgw == 8 ? fa : film_img[l * W + t + TILE];
+          if (l == D) {
+            // ---------------------------------------------- sdf head (thread = point) -> alpha -> transmittance
+            mbar_wait(&misc->acc_full[s], jobcnt & 1u);
+            jobcnt++;
+            tc_fence_after();
+            if (pt_role) {
+              {
+                uint32_t v4[4];
+                tmem_ld_32x4(tacc + 4, v4);          // heads16 rows 4, 5: hi / lo part of sigma_linear.weight
+                tmem_ld_wait();
+                tc_fence_before();
+                sdf = __uint_as_float(v4[0]) + __uint_as_float(v4[1]) + bsig;
               }
-              store8(act_row, row7, cc * 4 + i8, o);
+              if (valid) a.sdf[gray * N + k] = sdf;
+              const float sigma = sigmoid_precise(-sdf * inv_beta) * inv_beta;
+              const float alpha = 1.0f - expf(-sigma * dist);
+              const float om = 1.0f - alpha + 1e-10f;
+              omS[t] = valid ? om : 1.0f;
+              // view-direction tile for the view-layer MMA (k-slots 12..14), reuses the point-tile buffer
+              st_v4(aux_row, 0u, 0u, 0u, 0u);
+              st_v4(aux_row + 128, 0u, 0u, pack_bf16x2(vx, vy), pack_bf16x2(vz, 0.f));
+              named_bar_sync(bar_id, TILE);
+              const int first_row = t - k;
+              float T = first_row < 0 ? misc->carry[s] : 1.0f;
+              for (int m = max(first_row, 0); m < t; ++m) T *= omS[m];
+              wgt = valid ? alpha * T : 0.f;
+              named_bar_sync(bar_id, TILE);
+              if (t == TILE - 1) misc->carry[s] = (k == N - 1) ? 1.0f : T * om;
+              fence_proxy_async_smem();
             }
+            mbar_arrive(&misc->a_ready[s]);
           }
-          tc_fence_before();
-          fence_proxy_async_smem();
-          mbar_arrive(&misc->a_ready[s]);
-        }
-
-        // ------------------------------------------------ density -> alpha -> transmittance (nerf_utils.py:267-307)
-        sdf += bsig;
-        if (valid) a.sdf[gray * N + k] = sdf;
-        const float sigma = sigmoid_precise(-sdf * inv_beta) * inv_beta;
-        const float alpha = 1.0f - expf(-sigma * dist);
-        const float om = 1.0f - alpha + 1e-10f;
-        omS[t] = valid ? om : 1.0f;
-        named_bar_sync(bar_id, TILE);
-        const int first_row = t - k;               // row of sample 0 of my ray (negative: began in an earlier tile)
-        float T = first_row < 0 ? misc->carry[s] : 1.0f;
-        for (int m = max(first_row, 0); m < t; ++m) T *= omS[m];
-        const float wgt = valid ? alpha * T : 0.f;
-        ptS[t] = make_float4(wgt, vx, vy, vz);
-        flagS[t] = (rl << 3) | (valid ? 4 : 0) | ((valid && k == N - 1) ? 2 : 0) | ((valid && k == 0) ? 1 : 0);
-        named_bar_sync(bar_id, TILE);
-        if (t == TILE - 1) misc->carry[s] = (k == N - 1) ? 1.0f : T * om;
-
-        // ------------------------------------------------ view layer (thread = channel), features composited in registers
-        {
-          const float2 f0 = film_img[D * W + t], f1 = film_img[D * W + t + TILE];
-          const float4 tv0 = a.view[(size_t)img * W + t], tv1 = a.view[(size_t)img * W + t + TILE];
+          C3D_EPROF(e_pt);
           mbar_wait(&misc->acc_full[s], jobcnt & 1u);
+          C3D_EPROF(e_wait);
           jobcnt++;
           tc_fence_after();
+          if (l == D && pt_role) {
+            // the view-direction tile has been consumed: build Wgt[ray slot][point] (bf16, K-major SW128) in its place
+            const int myslot = rl - rl0;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const float scale = h ? f1.x : f0.x, shift0 = h ? f1.y : f0.y;
-            const float4 tv = h ? tv1 : tv0;
-            float cu = cur[h], sr = shift_ray[h];
-            float* fout = a.feature_map + ((size_t)img * a.n_rays + r0) * W + t + h * TILE;
-            uint8_t* abase = act + ((t + h * TILE) >> 6) * ACT_CHUNK;
-            uint32_t v[2][32];
-            tmem_ld_32x32(tacc + h * 128, v[0]);
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int jx = 0; jx < RAYS; ++jx)
+              st_bf16(aux_u32 + (uint32_t)((t >> 6) * 2048) + sw128_offset(jx, t & 63), jx == myslot ? wgt : 0.f);
+          }
+#pragma unroll 1
+          for (int hh = 0; hh < HPT; ++hh) {
+            // my channel (lane `t` of accumulator half h), 128 points in 8 chunks of 16, TMEM loads double-buffered
+            const int h = kEgw == 8 ? (te >> 7) : hh;
+            const uint32_t tcol = tacc + (uint32_t)h * 128u;
+            const uint32_t row_u32 = act_u32 + (uint32_t)(t + TILE * h) * 128u;
+            uint32_t v0[16], v1[16];
+            tmem_ld_32x16(tcol, v0);
+#pragma unroll 2
+            for (int cp = 0; cp < 4; ++cp) {               // 32 points per iteration
+              const uint32_t row = row_u32 + (uint32_t)(cp >> 1) * ACT_PBLOCK;
               tmem_ld_wait();
-              if (cc + 1 < 4) tmem_ld_32x32(tacc + h * 128 + (cc + 1) * 32, v[(cc + 1) & 1]);
-              const uint32_t(&vv)[32] = v[cc & 1];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const int p = cc * 32 + i;
-                const float4 pw = ptS[p];
-                const int fl = flagS[p];
-                if (fl & 1) sr = fmaf(tv.x, pw.y, fmaf(tv.y, pw.z, fmaf(tv.z, pw.w, shift0)));
-                const float feat = __sinf(fmaf(__uint_as_float(vv[i]), scale, sr));
-                cu = fmaf(pw.x, feat, cu);
-                *reinterpret_cast<__nv_bfloat16*>(abase + p * 128 + xoroff[p & 7]) = __float2bfloat16_rn(feat);
-                if (fl & 2) { fout[(size_t)(fl >> 3) * W] = cu; cu = 0.f; }
-              }
+              tmem_ld_32x16(tcol + cp * 32 + 16, v1);
+              epilogue16(v0, hh ? fb.x : fa.x, hh ? fb.y : fa.y, row, (cp & 1) * 4, c7);
+              tmem_ld_wait();
+              if (cp < 3) tmem_ld_32x16(tcol + (cp + 1) * 32, v0);
+              epilogue16(v1, hh ? fb.x : fa.x, hh ? fb.y : fa.y, row, (cp & 1) * 4 + 2, c7);
             }
-            cur[h] = cu; shift_ray[h] = sr;
           }
           tc_fence_before();
           fence_proxy_async_smem();
           mbar_arrive(&misc->a_ready[s]);
+          C3D_EPROF(e_epi);
         }
 
-        // ------------------------------------------------ rgb head + per-ray sums (nerf_utils.py:315,329-336)
+        // ------------------------------------------------ post job: composited features (thread = channel) + rgb (thread = point)
         {
           mbar_wait(&misc->acc_full[s], jobcnt & 1u);
           jobcnt++;
           tc_fence_after();
           uint32_t v4[4];
-          tmem_ld_32x4(tacc, v4);
+          tmem_ld_32x4(tacc + 32, v4);                   // raw rgb of my point (point-role threads)
+          const int tile_end = min((tile + 1) * TILE, npts);      // first point index beyond this tile
+#pragma unroll
+          for (int hh = 0; hh < HPT; ++hh) {
+            const int h = kEgw == 8 ? (te >> 7) : hh;
+            uint32_t fv[16];
+            tmem_ld_32x16(tacc + (uint32_t)h * 16u, fv);   // composited features of my channel; column = ray slot
+            tmem_ld_wait();
+            float* fbase = a.feature_map + ((size_t)img * a.n_rays + r0 + rl0) * W + t + TILE * h;
+#pragma unroll
+            for (int jx = 0; jx < RAYS; ++jx) {
+              const int rbeg = (rl0 + jx) * N, rend = rbeg + N;      // point range of ray slot jx inside the unit
+              if (rbeg < tile_end) {                                  // uniform: the slot is in use
+                float fvv = __uint_as_float(fv[jx]);
+                if (jx == 0) fvv += carry_f[hh];
+                if (rend <= tile_end) fbase[(size_t)jx * W] = fvv;    // ray complete
+                if (rend >= tile_end) carry_f[hh] = rend > tile_end ? fvv : 0.f;   // last slot of the tile
+              }
+            }
+          }
           tmem_ld_wait();
           tc_fence_before();
+          if (pt_role) {
+          // rgb / xyz / mask sums of my ray (nerf_utils.py:315,329-336)
           float vals[6];
           vals[0] = wgt * sigmoid_precise(__uint_as_float(v4[0]) + brgb0);
           vals[1] = wgt * sigmoid_precise(__uint_as_float(v4[1]) + brgb1);
@@ -418,16 +478,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_kernel(const Args a
             const int rid = __shfl_down_sync(0xffffffffu, rl, o);
             const bool same = (lane + o < 32) && (rid == rl);
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
-              const float y = __shfl_down_sync(0xffffffffu, vals[j], o);
-              if (same) vals[j] += y;
+            for (int jx = 0; jx < 6; ++jx) {
+              const float y = __shfl_down_sync(0xffffffffu, vals[jx], o);
+              if (same) vals[jx] += y;
             }
           }
           const int rprev = __shfl_up_sync(0xffffffffu, rl, 1);
-          float* racc = rayacc + (rl & (RSLOTS - 1)) * 8;
+          float* racc = rayacc + (rl & (2 * RAYS - 1)) * 8;
           if (valid && (lane == 0 || rprev != rl)) {
 #pragma unroll
-            for (int j = 0; j < 6; ++j) atomicAdd(racc + j, vals[j]);
+            for (int jx = 0; jx < 6; ++jx) atomicAdd(racc + jx, vals[jx]);
           }
           named_bar_sync(bar_id, TILE);
           if (valid && k == N - 1) {
@@ -439,69 +499,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_kernel(const Args a
             a.mask[gray * 2 + 0] = wgt;
             a.mask[gray * 2 + 1] = -sqrtf(x * x + y * y + z * z);
 #pragma unroll
-            for (int j = 0; j < 6; ++j) racc[j] = 0.f;
+            for (int jx = 0; jx < 6; ++jx) racc[jx] = 0.f;
+          }
           }
         }
       }  // tiles
     }    // units
+    if (eprof) {
+      C3D_EPROF(e_pt);
+      printf("c3d prof eg(slot %d): total %lld  wait_acc_full(layers) %lld  epilogue %lld  other(point stages, sdf/post waits) %lld\n",
+             s, clock64() - e_begin, e_wait, e_epi, e_pt);
+    }
   }
 
-  // ---------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
   if (kCluster > 1) cluster_sync_all();
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
-}
-
-// ------------------------------------------------------------------------------------------
-// Self-test tile product through the same descriptors / layouts:  D[128][N] = A[128][K] * B[N][K]^T
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B,
-                                                                float* __restrict__ Dout, int N, int K) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;                       // K/64 chunks x [128][64]
-  uint8_t* sB = smem + ACT_BYTES;           // K/64 chunks x [N][64]
-  __shared__ uint64_t bar;
-  __shared__ uint32_t tbase;
-  const int warp = threadIdx.x >> 5;
-  const int nchunk = K / 64;
-  for (int idx = threadIdx.x; idx < 128 * K; idx += 128) {
-    const int r = idx / K, k = idx - r * K;
-    *reinterpret_cast<uint16_t*>(sA + (k >> 6) * ACT_CHUNK + sw128_offset(r, k & 63)) = A[idx];
-  }
-  for (int idx = threadIdx.x; idx < N * K; idx += 128) {
-    const int r = idx / K, k = idx - r * K;
-    *reinterpret_cast<uint16_t*>(sB + (k >> 6) * (N * 128) + sw128_offset(r, k & 63)) = B[idx];
-  }
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
-  if (warp == 1) { tmem_alloc(&tbase, 256); tmem_relinquish(); }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tb = tbase;
-  if (threadIdx.x == 0) {
-    const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)N);
-    for (int c = 0; c < nchunk; ++c) {
-      const uint64_t ad = umma_desc_kmajor_sw128(smem_u32(sA + c * ACT_CHUNK));
-      const uint64_t bd = umma_desc_kmajor_sw128(smem_u32(sB + c * (N * 128)));
-      for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tb, ad + 2 * kk, bd + 2 * kk, idesc, (c | kk) != 0);
-    }
-    umma_commit(&bar);
-  }
-  mbar_wait(&bar, 0);
-  tc_fence_after();
-  const uint32_t taddr = tb + ((uint32_t)(warp * 32) << 16);
-  for (int c0 = 0; c0 < N; c0 += 4) {
-    uint32_t v4[4];
-    tmem_ld_32x4(taddr + c0, v4);
-    tmem_ld_wait();
-    for (int j = 0; j < 4; ++j) Dout[(size_t)threadIdx.x * N + c0 + j] = __uint_as_float(v4[j]);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tb, 256); }
 }
 
 }}  // namespace c3d::fused
