@@ -206,6 +206,7 @@ static int forward_fp32(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
     m.n_samples = p->n_samples; m.pts_per_img = (int)P; m.tiles_per_img = (int)((P + F32_TP - 1) / F32_TP);
     m.feat = reinterpret_cast<float*>(ck + w.c_feat); m.rgb = reinterpret_cast<float*>(ck + w.c_rgb);
     m.sdf = p->sdf + (size_t)i0 * P;
+    m.save_acc = nullptr; m.save_stride = 0;
     mlp_fp32_kernel<<<(unsigned)(ni * m.tiles_per_img), 256, F32_SMEM, st>>>(m);
     C3D_LAUNCH_CHECK();
     c3d_composite_params c;
@@ -349,14 +350,202 @@ int c3d_umma_selftest(const uint16_t* a, const uint16_t* b, float* d, int32_t N,
 
 }  // extern "C"
 
+namespace c3d {
+
+struct BwdWs {
+  size_t film, first, view, g_film, chunk, total;
+  int chunk_imgs;
+  size_t c_acc, c_feat, c_rgb, c_sdf, c_w, c_grgb, c_gsdf, c_pts, c_rd, c_vd, c_z, c_gpts, c_grd, c_gvd;
+};
+static BwdWs bwd_ws(const c3d_bwd_params* bp) {
+  const c3d_fwd_params* p = &bp->fwd;
+  BwdWs w;
+  memset(&w, 0, sizeof(w));
+  size_t o = 0;
+  const size_t b = (size_t)p->batch, P = (size_t)p->n_rays * p->n_samples, R = (size_t)p->n_rays, D = (size_t)p->D;
+  w.film = o;   o += align_up(b * (D + 1) * W * sizeof(float2), 256);
+  w.first = o;  o += align_up(b * W * sizeof(float4), 256);
+  w.view = o;   o += align_up(b * W * sizeof(float4), 256);
+  w.g_film = o; o += align_up(b * (D + 1) * W * sizeof(float2), 256);
+  w.chunk = o;
+  const bool poses = p->input_kind == C3D_INPUT_POSES;
+  const size_t per_img = P * (D + 1) * W * 4 + P * (12 + 4 + 4 + 12 + 4) + P * 12 + 2 * R * 12 +
+                         (poses ? P * 12 + 2 * R * 12 + P * 4 : 0) + 4096;
+  size_t ci = ((size_t)2 << 30) / per_img;
+  if (ci < 1) ci = 1;
+  if (ci > b) ci = b;
+  w.chunk_imgs = (int)ci;
+  size_t c = 0;
+  w.c_acc = c;  c += align_up(ci * P * D * W * 4, 256);
+  w.c_feat = c; c += align_up(ci * P * W * 4, 256);
+  w.c_rgb = c;  c += align_up(ci * P * 12, 256);
+  w.c_sdf = c;  c += align_up(ci * P * 4, 256);
+  w.c_w = c;    c += align_up(ci * P * 4, 256);
+  w.c_grgb = c; c += align_up(ci * P * 12, 256);
+  w.c_gsdf = c; c += align_up(ci * P * 4, 256);
+  w.c_gpts = c; c += align_up(ci * P * 12, 256);      // scratch when the caller does not ask for g_pts / POSES mode
+  w.c_grd = c;  c += align_up(ci * R * 12, 256);
+  w.c_gvd = c;  c += align_up(ci * R * 12, 256);
+  if (poses) {
+    w.c_pts = c; c += align_up(ci * P * 12, 256);
+    w.c_rd = c;  c += align_up(ci * R * 12, 256);
+    w.c_vd = c;  c += align_up(ci * R * 12, 256);
+    w.c_z = c;   c += align_up(ci * P * 4, 256);
+  }
+  w.total = o + c;
+  return w;
+}
+
+static int validate_bwd(const c3d_bwd_params* bp) {
+  C3D_CHECK_ARG(bp != nullptr, "params is NULL");
+  const c3d_fwd_params* p = &bp->fwd;
+  C3D_CHECK_ARG(p->abi_version == C3D_ABI_VERSION, "abi_version %d != library %d", p->abi_version, C3D_ABI_VERSION);
+  C3D_CHECK_ARG(p->input_kind == C3D_INPUT_POSES || p->input_kind == C3D_INPUT_POINTS, "bad input_kind %d", p->input_kind);
+  C3D_CHECK_ARG(p->batch >= 1 && p->n_rays >= 1, "batch=%d n_rays=%d must be >= 1", p->batch, p->n_rays);
+  C3D_CHECK_ARG(p->n_samples >= 2 && p->n_samples <= 256, "n_samples=%d outside [2,256]", p->n_samples);
+  C3D_CHECK_ARG(p->D >= 1 && p->D <= C3D_MAX_LAYERS, "D=%d outside [1,%d]", p->D, C3D_MAX_LAYERS);
+  C3D_CHECK_ARG((long long)p->batch * p->n_rays * p->n_samples < (1ll << 31), "batch*n_rays*n_samples overflows int32");
+  C3D_CHECK_ARG(p->packed && p->styles && p->near && p->far, "packed/styles/near/far must be non-NULL");
+  C3D_CHECK_ARG(p->feat_layout == C3D_FEAT_NHWC, "backward takes g_feature_map in (b,hw,256) layout");
+  if (p->input_kind == C3D_INPUT_POSES) {
+    C3D_CHECK_ARG(p->cam_poses && p->focal, "POSES input needs cam_poses and focal");
+    C3D_CHECK_ARG(p->img_size >= 1 && p->n_rays == p->img_size * p->img_size, "n_rays=%d != img_size^2", p->n_rays);
+  } else {
+    C3D_CHECK_ARG(p->pts && p->rays_d && p->viewdirs && p->z_vals, "POINTS input needs pts, rays_d, viewdirs, z_vals");
+  }
+  const BwdWs w = bwd_ws(bp);
+  C3D_CHECK_ARG(p->workspace && p->workspace_bytes >= w.total, "workspace too small: %zu < %zu", p->workspace_bytes, w.total);
+  C3D_CHECK_ARG(aligned16(p->workspace) && aligned16(bp->g_feature_map), "workspace / g_feature_map must be 16-byte aligned");
+  return C3D_OK;
+}
+
+}  // namespace c3d
+
 extern "C" {
-size_t c3d_backward_workspace_bytes(const c3d_bwd_params* p) { (void)p; return 0; }
-int c3d_nerf_backward(const c3d_bwd_params* p, c3d_stream_t stream) {
-  (void)p; (void)stream;
-  return c3d::fail(C3D_ERR_UNSUPPORTED, "c3d_nerf_backward: not built in this revision");
+
+size_t c3d_backward_workspace_bytes(const c3d_bwd_params* p) {
+  if (!p || p->fwd.batch < 1 || p->fwd.n_rays < 1 || p->fwd.n_samples < 1 || p->fwd.D < 1) return 0;
+  return bwd_ws(p).total;
 }
+
+int c3d_nerf_backward(const c3d_bwd_params* bp, c3d_stream_t stream) {
+  g_launches = 0;
+  int rc = validate_bwd(bp);
+  if (rc != C3D_OK) return rc;
+  const c3d_fwd_params* p = &bp->fwd;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const BwdWs w = bwd_ws(bp);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(p->workspace);
+  uint8_t* ck = ws + w.chunk;
+  const size_t P = (size_t)p->n_rays * p->n_samples, R = (size_t)p->n_rays;
+  const int D = p->D;
+  const PackedLayout L = packed_layout(D);
+  const bool poses = p->input_kind == C3D_INPUT_POSES;
+  float2* film = reinterpret_cast<float2*>(ws + w.film);
+  float4* view = reinterpret_cast<float4*>(ws + w.view);
+  float* g_film = reinterpret_cast<float*>(ws + w.g_film);
+  rc = launch_style_prep(p->packed, D, p->styles, p->batch, reinterpret_cast<float*>(film),
+                         reinterpret_cast<float*>(ws + w.first), reinterpret_cast<float*>(view), st);
+  if (rc != C3D_OK) return rc;
+  C3D_CUDA(cudaMemsetAsync(g_film, 0, (size_t)p->batch * (D + 1) * W * sizeof(float2), st));
+  C3D_CUDA(cudaFuncSetAttribute(mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F32_SMEM));
+  C3D_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
+  const float* beta_ptr = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p->packed) + L.scal) + 4;
+  for (int i0 = 0; i0 < p->batch; i0 += w.chunk_imgs) {
+    const int ni = (p->batch - i0 < w.chunk_imgs) ? p->batch - i0 : w.chunk_imgs;
+    const float *pts, *rays_d, *viewdirs, *z_vals;
+    c3d_raygen_params rg;
+    memset(&rg, 0, sizeof(rg));
+    if (poses) {
+      rg.batch = ni; rg.img_size = p->img_size; rg.n_samples = p->n_samples; rg.static_viewdirs = p->static_viewdirs;
+      rg.cam_poses = p->cam_poses + (size_t)i0 * 12; rg.focal = p->focal + i0; rg.near = p->near + i0; rg.far = p->far + i0;
+      rg.ray_offset = p->ray_offset ? p->ray_offset + (size_t)i0 * R : nullptr;
+      rg.pts = reinterpret_cast<float*>(ck + w.c_pts); rg.rays_d = reinterpret_cast<float*>(ck + w.c_rd);
+      rg.viewdirs = reinterpret_cast<float*>(ck + w.c_vd); rg.z_vals = reinterpret_cast<float*>(ck + w.c_z);
+      const long long n = (long long)ni * R;
+      raygen_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(rg);
+      C3D_LAUNCH_CHECK();
+      pts = rg.pts; rays_d = rg.rays_d; viewdirs = rg.viewdirs; z_vals = rg.z_vals;
+    } else {
+      pts = p->pts + (size_t)i0 * P * 3; rays_d = p->rays_d + (size_t)i0 * R * 3;
+      viewdirs = p->viewdirs + (size_t)i0 * R * 3; z_vals = p->z_vals + (size_t)i0 * P;
+    }
+    // gradient destinations of this chunk (scratch when the caller passed NULL, always scratch in POSES mode)
+    float* g_pts = (!poses && bp->g_pts) ? bp->g_pts + (size_t)i0 * P * 3 : reinterpret_cast<float*>(ck + w.c_gpts);
+    float* g_rd = (!poses && bp->g_rays_d) ? bp->g_rays_d + (size_t)i0 * R * 3 : reinterpret_cast<float*>(ck + w.c_grd);
+    float* g_vd = (!poses && bp->g_viewdirs) ? bp->g_viewdirs + (size_t)i0 * R * 3 : reinterpret_cast<float*>(ck + w.c_gvd);
+    C3D_CUDA(cudaMemsetAsync(g_vd, 0, (size_t)ni * R * 12, st));
+    // 1. forward recompute with saved accumulators
+    MlpF32Args m;
+    m.blob = reinterpret_cast<const uint8_t*>(p->packed); m.L = L;
+    m.film = film + (size_t)i0 * (D + 1) * W;
+    m.first = reinterpret_cast<const float4*>(ws + w.first) + (size_t)i0 * W;
+    m.view = view + (size_t)i0 * W;
+    m.pts = pts; m.viewdirs = viewdirs; m.near = p->near + i0; m.far = p->far + i0;
+    m.n_samples = p->n_samples; m.pts_per_img = (int)P; m.tiles_per_img = (int)((P + F32_TP - 1) / F32_TP);
+    m.feat = reinterpret_cast<float*>(ck + w.c_feat); m.rgb = reinterpret_cast<float*>(ck + w.c_rgb);
+    m.sdf = reinterpret_cast<float*>(ck + w.c_sdf);
+    m.save_acc = reinterpret_cast<float*>(ck + w.c_acc); m.save_stride = (size_t)ni * P * W;
+    mlp_fp32_kernel<<<(unsigned)(ni * m.tiles_per_img), 256, F32_SMEM, st>>>(m);
+    C3D_LAUNCH_CHECK();
+    // 2. compositing backward
+    CompositeBwdArgs c;
+    memset(&c, 0, sizeof(c));
+    c.n_rays = (long long)ni * R; c.n_samples = p->n_samples; c.n_feat = W; c.sigmoid_beta_ptr = beta_ptr;
+    c.rgb = m.rgb; c.sdf = m.sdf; c.features = m.feat; c.z_vals = z_vals; c.rays_d = rays_d; c.pts = pts;
+    c.g_rgb_map = bp->g_rgb_map ? bp->g_rgb_map + (size_t)i0 * R * 3 : nullptr;
+    c.g_feature_map = bp->g_feature_map ? bp->g_feature_map + (size_t)i0 * R * W : nullptr;
+    c.g_xyz = bp->g_xyz ? bp->g_xyz + (size_t)i0 * R * 3 : nullptr;
+    c.g_mask = bp->g_mask ? bp->g_mask + (size_t)i0 * R * 2 : nullptr;
+    c.g_sdf_in = bp->g_sdf ? bp->g_sdf + (size_t)i0 * P : nullptr;
+    c.weights = reinterpret_cast<float*>(ck + w.c_w); c.g_rgb = reinterpret_cast<float*>(ck + w.c_grgb);
+    c.g_sdf = reinterpret_cast<float*>(ck + w.c_gsdf); c.g_features = nullptr;
+    c.g_pts = g_pts; c.g_rays_d = g_rd;
+    composite_bwd_kernel<<<(unsigned)((c.n_rays + 7) / 8), 256, 0, st>>>(c);
+    C3D_LAUNCH_CHECK();
+    // 3. MLP backward
+    MlpBwdArgs mb;
+    mb.blob = m.blob; mb.L = L; mb.film = m.film; mb.view = m.view;
+    mb.pts = pts; mb.viewdirs = viewdirs; mb.near = m.near; mb.far = m.far;
+    mb.n_samples = p->n_samples; mb.pts_per_img = (int)P; mb.tiles_per_img = m.tiles_per_img;
+    mb.save_acc = m.save_acc; mb.save_stride = m.save_stride;
+    mb.weights = c.weights; mb.g_feature_map = c.g_feature_map; mb.g_rgb = c.g_rgb; mb.g_sdf = c.g_sdf;
+    mb.g_film = g_film + (size_t)i0 * (D + 1) * W * 2; mb.g_pts = g_pts; mb.g_viewdirs = g_vd;
+    mlp_bwd_kernel<<<(unsigned)(ni * mb.tiles_per_img), 256, BWD_SMEM, st>>>(mb);
+    C3D_LAUNCH_CHECK();
+    // 4. POSES entry: chain to the camera
+    if (poses && (bp->g_cam_poses || bp->g_focal)) {
+      dim3 grid((unsigned)((R + 127) / 128), ni);
+      raygen_bwd_kernel<<<grid, 128, 0, st>>>(rg, g_pts, g_rd, g_vd, bp->g_cam_poses ? bp->g_cam_poses + (size_t)i0 * 12 : nullptr,
+                                              bp->g_focal ? bp->g_focal + i0 : nullptr);
+      C3D_LAUNCH_CHECK();
+    }
+  }
+  if (bp->g_styles) {
+    film_bwd_kernel<<<dim3(D + 1, p->batch), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(p->packed), L, g_film, bp->g_styles);
+    C3D_LAUNCH_CHECK();
+  }
+  return C3D_OK;
+}
+
 int c3d_composite_backward(const c3d_composite_params* p, c3d_stream_t stream) {
-  (void)p; (void)stream;
-  return c3d::fail(C3D_ERR_UNSUPPORTED, "c3d_composite_backward: not built in this revision");
+  C3D_CHECK_ARG(p && p->n_rays >= 1, "n_rays must be >= 1");
+  C3D_CHECK_ARG(p->n_samples >= 1 && p->n_samples <= CMP_MAX_N, "n_samples=%d outside [1,%d]", p->n_samples, CMP_MAX_N);
+  C3D_CHECK_ARG(p->n_feat >= 0 && p->n_feat % 4 == 0, "n_feat=%d must be a multiple of 4", p->n_feat);
+  C3D_CHECK_ARG(p->rgb && p->sdf && p->z_vals && p->rays_d && p->pts, "rgb/sdf/z_vals/rays_d/pts must be non-NULL");
+  C3D_CHECK_ARG(p->sigmoid_beta_ptr, "composite backward needs sigmoid_beta_ptr (device scalar)");
+  C3D_CHECK_ARG(p->weights && p->g_rgb && p->g_sdf && p->g_pts && p->g_rays_d, "weights/g_rgb/g_sdf/g_pts/g_rays_d outputs are required");
+  C3D_CHECK_ARG(!p->features || !p->g_feature_map || p->g_features, "g_features output missing");
+  CompositeBwdArgs c;
+  memset(&c, 0, sizeof(c));
+  c.n_rays = p->n_rays; c.n_samples = p->n_samples; c.n_feat = p->n_feat; c.sigmoid_beta_ptr = p->sigmoid_beta_ptr;
+  c.rgb = p->rgb; c.sdf = p->sdf; c.features = p->features; c.z_vals = p->z_vals; c.rays_d = p->rays_d; c.pts = p->pts;
+  c.g_rgb_map = p->g_rgb_map; c.g_feature_map = p->g_feature_map; c.g_xyz = p->g_xyz; c.g_mask = p->g_mask;
+  c.weights = p->weights; c.g_rgb = p->g_rgb; c.g_sdf = p->g_sdf; c.g_features = p->g_features; c.g_pts = p->g_pts;
+  c.g_rays_d = p->g_rays_d;
+  composite_bwd_kernel<<<(unsigned)((p->n_rays + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(c);
+  C3D_LAUNCH_CHECK();
+  return C3D_OK;
 }
-}
+
+}  // extern "C"

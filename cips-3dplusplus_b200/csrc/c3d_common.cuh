@@ -27,6 +27,7 @@ constexpr int NCHUNK = W / KCHUNK;  // 4 K-chunks per layer
 //   scal     : float[8]         bsig, brgb[0..2], sigmoid_beta
 //   film     : per layer l<=D:  GwT[256 k][256 c], BwT[256 k][256 c], gb[256], bb[256]
 //   wT32     : per layer l in 1..D: WT[256 k][256 c] fp32 (view layer: columns 0..255 only)
+//   w32      : per layer l in 1..D: W[256 c][256 k] fp32, reference orientation (backward GEMMs contract over c)
 //   wbf16    : per layer l in 1..D: 4 K-chunks x [256 n][64 k] bf16, rows of 128 B, 16-byte units
 //              XOR-swizzled with (n & 7)  == UMMA K-major SWIZZLE_128B image of the smem stage
 //   heads16  : 4 K-chunks x [16 n][64 k] bf16, same swizzle: rows 0..2 = Wrgb, row 4 / 5 = hi / lo bf16 split
@@ -38,7 +39,7 @@ constexpr int NCHUNK = W / KCHUNK;  // 4 K-chunks per layer
 //              view-direction tile; slot 15 zero.  The point tile zeroes 12..15, the view tile zeroes 0..11.
 // ------------------------------------------------------------------------------------------
 struct PackedLayout {
-  size_t w0, wvdir, bias, wsig, wrgb, scal, film, wT32, wbf16, rgb16, w0img, total;
+  size_t w0, wvdir, bias, wsig, wrgb, scal, film, wT32, w32, wbf16, rgb16, w0img, total;
   int D;
 };
 constexpr size_t FILM_LAYER_FLOATS = 2 * (size_t)W * W + 2 * W;
@@ -61,6 +62,7 @@ __host__ __device__ inline PackedLayout packed_layout(int D) {
   L.scal = o;  o += 256;
   L.film = o;  o += sizeof(float) * FILM_LAYER_FLOATS * (size_t)(D + 1);
   L.wT32 = o;  o += sizeof(float) * (size_t)W * W * (size_t)D;
+  L.w32 = o;   o += sizeof(float) * (size_t)W * W * (size_t)D;
   o = align_up(o, 1024);
   L.wbf16 = o; o += WBF16_LAYER_BYTES * (size_t)D;
   L.rgb16 = o; o += RGB16_BYTES;

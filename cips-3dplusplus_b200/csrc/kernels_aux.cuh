@@ -88,6 +88,8 @@ __global__ void pack_matrix_kernel(c3d_raw_params raw, uint8_t* __restrict__ blo
     } else {
       float* dst = reinterpret_cast<float*>(blob + L.wT32) + (size_t)(l - 1) * W * W;
       for (int i = threadIdx.y; i < 32; i += 8) dst[(size_t)(c0 + i) * W + r0 + threadIdx.x] = tile[threadIdx.x][i];
+      float* dsn = reinterpret_cast<float*>(blob + L.w32) + (size_t)(l - 1) * W * W;
+      for (int i = threadIdx.y; i < 32; i += 8) dsn[(size_t)(r0 + i) * W + c0 + threadIdx.x] = tile[i][threadIdx.x];
       uint8_t* img = blob + L.wbf16 + (size_t)(l - 1) * WBF16_LAYER_BYTES;
       for (int i = threadIdx.y; i < 32; i += 8) {
         const int n = r0 + i, k = c0 + threadIdx.x;

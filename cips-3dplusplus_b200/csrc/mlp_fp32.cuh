@@ -24,6 +24,8 @@ struct MlpF32Args {
   float* feat;             // (imgs*pts_per_img, 256)
   float* rgb;              // (imgs*pts_per_img, 3)
   float* sdf;              // (imgs*pts_per_img)
+  float* save_acc;         // optional: (D, imgs*pts_per_img, 256) pre-FiLM accumulators of layers 1..D (backward)
+  size_t save_stride;      // imgs*pts_per_img*256
 };
 
 __device__ __forceinline__ void f32_gemm_layer(const float* __restrict__ WT /*[256 k][256 c] global*/,
@@ -103,8 +105,22 @@ __global__ void __launch_bounds__(256, 1) mlp_fp32_kernel(MlpF32Args a) {
   }
   float acc[8][8];
   const float* WT = reinterpret_cast<const float*>(a.blob + a.L.wT32);
+  auto save = [&](int l) {
+    if (!a.save_acc) return;
+    float* base = a.save_acc + (size_t)(l - 1) * a.save_stride;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int p = p0 + ty * 8 + i;
+      if (p < a.pts_per_img) {
+        float4* o = reinterpret_cast<float4*>(base + (img_pt0 + p) * W);
+        o[tx] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        o[32 + tx] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+      }
+    }
+  };
   for (int l = 1; l < D; ++l) {
     f32_gemm_layer(WT + (size_t)(l - 1) * W * W, actT, wS, acc, tx, ty);
+    save(l);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float2 f = a.film[((size_t)img * (D + 1) + l) * W + ch[j]];
@@ -131,6 +147,7 @@ __global__ void __launch_bounds__(256, 1) mlp_fp32_kernel(MlpF32Args a) {
   }
   // view layer (volume_renderer.py:151-152): K = 256 through the stage + 3 view-direction columns
   f32_gemm_layer(WT + (size_t)(D - 1) * W * W, actT, wS, acc, tx, ty);
+  save(D);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float2 f = a.film[((size_t)img * (D + 1) + D) * W + ch[j]];

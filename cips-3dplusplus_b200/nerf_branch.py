@@ -223,36 +223,43 @@ class NerfBranch(nn.Module):
 
     def _launch_backward(self, kind, meta, styles, a0, a1, a2, a3, near, far, g_rgb, g_feat, g_sdf, g_mask, g_xyz,
                          needs):
+        """c3d_nerf_backward: recomputes the forward in fp32 and returns gradients for styles and the geometric
+        inputs (POINTS: pts, rays_d, viewdirs; POSES: cam_poses, focal)."""
         lib = _abi.load()
         dev = styles.device
+        b, n_rays, N, img_size, static_viewdirs, nchw = meta
+        if any(needs[10:]):
+            raise NotImplementedError("gradients w.r.t. the renderer weights are not provided by libc3dpp (flip "
+                                      "inversion optimises latents and cameras); call renderer.requires_grad_(False)")
+        if nchw and g_feat is not None:
+            g_feat = g_feat.transpose(1, 2)
         B = _abi.BwdParams()
-        self._fill_common(B.fwd, kind, meta, styles, a0, a1, a2, a3, near, far)
+        self._fill_common(B.fwd, kind, (b, n_rays, N, img_size, static_viewdirs, False), styles, a0, a1, a2, a3, near, far)
         cot = [None if g is None else g.to(torch.float32).contiguous() for g in (g_rgb, g_feat, g_mask, g_xyz, g_sdf)]
         B.g_rgb_map, B.g_feature_map, B.g_mask, B.g_xyz, B.g_sdf = (None if g is None else g.data_ptr() for g in cot)
         # needs_input_grad indices: module, kind, meta, styles, a0, a1, a2, a3, near, far, *params
-        g_styles = torch.zeros_like(styles) if needs[3] else None
-        g_a0 = torch.zeros_like(a0) if needs[4] else None
-        g_a1 = torch.zeros_like(a1) if needs[5] else None
-        g_a2 = torch.zeros_like(a2) if (a2 is not None and needs[6] and kind == _abi.INPUT_POINTS) else None
+        g_styles = torch.empty_like(styles) if needs[3] else None
         B.g_styles = None if g_styles is None else g_styles.data_ptr()
+        g_a0 = g_a1 = g_a2 = None
         if kind == _abi.INPUT_POINTS:
+            g_a0 = torch.empty_like(a0) if needs[4] else None
+            g_a1 = torch.empty_like(a1) if needs[5] else None
+            g_a2 = torch.zeros_like(a2) if needs[6] else None
             B.g_pts = None if g_a0 is None else g_a0.data_ptr()
             B.g_rays_d = None if g_a1 is None else g_a1.data_ptr()
             B.g_viewdirs = None if g_a2 is None else g_a2.data_ptr()
         else:
+            g_a0 = torch.zeros_like(a0) if needs[4] else None
+            g_a1 = torch.zeros_like(a1) if needs[5] else None
             B.g_cam_poses = None if g_a0 is None else g_a0.data_ptr()
             B.g_focal = None if g_a1 is None else g_a1.data_ptr()
-        n_param = len(needs) - 10
-        g_packed = None
-        if any(needs[10:]):
-            raise NotImplementedError("gradients w.r.t. renderer weights are not provided by libc3dpp "
-                                      "(inversion optimises latents/cameras; call requires_grad_(False))")
         nws = lib.c3d_backward_workspace_bytes(B)
         ws = torch.empty(max(nws, 16), dtype=torch.uint8, device=dev)
         B.fwd.workspace, B.fwd.workspace_bytes = ws.data_ptr(), nws
         with torch.cuda.device(dev):
             _abi.check(lib.c3d_nerf_backward(B, torch.cuda.current_stream().cuda_stream), "c3d_nerf_backward")
-        return (g_styles, g_a0, g_a1, g_a2, None, None, None) + (None,) * n_param
+        self.last_launch_count = lib.c3d_last_launch_count()
+        return (g_styles, g_a0, g_a1, g_a2, None, None, None) + (None,) * (len(needs) - 10)
 
     def _run(self, kind, meta, styles, a0, a1, a2, a3, near, far):
         tensors = [styles, a0, a1, near, far] + [t for t in (a2, a3) if t is not None]

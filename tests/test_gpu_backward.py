@@ -1,0 +1,148 @@
+"""GPU gradient parity (flip-inversion path): autograd through NerfBranch vs the reference's own autograd
+(golden vectors from tests/golden/make_golden.py) and vs float64 torch restatements for the standalone pieces.
+Tolerance: rel-L2 <= 1e-3 (the backward runs in fp32 for both precision modes)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GRAD_CASES, load_case, load_weights, rel_l2
+
+pytestmark = pytest.mark.gpu
+GRAD_REL = 1e-3
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _t(x, grad=False):
+    t = torch.from_numpy(np.ascontiguousarray(x)).to(_dev())
+    return t.requires_grad_(True) if grad else t
+
+
+def _module(D, precision):
+    import cips3dpp_b200 as c3d
+    m = c3d.NerfBranch(D, precision=precision)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in load_weights(D).items()}, strict=True)
+    return m.to(_dev()).eval().requires_grad_(False)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", GRAD_CASES)
+def test_gradients_match_reference_autograd(case, precision):
+    c = load_case(case)
+    m = _module(int(c["D"]), precision)
+    styles, pts, rays_d, viewdirs = (_t(c[k], True) for k in ("styles", "pts", "rays_d", "viewdirs"))
+    rgb_map, feat, sdf, mask, xyz, _ = m(pts=pts, rays_d=rays_d, viewdirs=viewdirs, z_vals=_t(c["z_vals"]),
+                                         near=_t(c["near"]), far=_t(c["far"]), styles=styles)
+    loss = (rgb_map * _t(c["cot_rgb_map"])).sum() + 0.05 * (feat * _t(c["cot_feature_map"])).sum() \
+        + (mask * _t(c["cot_mask"])).sum() + (xyz * _t(c["cot_xyz"])).sum()
+    loss.backward()
+    tol_loss = 1e-4 if precision == "fp32" else 2e-2
+    assert abs(loss.item() - float(c["loss"])) <= tol_loss * max(1.0, abs(float(c["loss"])))
+    errs = dict(styles=rel_l2(styles.grad.cpu().numpy(), c["g_styles"]), pts=rel_l2(pts.grad.cpu().numpy(), c["g_pts"]),
+                rays_d=rel_l2(rays_d.grad.cpu().numpy(), c["g_rays_d"]),
+                viewdirs=rel_l2(viewdirs.grad.cpu().numpy(), c["g_viewdirs"]))
+    print(case, precision, errs)
+    assert max(errs.values()) < GRAD_REL, errs
+
+
+def _volume_integration_torch(rgb, sdf, feat, z, rd, pts, beta):
+    """float64 torch restatement of nerf_utils.py:230-338 (test reference for the standalone kernel)."""
+    dists = torch.cat([z[..., 1:] - z[..., :-1], torch.full_like(z[..., :1], 1e10)], -1) * rd.norm(dim=-1, keepdim=True)
+    sigma = torch.sigmoid(-sdf / beta) / beta
+    alpha = 1 - torch.exp(-sigma * dists)
+    T = torch.cumprod(torch.cat([torch.ones_like(alpha[..., :1]), 1 - alpha + 1e-10], -1), -1)[..., :-1]
+    w = alpha * T
+    rgb_map = -1 + 2 * (w[..., None] * torch.sigmoid(rgb)).sum(-2)
+    fmap = (w[..., None] * feat).sum(-2)
+    xyz = (w[..., None] * pts).sum(-2)
+    mask = torch.stack([w[..., -1], -xyz.norm(dim=-1)], -1)
+    return rgb_map, fmap, xyz, mask, w
+
+
+@pytest.mark.parametrize("R,N,C", [(300, 24, 256), (9, 128, 64), (5, 40, 0)])
+def test_composite_backward_matches_float64_autograd(R, N, C):
+    import cips3dpp_b200 as c3d
+    lib = c3d._abi.load()
+    g = torch.Generator().manual_seed(R + N)
+    rgb = torch.randn(R, N, 3, generator=g, dtype=torch.float64)
+    sdf = 0.1 * torch.randn(R, N, generator=g, dtype=torch.float64)
+    feat = torch.randn(R, N, max(C, 4), generator=g, dtype=torch.float64)
+    z = torch.sort(0.88 + 0.24 * torch.rand(R, N, generator=g, dtype=torch.float64), -1).values
+    rd = torch.randn(R, 3, generator=g, dtype=torch.float64)
+    pts = torch.randn(R, N, 3, generator=g, dtype=torch.float64)
+    ins = [t.clone().requires_grad_(True) for t in (rgb, sdf, feat, rd, pts)]
+    out = _volume_integration_torch(ins[0], ins[1], ins[2], z, ins[3], ins[4], 0.1)
+    cots = [torch.randn(o.shape, generator=g, dtype=torch.float64) for o in out[:4]]
+    if C == 0:
+        cots[1].zero_()
+    loss = sum((o * c).sum() for o, c in zip(out[:4], cots))
+    grads = torch.autograd.grad(loss, ins)
+    f32 = lambda t: t.to(torch.float32).to(_dev()).contiguous()
+    keep = dict(rgb=f32(rgb), sdf=f32(sdf), z=f32(z), rd=f32(rd), pts=f32(pts), beta=torch.tensor([0.1], device=_dev()),
+                g_rgb_map=f32(cots[0]), g_xyz=f32(cots[2]), g_mask=f32(cots[3]))
+    outs = dict(weights=torch.empty(R, N, device=_dev()), g_rgb=torch.empty(R, N, 3, device=_dev()),
+                g_sdf=torch.empty(R, N, device=_dev()), g_pts=torch.empty(R, N, 3, device=_dev()),
+                g_rays_d=torch.empty(R, 3, device=_dev()))
+    P = c3d._abi.CompositeParams()
+    P.n_rays, P.n_samples, P.n_feat = R, N, C
+    P.sigmoid_beta_ptr = keep["beta"].data_ptr()
+    P.rgb, P.sdf, P.z_vals, P.rays_d, P.pts = (keep[k].data_ptr() for k in ("rgb", "sdf", "z", "rd", "pts"))
+    P.g_rgb_map, P.g_xyz, P.g_mask = keep["g_rgb_map"].data_ptr(), keep["g_xyz"].data_ptr(), keep["g_mask"].data_ptr()
+    if C:
+        keep["feat"], keep["g_fm"] = f32(feat), f32(cots[1])
+        outs["g_features"] = torch.empty(R, N, C, device=_dev())
+        P.features, P.g_feature_map, P.g_features = keep["feat"].data_ptr(), keep["g_fm"].data_ptr(), outs["g_features"].data_ptr()
+    P.weights, P.g_rgb, P.g_sdf, P.g_pts, P.g_rays_d = (outs[k].data_ptr() for k in ("weights", "g_rgb", "g_sdf", "g_pts", "g_rays_d"))
+    c3d._abi.check(lib.c3d_composite_backward(P, torch.cuda.current_stream().cuda_stream), "c3d_composite_backward")
+    torch.cuda.synchronize()
+    n = lambda t: t.detach().cpu().numpy()
+    assert rel_l2(n(outs["weights"]), n(out[4])) < 1e-5
+    assert rel_l2(n(outs["g_rgb"]), n(grads[0])) < 1e-4
+    assert rel_l2(n(outs["g_sdf"]), n(grads[1])) < 1e-4
+    assert rel_l2(n(outs["g_rays_d"]), n(grads[3])) < 1e-4
+    assert rel_l2(n(outs["g_pts"]), n(grads[4])) < 1e-4
+    if C:
+        assert rel_l2(n(outs["g_features"]), n(grads[2])) < 1e-4
+
+
+def test_pose_gradients_match_points_entry():
+    """POSES entry backward (d cam_poses, d focal) == POINTS entry backward chained through a torch restatement of
+    ray generation (nerf_utils.py:17-66, 160-161)."""
+    c = load_case("ffhq_d2_n24")
+    m = _module(2, "fp32")
+    S, N = 8, 24
+    near, far, styles = _t(c["near"]), _t(c["far"]), _t(c["styles"], True)
+    pose, focal = _t(c["c2w"], True), _t(c["focal"].reshape(1), True)
+    out = m.render(pose, focal, near, far, styles, img_size=S, N_samples=N)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    cot = {k: torch.randn(out[k].shape, generator=g).to(_dev()) for k in ("rgb_map", "feature_map", "mask", "xyz")}
+    loss = sum((out[k] * cot[k]).sum() * (0.05 if k == "feature_map" else 1.0) for k in cot)
+    gp, gf, gs = torch.autograd.grad(loss, [pose, focal, styles])
+    # reference chain: torch ray generation -> POINTS entry
+    pose2, focal2, styles2 = (t.detach().clone().requires_grad_(True) for t in (pose, focal, styles))
+    lin = torch.linspace(0.5, S - 0.5, S, device=_dev())
+    yy, xx = torch.meshgrid(lin, lin, indexing="ij")
+    d_cam = torch.stack([(xx - S / 2) / focal2, -(yy - S / 2) / focal2, -torch.ones_like(xx)], -1).reshape(1, S * S, 3)
+    rays_d = (d_cam[:, :, None, :] * pose2[:, None, :3, :3]).sum(-1)
+    viewdirs = torch.nn.functional.normalize(rays_d, dim=-1)
+    z_vals = out["z_vals"].detach()
+    pts = pose2[:, None, None, :3, 3] + rays_d[:, :, None, :] * z_vals[..., None]
+    o2 = m(pts=pts, rays_d=rays_d, viewdirs=viewdirs, z_vals=z_vals, near=near, far=far, styles=styles2)
+    loss2 = (o2[0] * cot["rgb_map"]).sum() + 0.05 * (o2[1] * cot["feature_map"]).sum() + (o2[3] * cot["mask"]).sum() \
+        + (o2[4] * cot["xyz"]).sum()
+    gp2, gf2, gs2 = torch.autograd.grad(loss2, [pose2, focal2, styles2])
+    assert abs(loss.item() - loss2.item()) < 1e-3 * max(1.0, abs(loss2.item()))
+    assert rel_l2(gp.cpu().numpy(), gp2.cpu().numpy()) < 1e-3
+    assert rel_l2(gf.cpu().numpy(), gf2.cpu().numpy()) < 1e-3
+    assert rel_l2(gs.cpu().numpy(), gs2.cpu().numpy()) < 1e-3
+
+
+def test_weight_gradients_are_refused_loudly():
+    c = load_case("ffhq_d2_n24")
+    m = _module(2, "fp32").requires_grad_(True)
+    out = m(pts=_t(c["pts"]), rays_d=_t(c["rays_d"]), viewdirs=_t(c["viewdirs"]), z_vals=_t(c["z_vals"]),
+            near=_t(c["near"]), far=_t(c["far"]), styles=_t(c["styles"]))
+    with pytest.raises(NotImplementedError):
+        out[0].sum().backward()
