@@ -84,6 +84,14 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm overrides it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_baseline(cfg, n_images, reps=1):
     """oracle/nerf_oracle.c (kind 'port': the reference path is Python, nothing to compile) on host cores."""
     from oracle import c_oracle, nerf_oracle as O
@@ -92,13 +100,14 @@ def cpu_baseline(cfg, n_images, reps=1):
     packed = c_oracle.pack_params(params)
     sl = slice(0, n_images)
     times = []
+    nthr = host_threads()
     for _ in range(reps + 1):                                      # first pass = warm-up
         t0 = time.perf_counter()
         pts, rd, vd, z = c_oracle.prepare_inputs(c2w[sl], focal[sl], near[sl], far[sl], IMG, cfg["N"])
-        c_oracle.renderer_forward(params, pts, rd, vd, z, near[sl], far[sl], styles[sl], packed=packed)
+        c_oracle.renderer_forward(params, pts, rd, vd, z, near[sl], far[sl], styles[sl], nthreads=nthr, packed=packed)
         times.append(time.perf_counter() - t0)
     t = min(times[1:])
-    return dict(value=n_images * IMG * IMG / t, unit="rays/s", cores=c_oracle.num_threads(), kind="port",
+    return dict(value=n_images * IMG * IMG / t, unit="rays/s", cores=nthr, kind="port",
                 sample=f"{n_images} of {c2w.shape[0]} images of the step ({t:.2f} s, best of {reps})",
                 images_per_s=n_images / t, host_cpus=os.cpu_count()), t
 
@@ -117,7 +126,8 @@ def run_reference(args, cfg, rank, world):
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         pts, rd, vd, z = c_oracle.prepare_inputs(c2w[sl], focal[sl], near[sl], far[sl], IMG, cfg["N"])
-        c_oracle.renderer_forward(params, pts, rd, vd, z, near[sl], far[sl], styles[sl], packed=packed)
+        c_oracle.renderer_forward(params, pts, rd, vd, z, near[sl], far[sl], styles[sl], nthreads=host_threads(),
+                                  packed=packed)
         if i >= args.warmup:
             times.append(time.perf_counter() - t0)
     t = float(np.mean(times))
