@@ -7,5 +7,6 @@ from .nerf_branch import NerfBranch
 from .nerf_utils import Render, Camera
 from .patch import use_b200_nerf_branch
 from . import dist
+from .inversion import FlipInversion
 
-__all__ = ["NerfBranch", "Render", "Camera", "use_b200_nerf_branch", "dist", "_abi"]
+__all__ = ["NerfBranch", "Render", "Camera", "use_b200_nerf_branch", "dist", "FlipInversion", "_abi"]

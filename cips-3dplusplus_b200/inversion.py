@@ -1,0 +1,81 @@
+"""Batched flip GAN inversion through the NeRF branch -- the caller of the forward+backward hot path
+(reference: StyleGAN2Projector_Flip.project_wplus stage 1, exp/cips3d/models/projector_v9.py:862-1166, where only
+the cameras and w_render move; `_G_forward` :191-257; lr ramp `_get_cur_lr` :154-166).
+
+What is mirrored: per target one W+ latent `w_render (D+1, 256)` shared by the image and its horizontal flip
+(`w.repeat(2,1,1)`, :1050), one (azim, elev) per view, Adam(betas=(0.9, 0.999)), cosine ramp-down / linear ramp-up
+learning rate, gradient-norm clipping at 10, loss on the 64x64 thumbnail.  What is not: the 2-D decoder and the
+VGG perceptual network stay the reference's (out of scope) -- pass `loss_fn` to plug them in.
+Targets are independent, so ranks take disjoint targets and no gradient all-reduce is needed unless
+`shared_latent=True` (one latent fitted to all targets of all ranks), which uses `dist.allreduce_grads`.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import dist as c3d_dist
+from .nerf_utils import Camera
+
+
+def lr_ramp(step, num_steps, lr0, rampdown=0.25, rampup=0.05):
+    """projector_v9.py:154-166."""
+    t = step / num_steps
+    r = min(1.0, (1.0 - t) / rampdown)
+    r = 0.5 - 0.5 * math.cos(r * math.pi)
+    return lr0 * r * min(1.0, t / rampup)
+
+
+def thumb_mse(thumb, target):
+    return ((thumb - target) ** 2).mean(dim=(1, 2, 3)).sum()
+
+
+class FlipInversion:
+    def __init__(self, renderer, img_size=64, N_samples=24, cam_cfg=None, lr_latent=0.02, lr_cam=0.01, num_steps=200,
+                 loss_fn=thumb_mse, clip=10.0, shared_latent=False, static_viewdirs=True):
+        self.renderer, self.img_size, self.N = renderer, img_size, N_samples
+        self.cam_cfg = dict(fov_ang=6, dist_radius=0.12) if cam_cfg is None else dict(cam_cfg)
+        self.lr_latent, self.lr_cam, self.num_steps = lr_latent, lr_cam, num_steps
+        self.loss_fn, self.clip, self.shared_latent, self.static_viewdirs = loss_fn, clip, shared_latent, static_viewdirs
+
+    def render_thumbs(self, w, azim, elev):
+        """w (n, D+1, 256); azim, elev (n, 2, 1) -> thumbs (n*2, 3, S, S), differentiable."""
+        n, S = w.shape[0], self.img_size
+        loc = torch.cat([azim.reshape(-1, 1), elev.reshape(-1, 1)], 1)
+        pose, focal, near, far, _ = Camera.generate_camera_params(S, w.device, locations=loc, **self.cam_cfg)
+        styles = w.repeat_interleave(2, dim=0)                        # image and flip share the latent
+        out = self.renderer.render(pose, focal, near, far, styles, img_size=S, N_samples=self.N,
+                                   static_viewdirs=self.static_viewdirs)
+        return out["rgb_map"].reshape(n * 2, S, S, 3).permute(0, 3, 1, 2)
+
+    def run(self, targets, w_init, azim_init=None, elev_init=None, callback=None):
+        """targets (n, 3, S, S) in [-1, 1]; w_init (1 or n, D+1, 256).  Returns dict(w, azim, elev, losses)."""
+        dev, n = targets.device, targets.shape[0]
+        tgt = torch.stack([targets, targets.flip(-1)], 1).reshape(n * 2, *targets.shape[1:])
+        nw = 1 if self.shared_latent else n
+        w = w_init.detach().expand(nw, -1, -1).clone().requires_grad_(True)
+        azim = (torch.zeros(n, 2, 1, device=dev) if azim_init is None else azim_init.detach().clone()).requires_grad_(True)
+        elev = (torch.zeros(n, 2, 1, device=dev) if elev_init is None else elev_init.detach().clone()).requires_grad_(True)
+        opt_w = torch.optim.Adam([w], betas=(0.9, 0.999), lr=self.lr_latent)
+        opt_c = torch.optim.Adam([azim, elev], betas=(0.9, 0.999), lr=self.lr_cam)
+        losses = []
+        for step in range(self.num_steps):
+            for opt, lr0 in ((opt_w, self.lr_latent), (opt_c, self.lr_cam)):
+                for g in opt.param_groups:
+                    g["lr"] = lr_ramp(step, self.num_steps, lr0)
+            thumbs = self.render_thumbs(w.expand(n, -1, -1) if self.shared_latent else w, azim, elev)
+            loss = self.loss_fn(thumbs, tgt)
+            opt_w.zero_grad(set_to_none=True)
+            opt_c.zero_grad(set_to_none=True)
+            loss.backward()
+            if self.shared_latent and torch.distributed.is_available() and torch.distributed.is_initialized():
+                c3d_dist.allreduce_grads([w.grad])
+            torch.nn.utils.clip_grad_norm_([w], self.clip)
+            torch.nn.utils.clip_grad_norm_([azim, elev], self.clip)
+            opt_w.step()
+            opt_c.step()
+            losses.append(loss.detach())
+            if callback is not None:
+                callback(step, loss)
+        return dict(w=w.detach(), azim=azim.detach(), elev=elev.detach(), losses=torch.stack(losses))
