@@ -25,6 +25,7 @@ struct CompositeBwdArgs {
   const float* sigmoid_beta_ptr;
   const float* rgb; const float* sdf; const float* features; const float* z_vals; const float* rays_d; const float* pts;
   const float* g_rgb_map; const float* g_feature_map; const float* g_xyz; const float* g_mask; const float* g_sdf_in;
+  const float* gdot;  // optional (n_rays, N): precomputed g_feature_map . features (tensor-core path); overrides `features`
   float* weights;     // (n_rays, N) out
   float* g_rgb;       // (n_rays, N, 3) out
   float* g_sdf;       // (n_rays, N) out
@@ -81,7 +82,9 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(CompositeBwdArgs p) 
   const int C4 = p.n_feat >> 2;
   for (int k = 0; k < N; ++k) {
     float acc = 0.f;
-    if (p.g_feature_map && p.features) {
+    if (p.gdot) {
+      acc = p.gdot[ray * N + k];
+    } else if (p.g_feature_map && p.features) {
       const float4* f = reinterpret_cast<const float4*>(p.features) + ((size_t)ray * N + k) * C4;
       const float4* g = reinterpret_cast<const float4*>(p.g_feature_map) + (size_t)ray * C4;
       for (int c = lane; c < C4; c += 32) {

@@ -9,6 +9,7 @@
 #include "fused_common.cuh"
 #include "fused_bf16_sm100.cuh"
 #include "backward.cuh"
+#include "fused_bwd_sm100.cuh"
 
 namespace c3d {
 thread_local char g_err[512] = "";
@@ -109,17 +110,12 @@ static int launch_style_prep(const void* packed, int D, const float* styles, int
 
 static int gcd_(int a, int b) { return b ? gcd_(b, a % b) : a; }
 
-static int forward_bf16(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st) {
-  C3D_CHECK_ARG(p->n_samples >= fused::MIN_SAMPLES, "bf16 mode needs n_samples >= %d (got %d); use C3D_MODE_FP32",
-                fused::MIN_SAMPLES, p->n_samples);
-  uint8_t* ws = reinterpret_cast<uint8_t*>(p->workspace);
-  fused::Args a;
+static void fused_fill_args(fused::Args& a, const c3d_fwd_params* p, const float2* film, const float4* first,
+                            const float4* view) {
   memset(&a, 0, sizeof(a));
   a.blob = reinterpret_cast<const uint8_t*>(p->packed);
   a.L = packed_layout(p->D);
-  a.film = reinterpret_cast<const float2*>(ws + w.film);
-  a.first = reinterpret_cast<const float4*>(ws + w.first);
-  a.view = reinterpret_cast<const float4*>(ws + w.view);
+  a.film = film; a.first = first; a.view = view;
   a.batch = p->batch; a.n_rays = p->n_rays; a.n_samples = p->n_samples; a.D = p->D;
   a.img_size = p->img_size; a.static_viewdirs = p->static_viewdirs; a.input_kind = p->input_kind;
   // unit = whole rays whose points fill whole 128-row tiles when possible, >= 6 tiles
@@ -129,12 +125,17 @@ static int forward_bf16(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
   if (ur > p->n_rays) ur = p->n_rays;
   a.unit_rays = ur;
   a.units_per_img = (p->n_rays + ur - 1) / ur;
+  a.tiles_per_unit = (ur * p->n_samples + fused::TILE - 1) / fused::TILE;
+  a.n_tiles_g = (long long)a.batch * a.units_per_img * a.tiles_per_unit;
   a.cam_poses = p->cam_poses; a.focal = p->focal; a.near = p->near; a.far = p->far; a.ray_offset = p->ray_offset;
   a.pts = p->pts; a.rays_d = p->rays_d; a.viewdirs = p->viewdirs; a.z_vals = p->z_vals;
   a.rgb_map = p->rgb_map; a.feature_map = p->feature_map; a.sdf = p->sdf; a.mask = p->mask; a.xyz = p->xyz;
   a.z_vals_out = p->z_vals_out;
   { const char* d = getenv("C3D_DEBUG"); a.debug = d ? atoi(d) : 0; }
+}
 
+// kind: 0 forward, 1 forward + save (backward support), 2 backward
+static int fused_launch(const fused::Args& a, int kind, cudaStream_t st) {
   int dev = 0, nsm = 0;
   C3D_CUDA(cudaGetDevice(&dev));
   C3D_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
@@ -148,26 +149,37 @@ static int forward_bf16(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
   if (cluster == 2) grid = (grid + 1) & ~1;
   const char* genv = getenv("C3D_GRID");
   if (genv && atoi(genv) > 0) { grid = atoi(genv); if (cluster == 2) grid = (grid + 1) & ~1; }
-
   const char* eenv = getenv("C3D_EGW");
-  const int egw = (eenv && atoi(eenv) == 8) ? 8 : 4;      // epilogue warps per slot (tuning knob; 4 measured best)
+  const int egw = (kind == 0 && eenv && atoi(eenv) == 8) ? 8 : 4;   // epilogue warps per slot (tuning knob; 4 measured best)
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(fused::nthreads(egw));
-  cfg.dynamicSmemBytes = fused::SMEM_BYTES;
+  cfg.blockDim = dim3(kind == 2 ? fusedbwd::NTHREADS : fused::nthreads(egw));
+  cfg.dynamicSmemBytes = kind == 2 ? fusedbwd::SMEM_BYTES : fused::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   void (*kern)(const fused::Args);
-  if (egw == 8) kern = cluster == 2 ? fused::fused_forward_kernel<2, 8> : fused::fused_forward_kernel<1, 8>;
+  if (kind == 2) kern = cluster == 2 ? fusedbwd::fused_backward_kernel<2> : fusedbwd::fused_backward_kernel<1>;
+  else if (kind == 1) kern = cluster == 2 ? fused::fused_forward_kernel<2, 4, true> : fused::fused_forward_kernel<1, 4, true>;
+  else if (egw == 8) kern = cluster == 2 ? fused::fused_forward_kernel<2, 8> : fused::fused_forward_kernel<1, 8>;
   else kern = cluster == 2 ? fused::fused_forward_kernel<2, 4> : fused::fused_forward_kernel<1, 4>;
   C3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
   C3D_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   C3D_LAUNCH_CHECK();
   return C3D_OK;
+}
+
+static int forward_bf16(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st) {
+  C3D_CHECK_ARG(p->n_samples >= fused::MIN_SAMPLES, "bf16 mode needs n_samples >= %d (got %d); use C3D_MODE_FP32",
+                fused::MIN_SAMPLES, p->n_samples);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(p->workspace);
+  fused::Args a;
+  fused_fill_args(a, p, reinterpret_cast<const float2*>(ws + w.film), reinterpret_cast<const float4*>(ws + w.first),
+                  reinterpret_cast<const float4*>(ws + w.view));
+  return fused_launch(a, 0, st);
 }
 
 static int forward_fp32(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st, float* feat_out) {
@@ -396,6 +408,60 @@ static BwdWs bwd_ws(const c3d_bwd_params* bp) {
   return w;
 }
 
+// bf16 mode differentiates through the tensor-core kernels (forward with save + fused backward); fp32 mode and
+// n_samples < 8 use the FP32-pipe kernels.  C3D_BWD=simt forces the latter (A/B runs).
+static bool bwd_uses_tensor_path(const c3d_bwd_params* bp) {
+  const char* e = getenv("C3D_BWD");
+  if (e && strcmp(e, "simt") == 0) return false;
+  return bp->fwd.mode == C3D_MODE_BF16 && bp->fwd.n_samples >= fused::MIN_SAMPLES;
+}
+
+struct BwdTcWs {
+  size_t film, first, view, g_film, chunk, total;
+  int chunk_imgs, unit_rays, units_per_img, tiles_per_unit;
+  size_t c_acc, c_cos, c_feat, c_rgbpt, c_wpt, c_sdfpt, c_gdot, c_grgb, c_gsdf, c_wts, c_orgb, c_ofeat, c_omask, c_oxyz,
+      c_gpts, c_grd, c_gvd, c_pts, c_rd, c_vd, c_z;
+};
+static BwdTcWs bwd_tc_ws(const c3d_bwd_params* bp) {
+  const c3d_fwd_params* p = &bp->fwd;
+  BwdTcWs w;
+  memset(&w, 0, sizeof(w));
+  const size_t b = (size_t)p->batch, P = (size_t)p->n_rays * p->n_samples, R = (size_t)p->n_rays, D = (size_t)p->D;
+  const int u0 = 128 / gcd_(p->n_samples, 128);
+  int ur = u0;
+  while (ur * p->n_samples < 6 * 128) ur += u0;
+  if (ur > p->n_rays) ur = p->n_rays;
+  w.unit_rays = ur;
+  w.units_per_img = (p->n_rays + ur - 1) / ur;
+  w.tiles_per_unit = (ur * p->n_samples + fused::TILE - 1) / fused::TILE;
+  const size_t tiles_img = (size_t)w.units_per_img * w.tiles_per_unit;
+  size_t o = 0;
+  w.film = o;   o += align_up(b * (D + 1) * W * sizeof(float2), 256);
+  w.first = o;  o += align_up(b * W * sizeof(float4), 256);
+  w.view = o;   o += align_up(b * W * sizeof(float4), 256);
+  w.g_film = o; o += align_up(b * (D + 1) * W * sizeof(float2), 256);
+  w.chunk = o;
+  const bool poses = p->input_kind == C3D_INPUT_POSES;
+  const size_t per_img = tiles_img * 65536 * (2 * (D + 1) + 1) + P * (12 + 4 + 4 + 4 + 12 + 4 + 4 + 12) + R * (12 + 1024 + 8 + 12 + 24) +
+                         (poses ? P * 16 + R * 24 : 0) + 8192;
+  size_t ci = ((size_t)4 << 30) / per_img;
+  if (ci < 1) ci = 1;
+  if (ci > b) ci = b;
+  w.chunk_imgs = (int)ci;
+  size_t c = 0;
+  auto take = [&](size_t bytes) { const size_t at = c; c += align_up(bytes, 256); return at; };
+  w.c_acc = take(ci * tiles_img * 65536 * (D + 1));
+  w.c_cos = take(ci * tiles_img * 65536 * (D + 1));
+  w.c_feat = take(ci * tiles_img * 65536);
+  w.c_rgbpt = take(ci * P * 12); w.c_wpt = take(ci * P * 4); w.c_sdfpt = take(ci * P * 4); w.c_gdot = take(ci * P * 4);
+  w.c_grgb = take(ci * P * 12); w.c_gsdf = take(ci * P * 4); w.c_wts = take(ci * P * 4);
+  w.c_orgb = take(ci * R * 12); w.c_ofeat = take(ci * R * W * 4); w.c_omask = take(ci * R * 8); w.c_oxyz = take(ci * R * 12);
+  w.c_gpts = take(ci * P * 12); w.c_grd = take(ci * R * 12); w.c_gvd = take(ci * R * 12);
+  if (poses) { w.c_pts = take(ci * P * 12); w.c_rd = take(ci * R * 12); w.c_vd = take(ci * R * 12); w.c_z = take(ci * P * 4); }
+  w.total = o + c;
+  return w;
+}
+
 static int validate_bwd(const c3d_bwd_params* bp) {
   C3D_CHECK_ARG(bp != nullptr, "params is NULL");
   const c3d_fwd_params* p = &bp->fwd;
@@ -413,8 +479,8 @@ static int validate_bwd(const c3d_bwd_params* bp) {
   } else {
     C3D_CHECK_ARG(p->pts && p->rays_d && p->viewdirs && p->z_vals, "POINTS input needs pts, rays_d, viewdirs, z_vals");
   }
-  const BwdWs w = bwd_ws(bp);
-  C3D_CHECK_ARG(p->workspace && p->workspace_bytes >= w.total, "workspace too small: %zu < %zu", p->workspace_bytes, w.total);
+  const size_t need = bwd_uses_tensor_path(bp) ? bwd_tc_ws(bp).total : bwd_ws(bp).total;
+  C3D_CHECK_ARG(p->workspace && p->workspace_bytes >= need, "workspace too small: %zu < %zu", p->workspace_bytes, need);
   C3D_CHECK_ARG(aligned16(p->workspace) && aligned16(bp->g_feature_map), "workspace / g_feature_map must be 16-byte aligned");
   return C3D_OK;
 }
@@ -425,15 +491,23 @@ extern "C" {
 
 size_t c3d_backward_workspace_bytes(const c3d_bwd_params* p) {
   if (!p || p->fwd.batch < 1 || p->fwd.n_rays < 1 || p->fwd.n_samples < 1 || p->fwd.D < 1) return 0;
-  return bwd_ws(p).total;
+  return bwd_uses_tensor_path(p) ? bwd_tc_ws(p).total : bwd_ws(p).total;
 }
+
+static int backward_simt(const c3d_bwd_params* bp, cudaStream_t st);
+static int backward_tc(const c3d_bwd_params* bp, cudaStream_t st);
 
 int c3d_nerf_backward(const c3d_bwd_params* bp, c3d_stream_t stream) {
   g_launches = 0;
   int rc = validate_bwd(bp);
   if (rc != C3D_OK) return rc;
-  const c3d_fwd_params* p = &bp->fwd;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return bwd_uses_tensor_path(bp) ? backward_tc(bp, st) : backward_simt(bp, st);
+}
+
+static int backward_simt(const c3d_bwd_params* bp, cudaStream_t st) {
+  int rc;
+  const c3d_fwd_params* p = &bp->fwd;
   const BwdWs w = bwd_ws(bp);
   uint8_t* ws = reinterpret_cast<uint8_t*>(p->workspace);
   uint8_t* ck = ws + w.chunk;
@@ -527,6 +601,107 @@ int c3d_nerf_backward(const c3d_bwd_params* bp, c3d_stream_t stream) {
   }
   return C3D_OK;
 }
+
+static int backward_tc(const c3d_bwd_params* bp, cudaStream_t st) {
+  int rc;
+  const c3d_fwd_params* p = &bp->fwd;
+  const BwdTcWs w = bwd_tc_ws(bp);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(p->workspace);
+  uint8_t* ck = ws + w.chunk;
+  const size_t P = (size_t)p->n_rays * p->n_samples, R = (size_t)p->n_rays;
+  const int D = p->D;
+  const PackedLayout L = packed_layout(D);
+  const bool poses = p->input_kind == C3D_INPUT_POSES;
+  float2* film = reinterpret_cast<float2*>(ws + w.film);
+  float4* first = reinterpret_cast<float4*>(ws + w.first);
+  float4* view = reinterpret_cast<float4*>(ws + w.view);
+  float* g_film = reinterpret_cast<float*>(ws + w.g_film);
+  rc = launch_style_prep(p->packed, D, p->styles, p->batch, reinterpret_cast<float*>(film), reinterpret_cast<float*>(first),
+                         reinterpret_cast<float*>(view), st);
+  if (rc != C3D_OK) return rc;
+  C3D_CUDA(cudaMemsetAsync(g_film, 0, (size_t)p->batch * (D + 1) * W * sizeof(float2), st));
+  const float* beta_ptr = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p->packed) + L.scal) + 4;
+  for (int i0 = 0; i0 < p->batch; i0 += w.chunk_imgs) {
+    const int ni = (p->batch - i0 < w.chunk_imgs) ? p->batch - i0 : w.chunk_imgs;
+    c3d_fwd_params q = *p;                         // this chunk as a POINTS-entry launch
+    q.batch = ni; q.input_kind = C3D_INPUT_POINTS;
+    q.styles = p->styles + (size_t)i0 * (D + 1) * W; q.near = p->near + i0; q.far = p->far + i0;
+    c3d_raygen_params rg;
+    memset(&rg, 0, sizeof(rg));
+    if (poses) {
+      rg.batch = ni; rg.img_size = p->img_size; rg.n_samples = p->n_samples; rg.static_viewdirs = p->static_viewdirs;
+      rg.cam_poses = p->cam_poses + (size_t)i0 * 12; rg.focal = p->focal + i0; rg.near = q.near; rg.far = q.far;
+      rg.ray_offset = p->ray_offset ? p->ray_offset + (size_t)i0 * R : nullptr;
+      rg.pts = reinterpret_cast<float*>(ck + w.c_pts); rg.rays_d = reinterpret_cast<float*>(ck + w.c_rd);
+      rg.viewdirs = reinterpret_cast<float*>(ck + w.c_vd); rg.z_vals = reinterpret_cast<float*>(ck + w.c_z);
+      const long long n = (long long)ni * R;
+      raygen_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(rg);
+      C3D_LAUNCH_CHECK();
+      q.pts = rg.pts; q.rays_d = rg.rays_d; q.viewdirs = rg.viewdirs; q.z_vals = rg.z_vals;
+    } else {
+      q.pts = p->pts + (size_t)i0 * P * 3; q.rays_d = p->rays_d + (size_t)i0 * R * 3;
+      q.viewdirs = p->viewdirs + (size_t)i0 * R * 3; q.z_vals = p->z_vals + (size_t)i0 * P;
+    }
+    q.rgb_map = reinterpret_cast<float*>(ck + w.c_orgb); q.feature_map = reinterpret_cast<float*>(ck + w.c_ofeat);
+    q.mask = reinterpret_cast<float*>(ck + w.c_omask); q.xyz = reinterpret_cast<float*>(ck + w.c_oxyz);
+    q.sdf = reinterpret_cast<float*>(ck + w.c_sdfpt); q.z_vals_out = nullptr;
+    float* g_pts = (!poses && bp->g_pts) ? bp->g_pts + (size_t)i0 * P * 3 : reinterpret_cast<float*>(ck + w.c_gpts);
+    float* g_rd = (!poses && bp->g_rays_d) ? bp->g_rays_d + (size_t)i0 * R * 3 : reinterpret_cast<float*>(ck + w.c_grd);
+    float* g_vd = (!poses && bp->g_viewdirs) ? bp->g_viewdirs + (size_t)i0 * R * 3 : reinterpret_cast<float*>(ck + w.c_gvd);
+    C3D_CUDA(cudaMemsetAsync(g_vd, 0, (size_t)ni * R * 12, st));
+    const float* gF = bp->g_feature_map ? bp->g_feature_map + (size_t)i0 * R * W : nullptr;
+    // 1. forward on the tensor cores, keeping bf16 acc / cos tiles per layer and per-point rgb / weights
+    fused::Args a;
+    fused_fill_args(a, &q, film + (size_t)i0 * (D + 1) * W, first + (size_t)i0 * W, view + (size_t)i0 * W);
+    a.save_acc = reinterpret_cast<__nv_bfloat16*>(ck + w.c_acc); a.save_cos = reinterpret_cast<__nv_bfloat16*>(ck + w.c_cos);
+    a.save_feat = reinterpret_cast<__nv_bfloat16*>(ck + w.c_feat);
+    a.rgb_pt = reinterpret_cast<float*>(ck + w.c_rgbpt); a.w_pt = reinterpret_cast<float*>(ck + w.c_wpt);
+    a.g_feature_map = gF;
+    rc = fused_launch(a, 1, st);
+    if (rc != C3D_OK) return rc;
+    // 2. d(volume_integration): needs g_feature_map . feat per point
+    float* gdot = reinterpret_cast<float*>(ck + w.c_gdot);
+    if (gF) {
+      const long long warps = a.n_tiles_g * 16;
+      fusedbwd::gdot_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(a, gdot);
+      C3D_LAUNCH_CHECK();
+    }
+    CompositeBwdArgs c;
+    memset(&c, 0, sizeof(c));
+    c.n_rays = (long long)ni * R; c.n_samples = p->n_samples; c.n_feat = W; c.sigmoid_beta_ptr = beta_ptr;
+    c.rgb = a.rgb_pt; c.sdf = q.sdf; c.features = nullptr; c.gdot = gF ? gdot : nullptr;
+    c.z_vals = q.z_vals; c.rays_d = q.rays_d; c.pts = q.pts;
+    c.g_rgb_map = bp->g_rgb_map ? bp->g_rgb_map + (size_t)i0 * R * 3 : nullptr;
+    c.g_feature_map = nullptr;
+    c.g_xyz = bp->g_xyz ? bp->g_xyz + (size_t)i0 * R * 3 : nullptr;
+    c.g_mask = bp->g_mask ? bp->g_mask + (size_t)i0 * R * 2 : nullptr;
+    c.g_sdf_in = bp->g_sdf ? bp->g_sdf + (size_t)i0 * P : nullptr;
+    c.weights = reinterpret_cast<float*>(ck + w.c_wts); c.g_rgb = reinterpret_cast<float*>(ck + w.c_grgb);
+    c.g_sdf = reinterpret_cast<float*>(ck + w.c_gsdf); c.g_features = nullptr; c.g_pts = g_pts; c.g_rays_d = g_rd;
+    composite_bwd_kernel<<<(unsigned)((c.n_rays + 7) / 8), 256, 0, st>>>(c);
+    C3D_LAUNCH_CHECK();
+    // 3. fused tensor-core backward of the MLP
+    a.g_rgb_pt = c.g_rgb; a.g_sdf_pt = c.g_sdf; a.g_film = g_film + (size_t)i0 * (D + 1) * W * 2;
+    a.g_pts = g_pts; a.g_viewdirs = g_vd;
+    rc = fused_launch(a, 2, st);
+    if (rc != C3D_OK) return rc;
+    if (poses && (bp->g_cam_poses || bp->g_focal)) {
+      dim3 grid((unsigned)((R + 127) / 128), ni);
+      raygen_bwd_kernel<<<grid, 128, 0, st>>>(rg, g_pts, g_rd, g_vd, bp->g_cam_poses ? bp->g_cam_poses + (size_t)i0 * 12 : nullptr,
+                                              bp->g_focal ? bp->g_focal + i0 : nullptr);
+      C3D_LAUNCH_CHECK();
+    }
+  }
+  if (bp->g_styles) {
+    film_bwd_kernel<<<dim3(D + 1, p->batch), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(p->packed), L, g_film, bp->g_styles);
+    C3D_LAUNCH_CHECK();
+  }
+  return C3D_OK;
+}
+
+}  // extern "C" (helpers above are static)
+
+extern "C" {
 
 int c3d_composite_backward(const c3d_composite_params* p, c3d_stream_t stream) {
   C3D_CHECK_ARG(p && p->n_rays >= 1, "n_rays must be >= 1");

@@ -37,9 +37,15 @@ constexpr int NCHUNK = W / KCHUNK;  // 4 K-chunks per layer
 //              k-slots 4j..4j+3 (j = x,y,z) = (hi, hi, lo, hi) of W0[n][j]  x  point tile (hi, mid, hi, lo) of the
 //              normalised coordinate (split product exact to ~2^-18); slots 12..14 = bf16(Wview[n][256+j]) x
 //              view-direction tile; slot 15 zero.  The point tile zeroes 12..15, the view tile zeroes 0..11.
+//   wbf16T   : per layer l in 1..D: 4 chunks x [256 k][64 c] bf16, same swizzle: W_l transposed (rows = input channel k,
+//              contraction over the output channel c) -- the A operand of the backward MMAs  g_h = W^T g_acc
+//   bwd16    : three backward side images:
+//              [0] K16 image [256 c][16]: slots 0..2 and 3..5 = bf16(Wrgb[j][c]) (pair with hi / lo of g_rgb), rest zero
+//              [1] K16 image [256 k][16]: slots 6, 7 = bf16(sigma_linear.weight[k]) (pair with hi / lo of g_sdf), rest zero
+//              [2] heads image 4 chunks x [16 n][64 c] (sw128): rows 0..2 = W0[c][j], rows 4..6 = Wview[c][256+j]
 // ------------------------------------------------------------------------------------------
 struct PackedLayout {
-  size_t w0, wvdir, bias, wsig, wrgb, scal, film, wT32, w32, wbf16, rgb16, w0img, total;
+  size_t w0, wvdir, bias, wsig, wrgb, scal, film, wT32, w32, wbf16, rgb16, w0img, wbf16T, bwd16, total;
   int D;
 };
 constexpr size_t FILM_LAYER_FLOATS = 2 * (size_t)W * W + 2 * W;
@@ -67,6 +73,8 @@ __host__ __device__ inline PackedLayout packed_layout(int D) {
   L.wbf16 = o; o += WBF16_LAYER_BYTES * (size_t)D;
   L.rgb16 = o; o += RGB16_BYTES;
   L.w0img = o; o += W0IMG_BYTES;
+  L.wbf16T = o; o += WBF16_LAYER_BYTES * (size_t)D;
+  L.bwd16 = o; o += 3 * W0IMG_BYTES;
   L.total = align_up(o, 1024);
   return L;
 }

@@ -90,6 +90,34 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], float scale,
   }
 }
 
+// Same, additionally keeping what the backward needs: bf16(acc) and bf16(cos(arg)) (and the output itself for the view
+// layer) in global memory, layout [point group][channel][8 points] so a warp writes 512 contiguous bytes per group.
+__device__ __forceinline__ void epilogue16_save(const uint32_t (&v)[16], float scale, float shift, uint32_t row_addr,
+                                                int u0, int c7, __nv_bfloat16* sacc, __nv_bfloat16* scos,
+                                                __nv_bfloat16* sfeat /* NULL unless view layer */) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    float o[8], cs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float arg = fmaf(__uint_as_float(v[g * 8 + i]), scale, shift);
+      o[i] = __sinf(arg);
+      cs[i] = __cosf(arg);
+    }
+    const uint4 po = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    st_v4(row_addr + (uint32_t)(((u0 + g) ^ c7) << 4), po.x, po.y, po.z, po.w);
+    const size_t goff = (size_t)g * (W * 8);
+    *reinterpret_cast<uint4*>(sacc + goff) =
+        make_uint4(pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1])),
+                   pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
+                   pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
+                   pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
+    *reinterpret_cast<uint4*>(scos + goff) =
+        make_uint4(pack_bf16x2(cs[0], cs[1]), pack_bf16x2(cs[2], cs[3]), pack_bf16x2(cs[4], cs[5]), pack_bf16x2(cs[6], cs[7]));
+    if (sfeat) *reinterpret_cast<uint4*>(sfeat + goff) = po;
+  }
+}
+
 // sin(acc * scale + shift) for 32 consecutive points of one channel -> bf16 -> four 16-byte stores into H^T.
 // row_addr = tile + block(p0) + channel*128 (shared address), u0 = unit index of p0 inside its 64-point block.
 __device__ __forceinline__ void epilogue32(const uint32_t (&v)[32], float scale, float shift, uint32_t row_addr,
@@ -104,7 +132,7 @@ __device__ __forceinline__ void epilogue32(const uint32_t (&v)[32], float scale,
   }
 }
 
-template <int kCluster, int kEgw>
+template <int kCluster, int kEgw, bool kSave = false>
 __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const Args a) {
   constexpr int EG_THREADS = kEgw * 32;
   constexpr int NTHREADS = nthreads(kEgw);
@@ -317,6 +345,7 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
 
       for (int tile = 0; tile < ntiles; ++tile) {
         // ------------------------------------------------ geometry of my point (nerf_utils.py:17-170)
+        const long long tile_g = (long long)u * a.tiles_per_unit + tile;   // index of this tile in the saved tensors
         const int q = tile * TILE + t;
         const bool valid = q < npts;
         const int qc = valid ? q : npts - 1;
@@ -426,10 +455,23 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
               const uint32_t row = row_u32 + (uint32_t)(cp >> 1) * ACT_PBLOCK;
               tmem_ld_wait();
               tmem_ld_32x16(tcol + cp * 32 + 16, v1);
-              epilogue16(v0, hh ? fb.x : fa.x, hh ? fb.y : fa.y, row, (cp & 1) * 4, c7);
-              tmem_ld_wait();
-              if (cp < 3) tmem_ld_32x16(tcol + (cp + 1) * 32, v0);
-              epilogue16(v1, hh ? fb.x : fa.x, hh ? fb.y : fa.y, row, (cp & 1) * 4 + 2, c7);
+              if (kSave) {
+                // element offset of (layer l, this tile, point group 4*cp, my channel)
+                const size_t so = ((((size_t)l * a.n_tiles_g + tile_g) * 16 + cp * 4) * W + (t + TILE * h)) * 8;
+                const size_t fo = (((size_t)tile_g * 16 + cp * 4) * W + (t + TILE * h)) * 8;
+                epilogue16_save(v0, hh ? fb.x : fa.x, hh ? fb.y : fa.y, row, (cp & 1) * 4, c7, a.save_acc + so,
+                                a.save_cos + so, l == D ? a.save_feat + fo : nullptr);
+                tmem_ld_wait();
+                if (cp < 3) tmem_ld_32x16(tcol + (cp + 1) * 32, v0);
+                epilogue16_save(v1, hh ? fb.x : fa.x, hh ? fb.y : fa.y, row, (cp & 1) * 4 + 2, c7,
+                                a.save_acc + so + 2 * W * 8, a.save_cos + so + 2 * W * 8,
+                                l == D ? a.save_feat + fo + 2 * W * 8 : nullptr);
+              } else {
+                epilogue16(v0, hh ? fb.x : fa.x, hh ? fb.y : fa.y, row, (cp & 1) * 4, c7);
+                tmem_ld_wait();
+                if (cp < 3) tmem_ld_32x16(tcol + (cp + 1) * 32, v0);
+                epilogue16(v1, hh ? fb.x : fa.x, hh ? fb.y : fa.y, row, (cp & 1) * 4 + 2, c7);
+              }
             }
           }
           tc_fence_before();
@@ -468,6 +510,11 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
           tc_fence_before();
           if (pt_role) {
           // rgb / xyz / mask sums of my ray (nerf_utils.py:315,329-336)
+          if (kSave && valid) {
+            float* ro = a.rgb_pt + (gray * N + k) * 3;
+            ro[0] = __uint_as_float(v4[0]) + brgb0; ro[1] = __uint_as_float(v4[1]) + brgb1; ro[2] = __uint_as_float(v4[2]) + brgb2;
+            a.w_pt[gray * N + k] = wgt;
+          }
           float vals[6];
           vals[0] = wgt * sigmoid_precise(__uint_as_float(v4[0]) + brgb0);
           vals[1] = wgt * sigmoid_precise(__uint_as_float(v4[1]) + brgb1);

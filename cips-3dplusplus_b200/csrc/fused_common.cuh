@@ -22,6 +22,17 @@ struct Args {
   const float* pts; const float* rays_d; const float* viewdirs; const float* z_vals;
   float* rgb_map; float* feature_map; float* sdf; float* mask; float* xyz; float* z_vals_out;
   int debug;   // bit 0: producer skips the weight copies (timing experiments only; results are garbage)
+  // ---- backward support (NULL in plain forward launches) ----
+  // bf16 tiles [layer][tile_g][point group 16][channel 256][8 points]; tile_g = unit * tiles_per_unit + tile
+  __nv_bfloat16* save_acc;    // pre-FiLM accumulators, layers 0..D
+  __nv_bfloat16* save_cos;    // cos of the SIREN argument, layers 0..D
+  __nv_bfloat16* save_feat;   // view-layer output (one layer)
+  float* rgb_pt;              // (b, n_rays, N, 3) raw rgb head output
+  float* w_pt;                // (b, n_rays, N) compositing weights
+  int tiles_per_unit; long long n_tiles_g;
+  // backward kernel inputs / outputs
+  const float* g_rgb_pt; const float* g_sdf_pt; const float* g_feature_map;
+  float* g_film; float* g_pts; float* g_viewdirs;
 };
 
 

@@ -60,6 +60,22 @@ __global__ void pack_small_kernel(c3d_raw_params raw, uint8_t* __restrict__ blob
     *reinterpret_cast<__nv_bfloat16*>(w0i + k16_offset(c, 12 + j)) = __float2bfloat16_rn(raw.views_weight[c * (W + 3) + W + j]);
   }
   *reinterpret_cast<__nv_bfloat16*>(w0i + k16_offset(c, 15)) = __float2bfloat16_rn(0.f);
+  // backward side images (layout comment in c3d_common.cuh)
+  uint8_t* b0 = blob + L.bwd16;
+  uint8_t* b1 = b0 + W0IMG_BYTES;
+  uint8_t* b2 = b1 + W0IMG_BYTES;
+  for (int k = 0; k < 16; ++k) {
+    const float v0 = k < 6 ? raw.rgb_weight[(k % 3) * W + c] : 0.f;
+    const float v1 = (k == 6 || k == 7) ? raw.sigma_weight[c] : 0.f;
+    *reinterpret_cast<__nv_bfloat16*>(b0 + k16_offset(c, k)) = __float2bfloat16_rn(v0);
+    *reinterpret_cast<__nv_bfloat16*>(b1 + k16_offset(c, k)) = __float2bfloat16_rn(v1);
+  }
+  for (int n = 0; n < 16; ++n) {
+    float v = 0.f;
+    if (n < 3) v = raw.pts_weight[0][c * 3 + n];
+    else if (n >= 4 && n < 7) v = raw.views_weight[c * (W + 3) + W + (n - 4)];
+    *reinterpret_cast<__nv_bfloat16*>(b2 + (size_t)(c >> 6) * (16 * 128) + sw128_offset(n, c & 63)) = __float2bfloat16_rn(v);
+  }
 }
 
 // grid (D+1 layers, 256/32 row tiles), block (32,8): transposes 32x32 tiles of the three 256x256
@@ -91,9 +107,13 @@ __global__ void pack_matrix_kernel(c3d_raw_params raw, uint8_t* __restrict__ blo
       float* dsn = reinterpret_cast<float*>(blob + L.w32) + (size_t)(l - 1) * W * W;
       for (int i = threadIdx.y; i < 32; i += 8) dsn[(size_t)(r0 + i) * W + c0 + threadIdx.x] = tile[i][threadIdx.x];
       uint8_t* img = blob + L.wbf16 + (size_t)(l - 1) * WBF16_LAYER_BYTES;
+      uint8_t* imgT = blob + L.wbf16T + (size_t)(l - 1) * WBF16_LAYER_BYTES;
       for (int i = threadIdx.y; i < 32; i += 8) {
         const int n = r0 + i, k = c0 + threadIdx.x;
         *reinterpret_cast<__nv_bfloat16*>(img + (size_t)(k >> 6) * WBF16_CHUNK_BYTES + sw128_offset(n, k & 63)) =
+            __float2bfloat16_rn(tile[i][threadIdx.x]);
+        // transposed image: row = input channel k, column = output channel n
+        *reinterpret_cast<__nv_bfloat16*>(imgT + (size_t)(n >> 6) * WBF16_CHUNK_BYTES + sw128_offset(k, n & 63)) =
             __float2bfloat16_rn(tile[i][threadIdx.x]);
       }
     }

@@ -8,7 +8,8 @@ import torch
 from conftest import GRAD_CASES, load_case, load_weights, rel_l2
 
 pytestmark = pytest.mark.gpu
-GRAD_REL = 1e-3
+GRAD_REL = 1e-3          # fp32 mode (FP32-pipe backward)
+GRAD_REL_BF16 = 5e-2     # bf16 mode (tensor-core backward of the bf16 forward; measured 3.3e-2 at D=8, ~1e-2 at D=2)
 
 
 def _dev():
@@ -44,7 +45,7 @@ def test_gradients_match_reference_autograd(case, precision):
                 rays_d=rel_l2(rays_d.grad.cpu().numpy(), c["g_rays_d"]),
                 viewdirs=rel_l2(viewdirs.grad.cpu().numpy(), c["g_viewdirs"]))
     print(case, precision, errs)
-    assert max(errs.values()) < GRAD_REL, errs
+    assert max(errs.values()) < (GRAD_REL if precision == "fp32" else GRAD_REL_BF16), errs
 
 
 def _volume_integration_torch(rgb, sdf, feat, z, rd, pts, beta):
