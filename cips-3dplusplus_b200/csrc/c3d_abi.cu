@@ -110,6 +110,23 @@ static int launch_style_prep(const void* packed, int D, const float* styles, int
 
 static int gcd_(int a, int b) { return b ? gcd_(b, a % b) : a; }
 
+// Work unit = whole rays whose points fill whole 128-row tiles when possible (u0 rays); about 6 tiles per unit for
+// large batches, fewer when that would leave slots of the persistent grid without work (small batches).
+static int unit_rays_for(const c3d_fwd_params* p) {
+  static int nsm = 0;
+  if (nsm == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) nsm = 148;
+  }
+  const int u0 = 128 / gcd_(p->n_samples, 128);
+  int ur = u0;
+  while (ur * p->n_samples < 6 * 128) ur += u0;
+  const long long want = 4ll * 2 * nsm;                       // >= 4 units per slot before units grow beyond u0
+  while (ur > u0 && (long long)p->batch * ((p->n_rays + ur - 1) / ur) < want) ur -= u0;
+  if (ur > p->n_rays) ur = p->n_rays;
+  return ur;
+}
+
 static void fused_fill_args(fused::Args& a, const c3d_fwd_params* p, const float2* film, const float4* first,
                             const float4* view) {
   memset(&a, 0, sizeof(a));
@@ -118,12 +135,8 @@ static void fused_fill_args(fused::Args& a, const c3d_fwd_params* p, const float
   a.film = film; a.first = first; a.view = view;
   a.batch = p->batch; a.n_rays = p->n_rays; a.n_samples = p->n_samples; a.D = p->D;
   a.img_size = p->img_size; a.static_viewdirs = p->static_viewdirs; a.input_kind = p->input_kind;
-  // unit = whole rays whose points fill whole 128-row tiles when possible, >= 6 tiles
-  const int u0 = 128 / gcd_(p->n_samples, 128);
-  int ur = u0;
-  while (ur * p->n_samples < 6 * 128) ur += u0;
-  if (ur > p->n_rays) ur = p->n_rays;
-  a.unit_rays = ur;
+  a.unit_rays = unit_rays_for(p);
+  const int ur = a.unit_rays;
   a.units_per_img = (p->n_rays + ur - 1) / ur;
   a.tiles_per_unit = (ur * p->n_samples + fused::TILE - 1) / fused::TILE;
   a.n_tiles_g = (long long)a.batch * a.units_per_img * a.tiles_per_unit;
@@ -427,10 +440,7 @@ static BwdTcWs bwd_tc_ws(const c3d_bwd_params* bp) {
   BwdTcWs w;
   memset(&w, 0, sizeof(w));
   const size_t b = (size_t)p->batch, P = (size_t)p->n_rays * p->n_samples, R = (size_t)p->n_rays, D = (size_t)p->D;
-  const int u0 = 128 / gcd_(p->n_samples, 128);
-  int ur = u0;
-  while (ur * p->n_samples < 6 * 128) ur += u0;
-  if (ur > p->n_rays) ur = p->n_rays;
+  const int ur = unit_rays_for(p);
   w.unit_rays = ur;
   w.units_per_img = (p->n_rays + ur - 1) / ur;
   w.tiles_per_unit = (ur * p->n_samples + fused::TILE - 1) / fused::TILE;

@@ -118,20 +118,6 @@ __device__ __forceinline__ void epilogue16_save(const uint32_t (&v)[16], float s
   }
 }
 
-// sin(acc * scale + shift) for 32 consecutive points of one channel -> bf16 -> four 16-byte stores into H^T.
-// row_addr = tile + block(p0) + channel*128 (shared address), u0 = unit index of p0 inside its 64-point block.
-__device__ __forceinline__ void epilogue32(const uint32_t (&v)[32], float scale, float shift, uint32_t row_addr,
-                                           int u0, int c7) {
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    float o[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = __sinf(fmaf(__uint_as_float(v[g * 8 + i]), scale, shift));
-    st_v4(row_addr + (uint32_t)(((u0 + g) ^ c7) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-          pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-  }
-}
-
 template <int kCluster, int kEgw, bool kSave = false>
 __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const Args a) {
   constexpr int EG_THREADS = kEgw * 32;
