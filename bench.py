@@ -144,6 +144,54 @@ def run_reference(args, cfg, rank, world):
     }))
 
 
+def side_measurements(m, params, devt, D, N, dev, timed):
+    """Two side lines SURVEY.md section 8(d) asks for, at N=1 only, outside the headline timed region:
+    (1) the standalone compositing kernel against the HBM roofline on reference-layout inputs
+    ((1056 N + 1152) algorithmic bytes per ray); (2) the reference's own formulation of the path as plain PyTorch
+    (cuBLAS + ATen, fp32 as the reference runs it, and under bf16 autocast) on the same GPU, on 8 images."""
+    import torch
+    import cips3dpp_b200 as c3d
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch_ref
+    out = {}
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    R = 16 * IMG * IMG
+    g = torch.Generator(device=dev).manual_seed(3)
+    rgb = torch.randn(R, N, 3, device=dev, generator=g)
+    sdf = 0.1 * torch.randn(R, N, 1, device=dev, generator=g)
+    feat = torch.randn(R, N, 256, device=dev, generator=g)
+    z = torch.sort(0.88 + 0.24 * torch.rand(R, N, device=dev, generator=g), dim=-1).values
+    rd = torch.randn(R, 3, device=dev, generator=g)
+    pts = torch.randn(R, N, 3, device=dev, generator=g)
+    beta = torch.tensor([0.1], device=dev)
+    ms, ms_min, _ = timed(lambda: c3d.Render.volume_integration(rgb, sdf, feat, z, rd, pts, sigmoid_beta=beta), 10, 3)
+    nbytes = (1056 * N + 1152) * R
+    hbm = peaks.get("hbm_gbs", 6500.0)
+    out["composite_kernel"] = {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                               "frac": nbytes / (ms * 1e-3) / 1e9 / hbm, "rays": R, "ms": ms,
+                               "bytes_per_ray": 1056 * N + 1152, "rays_per_s": R / (ms * 1e-3)}
+    del rgb, sdf, feat, z, rd, pts
+    nb = min(8, devt[0].shape[0])
+    tp = {k: torch.from_numpy(v).to(dev) for k, v in params.items()}
+    a = [t[:nb] for t in devt]
+
+    def torch_path():
+        with torch.no_grad():
+            return torch_ref.render_thumb(tp, a[0], a[1], a[2], a[3], a[4], IMG, N, False)
+
+    def torch_path_bf16():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return torch_path()
+    res = {}
+    for name, fn in (("fp32", torch_path), ("bf16_autocast", torch_path_bf16)):
+        ms, _, _ = timed(fn, 3, 2)
+        res[name] = {"images_per_s": nb / (ms * 1e-3), "rays_per_s": nb * IMG * IMG / (ms * 1e-3), "ms": ms}
+    out["torch_gpu_baseline"] = {"what": "reference formulation as plain PyTorch (cuBLAS + ATen) on this GPU",
+                                 "images": nb, **res}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,6 +201,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the compositing-kernel and torch-on-GPU side lines")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
@@ -252,6 +301,9 @@ def main():
         return float(t.item())
 
     ms_step, ms_e2e, ms_sp_m = maxr(ms_step), maxr(ms_e2e), maxr(ms_sp)
+    extras = {}
+    if world == 1 and not args.no_extras:
+        extras = side_measurements(m, params, devt, D, N, dev, timed)
     rays_step = B * IMG * IMG
     value = world * rays_step / (ms_step * 1e-3)
     e2e_value = world * rays_step / (ms_e2e * 1e-3)
@@ -291,6 +343,7 @@ def main():
                          "frac_of_burst": achieved / peaks.get("bf16_tflops", 1590.0)},
             "clocks": sampler.summary(),
         }
+        line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_baseline(cfg, min(B, 8), reps=2)
             line["cpu_baseline"] = cb

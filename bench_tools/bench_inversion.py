@@ -32,3 +32,16 @@ with torch.no_grad():
     e1.record(); torch.cuda.synchronize()
 print(json.dumps(dict(D=D, targets=n, images=2 * n, precision=prec, ms_fwd_bwd=ms, ms_fwd=e0.elapsed_time(e1) / K,
                       images_per_s=2 * n / (ms * 1e-3))))
+# the whole optimisation step (camera glue, forward, loss, backward, clipping, Adam) eagerly and as a CUDA graph
+tg = tgt[0::2].contiguous()
+w0 = torch.zeros(1, D + 1, 256, device=dev)
+inv.num_steps = 3
+inv.run(tg, w0)                                                      # warm: optimiser / allocator first-use costs
+for graph in (False, True):
+    t = {}
+    for steps in (10, 60):
+        inv.num_steps = steps
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        inv.run(tg, w0, cuda_graph=graph)
+        torch.cuda.synchronize(); t[steps] = time.perf_counter() - t0
+    print(json.dumps(dict(full_step_cuda_graph=graph, ms_per_step=(t[60] - t[10]) / 50 * 1e3, setup_s=t[10])))

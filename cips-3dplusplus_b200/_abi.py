@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libc3dpp.so")
 SRC = os.path.join(HERE, "csrc", "c3d_abi.cu")
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_LAYERS = 16
 MODE_FP32, MODE_BF16 = 0, 1
 INPUT_POSES, INPUT_POINTS = 0, 1
@@ -30,6 +30,14 @@ class RawParams(C.Structure):
                             "sigma_weight", "sigma_bias", "sigmoid_beta")]
 
 
+class ParamGrads(C.Structure):
+    _fields_ = [(n, _fp * MAX_LAYERS) for n in ("pts_weight", "pts_bias", "pts_gamma_weight", "pts_gamma_bias",
+                                                "pts_beta_weight", "pts_beta_bias")] + \
+        [(n, _fp) for n in ("views_weight", "views_bias", "views_gamma_weight", "views_gamma_bias",
+                            "views_beta_weight", "views_beta_bias", "rgb_weight", "rgb_bias",
+                            "sigma_weight", "sigma_bias", "sigmoid_beta")]
+
+
 class FwdParams(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("abi_version", "mode", "input_kind", "feat_layout", "batch", "n_rays",
                                          "n_samples", "D", "img_size", "static_viewdirs")] + \
@@ -42,7 +50,7 @@ class FwdParams(C.Structure):
 class BwdParams(C.Structure):
     _fields_ = [("fwd", FwdParams)] + \
         [(n, _fp) for n in ("g_rgb_map", "g_feature_map", "g_mask", "g_xyz", "g_sdf",
-                            "g_styles", "g_pts", "g_rays_d", "g_viewdirs", "g_cam_poses", "g_focal", "g_packed_fp32")]
+                            "g_styles", "g_pts", "g_rays_d", "g_viewdirs", "g_cam_poses", "g_focal", "g_params")]
 
 
 class RaygenParams(C.Structure):

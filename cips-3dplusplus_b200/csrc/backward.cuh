@@ -32,6 +32,7 @@ struct CompositeBwdArgs {
   float* g_features;  // (n_rays, N, n_feat) out or NULL (the MLP backward forms w * g_feature_map itself)
   float* g_pts;       // (n_rays, N, 3) out (overwritten)
   float* g_rays_d;    // (n_rays, 3) out (overwritten)
+  float* g_beta;      // optional scalar: d sigmoid_beta, atomically accumulated
 };
 
 __global__ void __launch_bounds__(256) composite_bwd_kernel(CompositeBwdArgs p) {
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(CompositeBwdArgs p) 
     if (lane == 0) GW[k] = acc;
   }
   __syncwarp();
-  float g_dn = 0.f;
+  float g_dn = 0.f, g_b = 0.f;
   for (int k0 = 0; k0 < N; k0 += 32) {
     const int k = k0 + lane;
     if (k < N) {
@@ -129,13 +130,16 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(CompositeBwdArgs p) 
       const float g_sigma = g_alpha * (dz * dnorm) * one_m_alpha;
       p.g_sdf[ray * N + k] = -g_sigma * s * (1.0f - s) * inv_beta * inv_beta + (p.g_sdf_in ? p.g_sdf_in[ray * N + k] : 0.f);
       g_dn = fmaf(g_alpha * sigma, one_m_alpha * dz, g_dn);
+      // sigma = s(-sdf/beta)/beta  =>  d sigma / d beta = (s (1-s) sdf / beta - s) / beta^2
+      g_b = fmaf(g_sigma, (s * (1.0f - s) * sdf[k] * inv_beta - s) * inv_beta * inv_beta, g_b);
       if (p.g_features) {
         // handled below (needs all lanes)
       }
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) g_dn += __shfl_xor_sync(0xffffffffu, g_dn, o);
+  for (int o = 16; o > 0; o >>= 1) { g_dn += __shfl_xor_sync(0xffffffffu, g_dn, o); g_b += __shfl_xor_sync(0xffffffffu, g_b, o); }
+  if (lane == 0 && p.g_beta) atomicAdd(p.g_beta, g_b);
   if (lane == 0) {
     const float c = dnorm > 0.f ? g_dn / dnorm : 0.f;
     p.g_rays_d[ray * 3 + 0] = c * rd[0]; p.g_rays_d[ray * 3 + 1] = c * rd[1]; p.g_rays_d[ray * 3 + 2] = c * rd[2];
@@ -164,11 +168,13 @@ struct MlpBwdArgs {
   float* g_film;                                   // (imgs, D+1, 256, 2): (sum g_a*acc, sum g_a), atomically accumulated
   float* g_pts;                                    // (pts, 3) += through layer 0
   float* g_viewdirs;                               // (imgs, n_rays, 3) atomically accumulated, or NULL
+  float* dump_h; float* dump_g; size_t dump_stride; // kDump: (D+1, pts, 256) layer outputs / accumulator cotangents
 };
 
 // smem: gT [256][F32_LD] (cotangent of the pre-FiLM accumulators, transposed) | wS [32][256] | pS, vS | red [8][256][2]
 constexpr size_t BWD_SMEM = sizeof(float) * ((size_t)W * F32_LD + (size_t)F32_KC * W + F32_TP * 8 + 8 * W * 2);
 
+template <bool kDump>
 __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(MlpBwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* gT = smem;
@@ -200,6 +206,16 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(MlpBwdArgs a) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) { pval[i] = p0 + ty * 8 + i < a.pts_per_img; pidx[i] = min(p0 + ty * 8 + i, a.pts_per_img - 1); }
 
+  // kDump: row-major (point, 256) stores of my 8x8 block, two float4 per point
+  auto dump_rows = [&](float* base, const float (&v)[8][8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (pval[i]) {
+        float4* o = reinterpret_cast<float4*>(base + (img_pt0 + pidx[i]) * W);
+        o[tx] = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+        o[32 + tx] = make_float4(v[i][4], v[i][5], v[i][6], v[i][7]);
+      }
+  };
   float g[8][8];                                   // cotangent of the layer's output h_l for my (point, channel) block
   // ---- view layer output cotangent: g_f = w * g_feature_map[ray] + Wrgb^T g_rgb
   {
@@ -233,6 +249,7 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(MlpBwdArgs a) {
       const float4 a0 = ap[tx], a1 = ap[32 + tx];
       const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       const float* v = vS + (ty * 8 + i) * 4;
+      float hv[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float2 f = a.film[((size_t)img * (D + 1) + l) * W + ch[j]];
@@ -241,19 +258,29 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(MlpBwdArgs a) {
           const float4 wv = reinterpret_cast<const float4*>(a.blob + a.L.wvdir)[ch[j]];
           accv += fmaf(wv.x, v[0], fmaf(wv.y, v[1], wv.z * v[2]));            // acc + Wv . v ; d a / d gamma = this + b
           arg = fmaf(f.x, accv, f.y);
-          const float ga = pval[i] ? g[i][j] * cosf(arg) : 0.f;
+          float sn, cn;
+          if (kDump) { sincosf(arg, &sn, &cn); hv[j] = sn; } else cn = cosf(arg);
+          const float ga = pval[i] ? g[i][j] * cn : 0.f;
           const float gs = ga * f.x;
           gv[i][0] = fmaf(gs, wv.x, gv[i][0]); gv[i][1] = fmaf(gs, wv.y, gv[i][1]); gv[i][2] = fmaf(gs, wv.z, gv[i][2]);
           cs[j].x = fmaf(ga, accv, cs[j].x); cs[j].y += ga;
           g[i][j] = ga * f.x;
         } else {
           arg = fmaf(f.x, accv, f.y);
-          const float ga = pval[i] ? g[i][j] * cosf(arg) : 0.f;
+          float sn, cn;
+          if (kDump) { sincosf(arg, &sn, &cn); hv[j] = sn; } else cn = cosf(arg);
+          const float ga = pval[i] ? g[i][j] * cn : 0.f;
           cs[j].x = fmaf(ga, accv, cs[j].x); cs[j].y += ga;
           g[i][j] = ga * f.x;                       // cotangent of acc_l
         }
       }
+      if (kDump && pval[i]) {                       // h_l row of this point
+        float4* o = reinterpret_cast<float4*>(a.dump_h + (size_t)l * a.dump_stride + (img_pt0 + pidx[i]) * W);
+        o[tx] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        o[32 + tx] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+      }
     }
+    if (kDump) dump_rows(a.dump_g + (size_t)l * a.dump_stride, g);
     if (l == D && a.g_viewdirs) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -313,9 +340,15 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_kernel(MlpBwdArgs a) {
       for (int i = 0; i < 8; ++i) {
         const float* q = pS + (ty * 8 + i) * 4;
         const float accv = fmaf(w.x, q[0], fmaf(w.y, q[1], w.z * q[2]));
-        const float ga = pval[i] ? g[i][j] * cosf(fmaf(f.x, accv, f.y)) : 0.f;
+        float sn, cn;
+        if (kDump) sincosf(fmaf(f.x, accv, f.y), &sn, &cn); else cn = cosf(fmaf(f.x, accv, f.y));
+        const float ga = pval[i] ? g[i][j] * cn : 0.f;
         cs[j].x = fmaf(ga, accv, cs[j].x); cs[j].y += ga;
         const float gs = ga * f.x;
+        if (kDump && pval[i]) {
+          a.dump_h[(img_pt0 + pidx[i]) * W + ch[j]] = sn;
+          a.dump_g[(img_pt0 + pidx[i]) * W + ch[j]] = gs;
+        }
         gp[i][0] = fmaf(gs, w.x, gp[i][0]); gp[i][1] = fmaf(gs, w.y, gp[i][1]); gp[i][2] = fmaf(gs, w.z, gp[i][2]);
       }
     }

@@ -9,6 +9,7 @@
 #include "fused_common.cuh"
 #include "fused_bf16_sm100.cuh"
 #include "backward.cuh"
+#include "param_grads.cuh"
 #include "fused_bwd_sm100.cuh"
 
 namespace c3d {
@@ -380,7 +381,7 @@ namespace c3d {
 struct BwdWs {
   size_t film, first, view, g_film, chunk, total;
   int chunk_imgs;
-  size_t c_acc, c_feat, c_rgb, c_sdf, c_w, c_grgb, c_gsdf, c_pts, c_rd, c_vd, c_z, c_gpts, c_grd, c_gvd;
+  size_t c_acc, c_feat, c_rgb, c_sdf, c_w, c_grgb, c_gsdf, c_pts, c_rd, c_vd, c_z, c_gpts, c_grd, c_gvd, c_dh, c_dg;
 };
 static BwdWs bwd_ws(const c3d_bwd_params* bp) {
   const c3d_fwd_params* p = &bp->fwd;
@@ -394,8 +395,9 @@ static BwdWs bwd_ws(const c3d_bwd_params* bp) {
   w.g_film = o; o += align_up(b * (D + 1) * W * sizeof(float2), 256);
   w.chunk = o;
   const bool poses = p->input_kind == C3D_INPUT_POSES;
+  const bool pgrads = bp->g_params != nullptr;
   const size_t per_img = P * (D + 1) * W * 4 + P * (12 + 4 + 4 + 12 + 4) + P * 12 + 2 * R * 12 +
-                         (poses ? P * 12 + 2 * R * 12 + P * 4 : 0) + 4096;
+                         (poses ? P * 12 + 2 * R * 12 + P * 4 : 0) + (pgrads ? 2 * P * (D + 1) * W * 4 : 0) + 4096;
   size_t ci = ((size_t)2 << 30) / per_img;
   if (ci < 1) ci = 1;
   if (ci > b) ci = b;
@@ -417,6 +419,10 @@ static BwdWs bwd_ws(const c3d_bwd_params* bp) {
     w.c_vd = c;  c += align_up(ci * R * 12, 256);
     w.c_z = c;   c += align_up(ci * P * 4, 256);
   }
+  if (pgrads) {
+    w.c_dh = c; c += align_up(ci * P * (D + 1) * W * 4, 256);
+    w.c_dg = c; c += align_up(ci * P * (D + 1) * W * 4, 256);
+  }
   w.total = o + c;
   return w;
 }
@@ -426,6 +432,7 @@ static BwdWs bwd_ws(const c3d_bwd_params* bp) {
 static bool bwd_uses_tensor_path(const c3d_bwd_params* bp) {
   const char* e = getenv("C3D_BWD");
   if (e && strcmp(e, "simt") == 0) return false;
+  if (bp->g_params) return false;                    // parameter gradients come from the FP32-pipe kernels
   return bp->fwd.mode == C3D_MODE_BF16 && bp->fwd.n_samples >= fused::MIN_SAMPLES;
 }
 
@@ -489,6 +496,15 @@ static int validate_bwd(const c3d_bwd_params* bp) {
   } else {
     C3D_CHECK_ARG(p->pts && p->rays_d && p->viewdirs && p->z_vals, "POINTS input needs pts, rays_d, viewdirs, z_vals");
   }
+  if (bp->g_params) {
+    const c3d_param_grads* g = bp->g_params;
+    bool all = g->views_weight && g->views_bias && g->views_gamma_weight && g->views_gamma_bias && g->views_beta_weight &&
+               g->views_beta_bias && g->rgb_weight && g->rgb_bias && g->sigma_weight && g->sigma_bias && g->sigmoid_beta;
+    for (int l = 0; l < p->D; ++l)
+      all = all && g->pts_weight[l] && g->pts_bias[l] && g->pts_gamma_weight[l] && g->pts_gamma_bias[l] &&
+            g->pts_beta_weight[l] && g->pts_beta_bias[l];
+    C3D_CHECK_ARG(all, "g_params must carry every parameter gradient pointer of layers 0..D-1, the view layer and the heads");
+  }
   const size_t need = bwd_uses_tensor_path(bp) ? bwd_tc_ws(bp).total : bwd_ws(bp).total;
   C3D_CHECK_ARG(p->workspace && p->workspace_bytes >= need, "workspace too small: %zu < %zu", p->workspace_bytes, need);
   C3D_CHECK_ARG(aligned16(p->workspace) && aligned16(bp->g_feature_map), "workspace / g_feature_map must be 16-byte aligned");
@@ -533,7 +549,18 @@ static int backward_simt(const c3d_bwd_params* bp, cudaStream_t st) {
   if (rc != C3D_OK) return rc;
   C3D_CUDA(cudaMemsetAsync(g_film, 0, (size_t)p->batch * (D + 1) * W * sizeof(float2), st));
   C3D_CUDA(cudaFuncSetAttribute(mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F32_SMEM));
-  C3D_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
+  C3D_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
+  C3D_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
+  const c3d_param_grads* pg = bp->g_params;
+  if (pg) {                                          // everything below accumulates with atomics
+    for (int l = 0; l < D; ++l) C3D_CUDA(cudaMemsetAsync(pg->pts_weight[l], 0, sizeof(float) * W * (l == 0 ? 3 : W), st));
+    C3D_CUDA(cudaMemsetAsync(pg->views_weight, 0, sizeof(float) * W * (W + 3), st));
+    C3D_CUDA(cudaMemsetAsync(pg->rgb_weight, 0, sizeof(float) * 3 * W, st));
+    C3D_CUDA(cudaMemsetAsync(pg->rgb_bias, 0, sizeof(float) * 3, st));
+    C3D_CUDA(cudaMemsetAsync(pg->sigma_weight, 0, sizeof(float) * W, st));
+    C3D_CUDA(cudaMemsetAsync(pg->sigma_bias, 0, sizeof(float), st));
+    C3D_CUDA(cudaMemsetAsync(pg->sigmoid_beta, 0, sizeof(float), st));
+  }
   const float* beta_ptr = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p->packed) + L.scal) + 4;
   for (int i0 = 0; i0 < p->batch; i0 += w.chunk_imgs) {
     const int ni = (p->batch - i0 < w.chunk_imgs) ? p->batch - i0 : w.chunk_imgs;
@@ -584,7 +611,7 @@ static int backward_simt(const c3d_bwd_params* bp, cudaStream_t st) {
     c.g_sdf_in = bp->g_sdf ? bp->g_sdf + (size_t)i0 * P : nullptr;
     c.weights = reinterpret_cast<float*>(ck + w.c_w); c.g_rgb = reinterpret_cast<float*>(ck + w.c_grgb);
     c.g_sdf = reinterpret_cast<float*>(ck + w.c_gsdf); c.g_features = nullptr;
-    c.g_pts = g_pts; c.g_rays_d = g_rd;
+    c.g_pts = g_pts; c.g_rays_d = g_rd; c.g_beta = pg ? pg->sigmoid_beta : nullptr;
     composite_bwd_kernel<<<(unsigned)((c.n_rays + 7) / 8), 256, 0, st>>>(c);
     C3D_LAUNCH_CHECK();
     // 3. MLP backward
@@ -595,8 +622,46 @@ static int backward_simt(const c3d_bwd_params* bp, cudaStream_t st) {
     mb.save_acc = m.save_acc; mb.save_stride = m.save_stride;
     mb.weights = c.weights; mb.g_feature_map = c.g_feature_map; mb.g_rgb = c.g_rgb; mb.g_sdf = c.g_sdf;
     mb.g_film = g_film + (size_t)i0 * (D + 1) * W * 2; mb.g_pts = g_pts; mb.g_viewdirs = g_vd;
-    mlp_bwd_kernel<<<(unsigned)(ni * mb.tiles_per_img), 256, BWD_SMEM, st>>>(mb);
+    mb.dump_h = pg ? reinterpret_cast<float*>(ck + w.c_dh) : nullptr;
+    mb.dump_g = pg ? reinterpret_cast<float*>(ck + w.c_dg) : nullptr;
+    mb.dump_stride = (size_t)ni * P * W;
+    if (pg) mlp_bwd_kernel<true><<<(unsigned)(ni * mb.tiles_per_img), 256, BWD_SMEM, st>>>(mb);
+    else mlp_bwd_kernel<false><<<(unsigned)(ni * mb.tiles_per_img), 256, BWD_SMEM, st>>>(mb);
     C3D_LAUNCH_CHECK();
+    // 3b. parameter gradients of this chunk from the dumped layer outputs H[l] / accumulator cotangents G[l]
+    if (pg) {
+      const long long np = (long long)ni * P;
+      const int splits = (int)((np + 4095) / 4096 < 74 ? (np + 4095) / 4096 : 74);
+      const int per_cta = (int)(((np + splits - 1) / splits + WG_PC - 1) / WG_PC * WG_PC);
+      for (int l = 1; l <= D; ++l) {
+        wgrad_gemm_kernel<<<dim3(4, splits), 256, 0, st>>>(mb.dump_g + (size_t)l * mb.dump_stride, mb.dump_h + (size_t)(l - 1) * mb.dump_stride,
+                                                          np, per_cta, l < D ? pg->pts_weight[l] : pg->views_weight, l < D ? W : W + 3);
+        C3D_LAUNCH_CHECK();
+      }
+      HeadWgradArgs h;
+      memset(&h, 0, sizeof(h));
+      h.pts_per_img = (int)P;
+      const int hs = (int)((P + 2047) / 2048 < 64 ? (P + 2047) / 2048 : 64);
+      h.pts_per_cta = (int)((P + hs - 1) / hs);
+      // W_0 (256,3): G[0]^T (pts * 2/(far-near))
+      h.a = pts; h.a_cols = 3; h.a_div = 1; h.H = mb.dump_g; h.near = m.near; h.far = m.far;
+      h.out = pg->pts_weight[0]; h.so_j = 1; h.so_c = 3; h.out_sum = nullptr;
+      head_wgrad_kernel<<<dim3(hs, ni), 256, 0, st>>>(h);
+      C3D_LAUNCH_CHECK();
+      // view-direction columns of W_view (256,259)
+      h.a = viewdirs; h.a_div = p->n_samples; h.H = mb.dump_g + (size_t)D * mb.dump_stride; h.near = h.far = nullptr;
+      h.out = pg->views_weight + W; h.so_j = 1; h.so_c = W + 3;
+      head_wgrad_kernel<<<dim3(hs, ni), 256, 0, st>>>(h);
+      C3D_LAUNCH_CHECK();
+      // rgb head (3,256) on the view layer's output, sigma head (1,256) on h_{D-1}
+      h.a = c.g_rgb; h.a_div = 1; h.H = mb.dump_h + (size_t)D * mb.dump_stride; h.out = pg->rgb_weight; h.so_j = W; h.so_c = 1;
+      h.out_sum = pg->rgb_bias;
+      head_wgrad_kernel<<<dim3(hs, ni), 256, 0, st>>>(h);
+      C3D_LAUNCH_CHECK();
+      h.a = c.g_sdf; h.a_cols = 1; h.H = mb.dump_h + (size_t)(D - 1) * mb.dump_stride; h.out = pg->sigma_weight; h.out_sum = pg->sigma_bias;
+      head_wgrad_kernel<<<dim3(hs, ni), 256, 0, st>>>(h);
+      C3D_LAUNCH_CHECK();
+    }
     // 4. POSES entry: chain to the camera
     if (poses && (bp->g_cam_poses || bp->g_focal)) {
       dim3 grid((unsigned)((R + 127) / 128), ni);
@@ -607,6 +672,11 @@ static int backward_simt(const c3d_bwd_params* bp, cudaStream_t st) {
   }
   if (bp->g_styles) {
     film_bwd_kernel<<<dim3(D + 1, p->batch), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(p->packed), L, g_film, bp->g_styles);
+    C3D_LAUNCH_CHECK();
+  }
+  if (pg) {
+    film_param_bwd_kernel<<<dim3(D + 1, W), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(p->packed), L, *pg, g_film, film,
+                                                           p->styles, p->batch);
     C3D_LAUNCH_CHECK();
   }
   return C3D_OK;
@@ -727,7 +797,7 @@ int c3d_composite_backward(const c3d_composite_params* p, c3d_stream_t stream) {
   c.rgb = p->rgb; c.sdf = p->sdf; c.features = p->features; c.z_vals = p->z_vals; c.rays_d = p->rays_d; c.pts = p->pts;
   c.g_rgb_map = p->g_rgb_map; c.g_feature_map = p->g_feature_map; c.g_xyz = p->g_xyz; c.g_mask = p->g_mask;
   c.weights = p->weights; c.g_rgb = p->g_rgb; c.g_sdf = p->g_sdf; c.g_features = p->g_features; c.g_pts = p->g_pts;
-  c.g_rays_d = p->g_rays_d;
+  c.g_rays_d = p->g_rays_d; c.g_beta = p->g_sigmoid_beta;   // accumulated (+=): zero it before the call
   composite_bwd_kernel<<<(unsigned)((p->n_rays + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(c);
   C3D_LAUNCH_CHECK();
   return C3D_OK;

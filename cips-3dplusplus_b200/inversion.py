@@ -49,33 +49,76 @@ class FlipInversion:
                                    static_viewdirs=self.static_viewdirs)
         return out["rgb_map"].reshape(n * 2, S, S, 3).permute(0, 3, 1, 2)
 
-    def run(self, targets, w_init, azim_init=None, elev_init=None, callback=None):
-        """targets (n, 3, S, S) in [-1, 1]; w_init (1 or n, D+1, 256).  Returns dict(w, azim, elev, losses)."""
+    def run(self, targets, w_init, azim_init=None, elev_init=None, callback=None, cuda_graph=False):
+        """targets (n, 3, S, S) in [-1, 1]; w_init (1 or n, D+1, 256).  Returns dict(w, azim, elev, losses).
+
+        `cuda_graph=True` captures one whole optimisation step (camera glue, forward, loss, backward, clipping,
+        both Adam updates) into a CUDA graph and replays it `num_steps` times; only the two learning rates are
+        written from the host between replays.  It needs frozen renderer weights, a capturable `loss_fn`, and is
+        refused together with a cross-rank shared latent (the all-reduce stays outside graphs)."""
         dev, n = targets.device, targets.shape[0]
         tgt = torch.stack([targets, targets.flip(-1)], 1).reshape(n * 2, *targets.shape[1:])
         nw = 1 if self.shared_latent else n
         w = w_init.detach().expand(nw, -1, -1).clone().requires_grad_(True)
         azim = (torch.zeros(n, 2, 1, device=dev) if azim_init is None else azim_init.detach().clone()).requires_grad_(True)
         elev = (torch.zeros(n, 2, 1, device=dev) if elev_init is None else elev_init.detach().clone()).requires_grad_(True)
-        opt_w = torch.optim.Adam([w], betas=(0.9, 0.999), lr=self.lr_latent)
-        opt_c = torch.optim.Adam([azim, elev], betas=(0.9, 0.999), lr=self.lr_cam)
-        losses = []
-        for step in range(self.num_steps):
-            for opt, lr0 in ((opt_w, self.lr_latent), (opt_c, self.lr_cam)):
-                for g in opt.param_groups:
-                    g["lr"] = lr_ramp(step, self.num_steps, lr0)
+        multi_rank = self.shared_latent and torch.distributed.is_available() and torch.distributed.is_initialized()
+        if cuda_graph and multi_rank:
+            raise ValueError("cuda_graph=True cannot be combined with a latent shared across ranks")
+        if cuda_graph:                                               # learning rates live on the device
+            lr_w, lr_c = torch.zeros((), device=dev), torch.zeros((), device=dev)
+            opt_w = torch.optim.Adam([w], betas=(0.9, 0.999), lr=lr_w, capturable=True)
+            opt_c = torch.optim.Adam([azim, elev], betas=(0.9, 0.999), lr=lr_c, capturable=True)
+        else:
+            opt_w = torch.optim.Adam([w], betas=(0.9, 0.999), lr=self.lr_latent)
+            opt_c = torch.optim.Adam([azim, elev], betas=(0.9, 0.999), lr=self.lr_cam)
+
+        def one_step():
             thumbs = self.render_thumbs(w.expand(n, -1, -1) if self.shared_latent else w, azim, elev)
             loss = self.loss_fn(thumbs, tgt)
             opt_w.zero_grad(set_to_none=True)
             opt_c.zero_grad(set_to_none=True)
             loss.backward()
-            if self.shared_latent and torch.distributed.is_available() and torch.distributed.is_initialized():
+            if multi_rank:
                 c3d_dist.allreduce_grads([w.grad])
             torch.nn.utils.clip_grad_norm_([w], self.clip)
             torch.nn.utils.clip_grad_norm_([azim, elev], self.clip)
             opt_w.step()
             opt_c.step()
-            losses.append(loss.detach())
+            return loss.detach()
+
+        losses = []
+        if cuda_graph:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                            # warm-up at lr = 0: parameters do not move
+                for _ in range(2):
+                    one_step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            for opt in (opt_w, opt_c):                               # forget the warm-up in the Adam moments
+                for st in opt.state.values():
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss_static = one_step()
+            lrs = torch.tensor([[lr_ramp(s, self.num_steps, l0) for l0 in (self.lr_latent, self.lr_cam)]
+                                for s in range(self.num_steps)], dtype=torch.float32).to(dev)
+            for step in range(self.num_steps):
+                lr_w.copy_(lrs[step, 0])
+                lr_c.copy_(lrs[step, 1])
+                graph.replay()
+                losses.append(loss_static.clone())
+                if callback is not None:
+                    callback(step, losses[-1])
+            return dict(w=w.detach(), azim=azim.detach(), elev=elev.detach(), losses=torch.stack(losses))
+
+        for step in range(self.num_steps):
+            for opt, lr0 in ((opt_w, self.lr_latent), (opt_c, self.lr_cam)):
+                for g in opt.param_groups:
+                    g["lr"] = lr_ramp(step, self.num_steps, lr0)
+            losses.append(one_step())
             if callback is not None:
-                callback(step, loss)
+                callback(step, losses[-1])
         return dict(w=w.detach(), azim=azim.detach(), elev=elev.detach(), losses=torch.stack(losses))

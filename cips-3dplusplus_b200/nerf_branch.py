@@ -10,6 +10,7 @@ There is no PyTorch fallback: CPU tensors or a missing library raise.
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 
 import torch
@@ -140,6 +141,24 @@ class NerfBranch(nn.Module):
                self.sigmoid_beta]
         return ps
 
+    def _fill_param_struct(self, raw, tensors):
+        """Device pointers of `tensors` (in `_ordered_params` order) into a RawParams / ParamGrads struct."""
+        D = self.N_layers_renderer
+        it = iter(tensors)
+        for l in range(D + 1):
+            w, b, gw, gb, bw, bb = (next(it) for _ in range(6))
+            if l < D:
+                raw.pts_weight[l], raw.pts_bias[l] = w.data_ptr(), b.data_ptr()
+                raw.pts_gamma_weight[l], raw.pts_gamma_bias[l] = gw.data_ptr(), gb.data_ptr()
+                raw.pts_beta_weight[l], raw.pts_beta_bias[l] = bw.data_ptr(), bb.data_ptr()
+            else:
+                raw.views_weight, raw.views_bias = w.data_ptr(), b.data_ptr()
+                raw.views_gamma_weight, raw.views_gamma_bias = gw.data_ptr(), gb.data_ptr()
+                raw.views_beta_weight, raw.views_beta_bias = bw.data_ptr(), bb.data_ptr()
+        rw, rb, sw, sb, sbeta = (next(it) for _ in range(5))
+        raw.rgb_weight, raw.rgb_bias = rw.data_ptr(), rb.data_ptr()
+        raw.sigma_weight, raw.sigma_bias, raw.sigmoid_beta = sw.data_ptr(), sb.data_ptr(), sbeta.data_ptr()
+
     def packed_weights(self):
         """Kernel-layout weight blob, rebuilt when any parameter changed (keyed on tensor versions)."""
         ps = self._ordered_params()
@@ -154,20 +173,7 @@ class NerfBranch(nn.Module):
         keep = [_f32c(p) for p in ps]
         raw = _abi.RawParams()
         raw.D = D
-        it = iter(keep)
-        for l in range(D + 1):
-            w, b, gw, gb, bw, bb = (next(it) for _ in range(6))
-            if l < D:
-                raw.pts_weight[l], raw.pts_bias[l] = w.data_ptr(), b.data_ptr()
-                raw.pts_gamma_weight[l], raw.pts_gamma_bias[l] = gw.data_ptr(), gb.data_ptr()
-                raw.pts_beta_weight[l], raw.pts_beta_bias[l] = bw.data_ptr(), bb.data_ptr()
-            else:
-                raw.views_weight, raw.views_bias = w.data_ptr(), b.data_ptr()
-                raw.views_gamma_weight, raw.views_gamma_bias = gw.data_ptr(), gb.data_ptr()
-                raw.views_beta_weight, raw.views_beta_bias = bw.data_ptr(), bb.data_ptr()
-        rw, rb, sw, sb, sbeta = (next(it) for _ in range(5))
-        raw.rgb_weight, raw.rgb_bias = rw.data_ptr(), rb.data_ptr()
-        raw.sigma_weight, raw.sigma_bias, raw.sigmoid_beta = sw.data_ptr(), sb.data_ptr(), sbeta.data_ptr()
+        self._fill_param_struct(raw, keep)
         nbytes = lib.c3d_packed_bytes(D)
         blob = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
@@ -228,9 +234,7 @@ class NerfBranch(nn.Module):
         lib = _abi.load()
         dev = styles.device
         b, n_rays, N, img_size, static_viewdirs, nchw = meta
-        if any(needs[10:]):
-            raise NotImplementedError("gradients w.r.t. the renderer weights are not provided by libc3dpp (flip "
-                                      "inversion optimises latents and cameras); call renderer.requires_grad_(False)")
+        want_params = any(needs[10:])
         if nchw and g_feat is not None:
             g_feat = g_feat.transpose(1, 2)
         B = _abi.BwdParams()
@@ -253,13 +257,23 @@ class NerfBranch(nn.Module):
             g_a1 = torch.zeros_like(a1) if needs[5] else None
             B.g_cam_poses = None if g_a0 is None else g_a0.data_ptr()
             B.g_focal = None if g_a1 is None else g_a1.data_ptr()
+        g_params, pg = [], None
+        if want_params:                                              # training: the FP32-pipe backward also fills these
+            g_params = [torch.empty_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
+                        for p in self._ordered_params()]
+            pg = _abi.ParamGrads()
+            self._fill_param_struct(pg, g_params)
+            B.g_params = C.cast(C.pointer(pg), C.c_void_p)
         nws = lib.c3d_backward_workspace_bytes(B)
         ws = torch.empty(max(nws, 16), dtype=torch.uint8, device=dev)
         B.fwd.workspace, B.fwd.workspace_bytes = ws.data_ptr(), nws
         with torch.cuda.device(dev):
             _abi.check(lib.c3d_nerf_backward(B, torch.cuda.current_stream().cuda_stream), "c3d_nerf_backward")
         self.last_launch_count = lib.c3d_last_launch_count()
-        return (g_styles, g_a0, g_a1, g_a2, None, None, None) + (None,) * (len(needs) - 10)
+        g_params = [g.to(p.dtype) if need else None
+                    for g, p, need in zip(g_params, self._ordered_params(), needs[10:])] if want_params \
+            else [None] * (len(needs) - 10)
+        return (g_styles, g_a0, g_a1, g_a2, None, None, None) + tuple(g_params)
 
     def _run(self, kind, meta, styles, a0, a1, a2, a3, near, far):
         tensors = [styles, a0, a1, near, far] + [t for t in (a2, a3) if t is not None]

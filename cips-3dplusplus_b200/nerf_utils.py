@@ -130,13 +130,14 @@ class Camera:
         cam_dir = torch.stack([torch.cos(elev) * torch.sin(azim), torch.sin(elev), torch.cos(elev) * torch.cos(azim)],
                               dim=1).view(-1, 3)
         cam_loc = dist * cam_dir
-        up = torch.tensor([[0.0, 1.0, 0.0]], device=device) * torch.ones_like(dist)
+        up = torch.zeros(n, 3, device=device)                    # (0, 1, 0), built without a host copy (graph-capturable)
+        up[:, 1] = 1.0
         z_ax = F.normalize(cam_dir, eps=1e-5)
         x_ax = F.normalize(torch.cross(up, z_ax, dim=1), eps=1e-5)
         y_ax = F.normalize(torch.cross(z_ax, x_ax, dim=1), eps=1e-5)
-        degenerate = torch.isclose(x_ax, torch.tensor(0.0, device=device), atol=5e-3).all(dim=1, keepdim=True)
-        if degenerate.any():
-            x_ax = torch.where(degenerate, F.normalize(torch.cross(y_ax, z_ax, dim=1), eps=1e-5), x_ax)
+        # degenerate-x fix (:428-431) applied as an unconditional select: no host sync, same values
+        degenerate = (x_ax.abs() <= 5e-3).all(dim=1, keepdim=True)
+        x_ax = torch.where(degenerate, F.normalize(torch.cross(y_ax, z_ax, dim=1), eps=1e-5), x_ax)
         rot = torch.stack([x_ax, y_ax, z_ax], dim=2)              # columns are the camera axes
         extrinsics = torch.cat([rot, cam_loc[:, :, None]], dim=-1)
         return extrinsics, focal, near, far, viewpoint

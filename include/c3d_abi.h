@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define C3D_ABI_VERSION 3
+#define C3D_ABI_VERSION 4
 #define C3D_MAX_LAYERS 16
 #define C3D_W 256
 
@@ -65,6 +65,28 @@ typedef struct c3d_raw_params {
   const float* sigma_bias;                          /* (1) */
   const float* sigmoid_beta;                        /* (1) */
 } c3d_raw_params;
+
+/* Gradients w.r.t. the same tensors (same shapes), written by c3d_nerf_backward when requested.  Either the whole
+ * set is given (every pointer of layers 0..D-1, the view layer, both heads and sigmoid_beta non-NULL) or none. */
+typedef struct c3d_param_grads {
+  float* pts_weight[C3D_MAX_LAYERS];
+  float* pts_bias[C3D_MAX_LAYERS];
+  float* pts_gamma_weight[C3D_MAX_LAYERS];
+  float* pts_gamma_bias[C3D_MAX_LAYERS];
+  float* pts_beta_weight[C3D_MAX_LAYERS];
+  float* pts_beta_bias[C3D_MAX_LAYERS];
+  float* views_weight;
+  float* views_bias;
+  float* views_gamma_weight;
+  float* views_gamma_bias;
+  float* views_beta_weight;
+  float* views_beta_bias;
+  float* rgb_weight;
+  float* rgb_bias;
+  float* sigma_weight;
+  float* sigma_bias;
+  float* sigmoid_beta;
+} c3d_param_grads;
 
 typedef struct c3d_fwd_params {
   int32_t abi_version;       /* C3D_ABI_VERSION */
@@ -115,7 +137,8 @@ typedef struct c3d_bwd_params {
   float* g_viewdirs;         /* POINTS: (batch,n_rays,3) */
   float* g_cam_poses;        /* POSES: (batch,3,4) */
   float* g_focal;            /* POSES: (batch) */
-  float* g_packed_fp32;      /* optional: gradients of the fp32 section of the packed blob, or NULL */
+  const c3d_param_grads* g_params; /* HOST pointer or NULL: also return the gradients of the renderer's parameters
+                                      (training; runs the FP32-pipe backward in either mode) */
 } c3d_bwd_params;
 
 typedef struct c3d_raygen_params {

@@ -14,6 +14,9 @@ Outputs (committed):
                       cases reuse layers 0..D-1 + views/rgb/sigma heads of the same dict)
   case_*.npz          inputs (256-ray subsets of a 64x64 image) and reference outputs
   camera.npz          Camera.generate_camera_params + prepare_nerf_inputs checks
+  pgrads_*.npz        `--param-grads`: gradients w.r.t. every renderer parameter for the two *_grads cases, computed
+                      by the reference's autograd on the committed case inputs / cotangents (fp32; at D=8 the
+                      256x256 matrices are kept for layers 1 and 7 only, to bound the fixture size)
 """
 import os
 import sys
@@ -177,5 +180,34 @@ def main():
     np.savez_compressed(os.path.join(HERE, "camera.npz"), **cam)
 
 
+def param_grads():
+    """Reference autograd w.r.t. the renderer parameters on the committed *_grads cases (same loss as `case`)."""
+    nu, vr = import_reference()
+    torch.set_num_threads(os.cpu_count())
+    w = np.load(os.path.join(HERE, "weights_seed0.npz"))
+    sd8 = {k: torch.from_numpy(w[k].astype(np.float32)) for k in w.files}
+    for name in ("ffhq_d2_n24_grads", "ffhq_d8_n24_grads_static"):
+        c = np.load(os.path.join(HERE, f"case_{name}.npz"))
+        D = int(c["D"])
+        R = vr.VolumeFeatureRenderer(N_layers_renderer=D, input_dim=3, hidden_dim=256, style_dim=256,
+                                     view_dim=3, with_sdf=True, output_features=True)
+        R.load_state_dict(sub_state(sd8, D), strict=True)
+        t = lambda k: torch.from_numpy(c[k])
+        rgb_map, feat, sdf, mask, xyz, _ = R(pts=t("pts"), rays_d=t("rays_d"), viewdirs=t("viewdirs"),
+                                             z_vals=t("z_vals"), near=t("near"), far=t("far"), styles=t("styles"))
+        loss = (rgb_map * t("cot_rgb_map")).sum() + (feat * t("cot_feature_map")).sum() * 0.05 \
+            + (mask * t("cot_mask")).sum() + (xyz * t("cot_xyz")).sum()
+        assert abs(loss.item() - float(c["loss"])) <= 1e-4 * abs(float(c["loss"])), (loss.item(), float(c["loss"]))
+        names = [k for k, _ in R.named_parameters()]
+        gs = torch.autograd.grad(loss, [p for _, p in R.named_parameters()])
+        keep = lambda k, g: g.numel() < 65536 or D <= 2 or "views" in k or k.split(".")[2] in ("1", str(D - 1))   # size
+        np.savez_compressed(os.path.join(HERE, f"pgrads_{name}.npz"),
+                            **{k: g.numpy() for k, g in zip(names, gs) if keep(k, g)})
+        print(name, {k: float(g.abs().mean()) for k, g in zip(names, gs) if "weight" not in k or "pts_linears.1." in k})
+
+
 if __name__ == "__main__":
-    main()
+    if "--param-grads" in sys.argv:
+        param_grads()
+    else:
+        main()

@@ -140,13 +140,43 @@ def test_pose_gradients_match_points_entry():
     assert rel_l2(gs.cpu().numpy(), gs2.cpu().numpy()) < 1e-3
 
 
-def test_weight_gradients_are_refused_loudly():
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", GRAD_CASES)
+def test_parameter_gradients_match_reference_autograd(case, precision):
+    """d loss / d every renderer parameter (training path) vs the reference's autograd (tests/golden/pgrads_*.npz,
+    generated by make_golden.py --param-grads); asking for them routes both modes through the FP32-pipe backward."""
+    import os
+    from conftest import GOLDEN
+    c = load_case(case)
+    ref = np.load(os.path.join(GOLDEN, f"pgrads_{case}.npz"))
+    m = _module(int(c["D"]), precision).requires_grad_(True)
+    styles = _t(c["styles"], True)
+    rgb_map, feat, sdf, mask, xyz, _ = m(pts=_t(c["pts"]), rays_d=_t(c["rays_d"]), viewdirs=_t(c["viewdirs"]),
+                                         z_vals=_t(c["z_vals"]), near=_t(c["near"]), far=_t(c["far"]), styles=styles)
+    loss = (rgb_map * _t(c["cot_rgb_map"])).sum() + 0.05 * (feat * _t(c["cot_feature_map"])).sum() \
+        + (mask * _t(c["cot_mask"])).sum() + (xyz * _t(c["cot_xyz"])).sum()
+    loss.backward()
+    assert rel_l2(styles.grad.cpu().numpy(), c["g_styles"]) < GRAD_REL
+    got = dict(m.named_parameters())
+    worst = ("", 0.0)
+    for k in ref.files:
+        e = rel_l2(got[k].grad.cpu().numpy(), ref[k])
+        worst = max(worst, (k, e), key=lambda t: t[1])
+        assert got[k].grad.shape == ref[k].shape
+        assert e < GRAD_REL, (k, e)
+    for k, p_ in got.items():
+        assert p_.grad is not None and torch.isfinite(p_.grad).all(), k
+    print(case, precision, "worst parameter gradient rel-L2", worst)
+
+
+def test_frozen_subset_of_parameters_gets_no_gradient():
     c = load_case("ffhq_d2_n24")
-    m = _module(2, "fp32").requires_grad_(True)
+    m = _module(2, "fp32").requires_grad_(False)
+    m.sigmoid_beta.requires_grad_(True)
     out = m(pts=_t(c["pts"]), rays_d=_t(c["rays_d"]), viewdirs=_t(c["viewdirs"]), z_vals=_t(c["z_vals"]),
             near=_t(c["near"]), far=_t(c["far"]), styles=_t(c["styles"]))
-    with pytest.raises(NotImplementedError):
-        out[0].sum().backward()
+    out[0].sum().backward()
+    assert m.sigmoid_beta.grad is not None and m.network.rgb_linear.weight.grad is None
 
 
 def _torch_params(D):
@@ -191,3 +221,24 @@ def test_inversion_loss_curve_within_one_percent(precision):
     print(precision, "loss first/last", theirs[0], theirs[-1], "max rel diff", rel.max())
     assert theirs[-1] < 0.7 * theirs[0]                                # the loop actually optimises
     assert rel.max() < 1e-2, rel
+
+
+def test_inversion_cuda_graph_matches_eager():
+    """The CUDA-graph replay of the optimisation step follows the eager loop (same kernels, capturable Adam)."""
+    import cips3dpp_b200 as c3d
+    D, S, N, steps, n = 2, 16, 24, 25, 2
+    m = _module(D, "bf16")
+    g = torch.Generator().manual_seed(11)
+    w_true = (0.6 * torch.randn(n, 1, 256, generator=g)).repeat(1, D + 1, 1).to(_dev())
+    inv = c3d.FlipInversion(m, img_size=S, N_samples=N, num_steps=steps)
+    with torch.no_grad():
+        az = torch.tensor([[[0.15], [-0.15]], [[-0.1], [0.1]]], device=_dev())
+        el = torch.tensor([[[0.05], [0.05]], [[-0.05], [-0.05]]], device=_dev())
+        targets = inv.render_thumbs(w_true, az, el)[0::2].contiguous()
+    w0 = torch.zeros(1, D + 1, 256, device=_dev())
+    eager = inv.run(targets, w0)
+    graph = inv.run(targets, w0, cuda_graph=True)
+    le, lg = eager["losses"].cpu().numpy(), graph["losses"].cpu().numpy()
+    assert le[-1] < 0.8 * le[0]
+    assert np.abs(le - lg).max() / le.max() < 2e-3, (le, lg)
+    assert rel_l2(graph["w"].cpu().numpy(), eager["w"].cpu().numpy()) < 2e-2
