@@ -27,6 +27,10 @@ CONFIGS = {
     # name: (D, N, latents, poses/latent, cam cfg, description)
     "c2": dict(D=8, N=24, latents=32, sweep=8, fov=6.0, radius=0.12, azim=0.3, elev=0.15,
                desc="FFHQ v10 NeRF branch 64x64, D=8, N=24, 32 latents x 8-pose yaw sweep (BASELINE configs[1])"),
+    "c2d2": dict(D=2, N=24, latents=32, sweep=8, fov=6.0, radius=0.12, azim=0.3, elev=0.15,
+                 desc="FFHQ v10 NeRF branch 64x64 at the shipped r1024 depth D=2, N=24, 32 latents x 8-pose yaw sweep"),
+    "c3": dict(D=2, N=128, latents=8, sweep=1, fov=6.0, radius=0.12, azim=0.3, elev=0.15,
+               desc="FFHQ v10 multi-view render NeRF branch 64x64, D=2, N=128, 8 images (BASELINE configs[2], NeRF part)"),
     "c4": dict(D=6, N=24, latents=32, sweep=1, fov=15.0, radius=0.3, azim=3.14, elev=0.0837,
                desc="CompCars v10 NeRF branch 64x64, D=6, N=24, batch 32 (BASELINE configs[3])"),
     "c1": dict(D=8, N=24, latents=1, sweep=1, fov=6.0, radius=0.12, azim=0.0, elev=0.0,

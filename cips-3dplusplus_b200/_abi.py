@@ -7,7 +7,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libc3dpp.so")
+LIB_PATH = os.environ.get("C3D_LIB") or os.path.join(HERE, "libc3dpp.so")   # C3D_LIB: A/B builds (bench_tools)
 SRC = os.path.join(HERE, "csrc", "c3d_abi.cu")
 ABI_VERSION = 4
 MAX_LAYERS = 16

@@ -359,6 +359,20 @@ int c3d_umma_selftest(const uint16_t* a, const uint16_t* b, float* d, int32_t N,
   }
   C3D_CHECK_ARG(N >= 16 && N <= 256 && N % 16 == 0, "N=%d must be a multiple of 16 in [16,256]", N);
   C3D_CHECK_ARG(K >= 64 && K <= 256 && K % 64 == 0, "K=%d must be 16 or a multiple of 64 in [64,256]", K);
+  if (variant & 8) {   // CTA-pair MMA (cta_group::2): a is (256,K), d is (256,N); bit 0: A MN-major
+    const int smem_p = 65536 + (N / 2) * 128 * (K / 64) + 1024;
+    C3D_CUDA(cudaFuncSetAttribute(fused::umma_pair_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem_p; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    C3D_CUDA(cudaLaunchKernelEx(&cfg, fused::umma_pair_selftest_kernel, a, b, d, (int)N, (int)K, (int)(variant & 1)));
+    C3D_LAUNCH_CHECK();
+    return C3D_OK;
+  }
   if (variant != 0) {  // MN-major operand layouts (bit 0: A, bit 1: B, bit 2: diagnostic LBO/SBO exchange)
     C3D_CHECK_ARG(N % 64 == 0, "MN-major self-test needs N %% 64 == 0 (got %d)", N);
     const int smem_mn = 2 * 65536 + 1024;

@@ -214,4 +214,63 @@ __global__ void __launch_bounds__(128, 1) umma_mn_selftest_kernel(const uint16_t
 }
 
 
+// Self-test of the CTA-pair MMA (cta_group::2), launched as ONE cluster of two CTAs:
+//   D[256][N] = A[256][K] * B[N][K]^T ; CTA r stages A rows r*128.. and B rows r*N/2.. ; the leader issues, both read back.
+// variant bit 0: A stored MN-major ([k][m], the compositing operand view).
+__global__ void __launch_bounds__(128, 1) umma_pair_selftest_kernel(const uint16_t* __restrict__ A, const uint16_t* __restrict__ B,
+                                                                     float* __restrict__ Dout, int N, int K, int variant) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                       // K-major: K/64 chunks x [128][64] ; MN-major: 2 blocks of [K rows][64 m]
+  uint8_t* sB = smem + 65536;               // K/64 chunks x [N/2][64]
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tbase;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const bool a_mn = variant & 1;
+  const int nh = N / 2;
+  const uint32_t blk = (uint32_t)K * 128u;
+  for (int idx = threadIdx.x; idx < 128 * K; idx += 128) {
+    const int r = idx / K, k = idx - r * K;
+    const uint32_t off = a_mn ? (uint32_t)(r >> 6) * blk + (uint32_t)k * 128u + (uint32_t)((((r & 63) >> 3) ^ (k & 7)) << 4) + (uint32_t)(r & 7) * 2u
+                              : (uint32_t)(k >> 6) * 16384u + sw128_offset(r, k & 63);
+    *reinterpret_cast<uint16_t*>(sA + off) = A[(size_t)(rank * 128 + r) * K + k];
+  }
+  for (int idx = threadIdx.x; idx < nh * K; idx += 128) {
+    const int r = idx / K, k = idx - r * K;
+    *reinterpret_cast<uint16_t*>(sB + (k >> 6) * (nh * 128) + sw128_offset(r, k & 63)) = B[(size_t)(rank * nh + r) * K + k];
+  }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 1) { tmem_alloc_pair(&tbase, 256); tmem_relinquish_pair(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tb = tbase;
+  if (rank == 0 && threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_bf16(256, (uint32_t)N, a_mn ? 1u : 0u, 0u);
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint64_t ad = a_mn ? umma_desc_mnmajor_sw128(smem_u32(sA) + ks * 2048, blk)
+                               : umma_desc_kmajor_sw128(smem_u32(sA + (ks >> 2) * 16384)) + 2 * (ks & 3);
+      const uint64_t bd = umma_desc_kmajor_sw128(smem_u32(sB + (ks >> 2) * (nh * 128))) + 2 * (ks & 3);
+      umma_bf16_ss_pair(tb, ad, bd, idesc, ks != 0);
+    }
+    umma_commit_pair(&bar, (uint16_t)0x3);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  const uint32_t taddr = tb + ((uint32_t)(warp * 32) << 16);
+  for (int c0 = 0; c0 < N; c0 += 4) {
+    uint32_t v4[4];
+    tmem_ld_32x4(taddr + c0, v4);
+    tmem_ld_wait();
+    for (int jx = 0; jx < 4; ++jx) Dout[(size_t)(rank * 128 + threadIdx.x) * N + c0 + jx] = __uint_as_float(v4[jx]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc_pair(tb, 256); }
+}
+
 }}  // namespace c3d::fused

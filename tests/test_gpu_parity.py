@@ -63,6 +63,23 @@ def test_umma_tile_product(N, K):
     np.testing.assert_array_equal(d.cpu().numpy(), a @ b.T)      # small integers: exact in bf16 x bf16 -> fp32
 
 
+@pytest.mark.parametrize("N,K,a_mn", [(256, 256, 0), (256, 64, 0), (16, 256, 0), (32, 128, 1), (128, 128, 1)])
+def test_umma_cta_pair_product(N, K, a_mn):
+    """cta_group::2 MMA issued by the leader CTA of a 2-CTA cluster: D[256][N], A rows and B rows split across the pair."""
+    import cips3dpp_b200 as c3d
+    lib = c3d._abi.load()
+    rng = np.random.default_rng(N * 7 + K + a_mn)
+    a = rng.integers(-4, 5, size=(256, K)).astype(np.float32)
+    b = rng.integers(-4, 5, size=(N, K)).astype(np.float32)
+    ta = _t(a).to(torch.bfloat16).view(torch.int16)
+    tb = _t(b).to(torch.bfloat16).view(torch.int16)
+    d = torch.full((256, N), float("nan"), device=_dev())
+    c3d._abi.check(lib.c3d_umma_selftest(ta.data_ptr(), tb.data_ptr(), d.data_ptr(), N, K, 8 | a_mn,
+                                         torch.cuda.current_stream().cuda_stream), "c3d_umma_selftest")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d.cpu().numpy(), a @ b.T)
+
+
 def test_umma_k16_operand_layout():
     """K=16 no-swizzle operand layout used by the layer-0 split product (fused v2)."""
     import cips3dpp_b200 as c3d
