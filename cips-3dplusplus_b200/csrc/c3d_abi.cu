@@ -8,6 +8,7 @@
 #include "mlp_fp32.cuh"
 #include "fused_common.cuh"
 #include "fused_bf16_sm100.cuh"
+#include "fused_pair_sm100.cuh"
 #include "backward.cuh"
 #include "param_grads.cuh"
 #include "fused_bwd_sm100.cuh"
@@ -23,8 +24,20 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// bf16 forward: C3D_FWD=pair selects the CTA-pair kernel (fused_pair_sm100.cuh), C3D_FWD=v3 the single-CTA one.
+#ifndef C3D_FWD_DEFAULT_PAIR
+#define C3D_FWD_DEFAULT_PAIR 0
+#endif
+static bool fwd_uses_pair(const c3d_fwd_params* p) {
+  const char* e = getenv("C3D_FWD");
+  bool pair = C3D_FWD_DEFAULT_PAIR != 0;
+  if (e && strcmp(e, "v3") == 0) pair = false;
+  if (e && strcmp(e, "pair") == 0) pair = true;
+  return pair && p->mode == C3D_MODE_BF16 && p->n_samples >= fused::MIN_SAMPLES;
+}
+
 struct FwdWs {
-  size_t film, first, view, chunk, total;
+  size_t film, first, view, wimg, kimg, chunk, total;
   int chunk_imgs;
   size_t c_feat, c_rgb, c_pts, c_rd, c_vd, c_z;   // offsets inside the fp32 chunk area
 };
@@ -35,6 +48,11 @@ static FwdWs fwd_ws(const c3d_fwd_params* p) {
   w.film = o;  o += align_up(b * (p->D + 1) * W * sizeof(float2), 256);
   w.first = o; o += align_up(b * W * sizeof(float4), 256);
   w.view = o;  o += align_up(b * W * sizeof(float4), 256);
+  w.wimg = w.kimg = 0;
+  if (fwd_uses_pair(p)) {
+    w.wimg = o; o += align_up(b * p->D * pairk::WIMG_LAYER_BYTES, 1024);
+    w.kimg = o; o += align_up(b * (p->D + 1) * pairk::KIMG_LAYER_BYTES, 1024);
+  }
   w.chunk = o;
   w.chunk_imgs = 0;
   w.c_feat = w.c_rgb = w.c_pts = w.c_rd = w.c_vd = w.c_z = 0;
@@ -186,9 +204,51 @@ static int fused_launch(const fused::Args& a, int kind, cudaStream_t st) {
   return C3D_OK;
 }
 
+// CTA-pair forward: per-image weight images, then one persistent launch of 2-CTA clusters (one CTA per SM).
+static int forward_pair(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st) {
+  int dev = 0, nsm = 0;
+  C3D_CUDA(cudaGetDevice(&dev));
+  C3D_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  uint8_t* ws = reinterpret_cast<uint8_t*>(p->workspace);
+  fused::Args a;
+  fused_fill_args(a, p, reinterpret_cast<const float2*>(ws + w.film), reinterpret_cast<const float4*>(ws + w.first),
+                  reinterpret_cast<const float4*>(ws + w.view));
+  // pair-unit = 2 * unit_rays rays of one image; shrink units while the persistent grid would be short of work
+  const int u0 = 128 / gcd_(p->n_samples, 128);
+  int ur = u0;
+  while (ur * p->n_samples < 6 * 128) ur += u0;
+  while (ur > u0 && (long long)p->batch * ((p->n_rays + 2 * ur - 1) / (2 * ur)) < 4ll * nsm) ur -= u0;
+  if (ur > p->n_rays) ur = p->n_rays;
+  a.unit_rays = ur;
+  a.units_per_img = (p->n_rays + 2 * ur - 1) / (2 * ur);
+  a.wimg = ws + w.wimg; a.kimg = ws + w.kimg;
+  { const char* e = getenv("C3D_STAGGER"); a.stagger = e ? atoi(e) : 0; }
+  film_weights_kernel<<<dim3(8, p->D, p->batch), 256, 0, st>>>(a.blob, a.L, a.film, ws + w.wimg);
+  C3D_LAUNCH_CHECK();
+  film_k16_kernel<<<dim3(p->D + 1, p->batch), 256, 0, st>>>(a.blob, a.L, a.film, ws + w.kimg);
+  C3D_LAUNCH_CHECK();
+  const long long total_pu = (long long)p->batch * a.units_per_img;
+  int grid = nsm & ~1;
+  if ((long long)grid > ((total_pu + 1) & ~1ll)) grid = (int)((total_pu + 1) & ~1ll);
+  const char* genv = getenv("C3D_GRID");
+  if (genv && atoi(genv) > 0) grid = (atoi(genv) + 1) & ~1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(pairk::NTHREADS); cfg.dynamicSmemBytes = pairk::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  C3D_CUDA(cudaFuncSetAttribute(pairk::fused_forward_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pairk::SMEM_BYTES));
+  C3D_CUDA(cudaLaunchKernelEx(&cfg, pairk::fused_forward_pair_kernel, a));
+  C3D_LAUNCH_CHECK();
+  return C3D_OK;
+}
+
 static int forward_bf16(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st) {
   C3D_CHECK_ARG(p->n_samples >= fused::MIN_SAMPLES, "bf16 mode needs n_samples >= %d (got %d); use C3D_MODE_FP32",
                 fused::MIN_SAMPLES, p->n_samples);
+  if (fwd_uses_pair(p)) return forward_pair(p, w, st);
   uint8_t* ws = reinterpret_cast<uint8_t*>(p->workspace);
   fused::Args a;
   fused_fill_args(a, p, reinterpret_cast<const float2*>(ws + w.film), reinterpret_cast<const float4*>(ws + w.first),

@@ -22,6 +22,8 @@ struct Args {
   const float* pts; const float* rays_d; const float* viewdirs; const float* z_vals;
   float* rgb_map; float* feature_map; float* sdf; float* mask; float* xyz; float* z_vals_out;
   int debug;   // bit 0: producer skips the weight copies (timing experiments only; results are garbage)
+  int stagger;                                // CTA-pair kernel: slot 1 starts this many cycles after slot 0
+  const uint8_t* wimg; const uint8_t* kimg;   // CTA-pair kernel: per-image FiLM-folded weight images (film_weights_kernel)
   // ---- backward support (NULL in plain forward launches) ----
   // bf16 tiles [layer][tile_g][point group 16][channel 256][8 points]; tile_g = unit * tiles_per_unit + tile
   __nv_bfloat16* save_acc;    // pre-FiLM accumulators, layers 0..D

@@ -1,0 +1,636 @@
+// Fused NeRF-branch forward for sm_100a, CTA-pair version (fourth structure of the round; profiles/r01_fused.md).
+//
+// Reference semantics: exp/cips3d/volume_renderer.py:133-160,192-283, exp/cips3d/nerf_utils.py:17-218,230-338.
+//
+// What changed against fused_bf16_sm100.cuh and why
+//   * FiLM is folded into the GEMM.  film_weights_kernel (kernels_aux.cuh) writes, per image, bf16(gamma_c * W_l[c][k]) in
+//     the stage layout plus a K = 16 side image holding the shift (gamma b + beta, hi/lo split, multiplied by two "ones"
+//     slots of the point tile), the layer-0 weights and the view-direction columns.  The accumulator is the SIREN argument
+//     itself, so the epilogue is sin -> bf16 -> store with no per-channel constants.
+//   * That frees the orientation: D[point][channel] = H * W'^T, TMEM lanes are points.  A thread owns one point of its
+//     tile in every stage (geometry, layer epilogues, sdf / transmittance, rgb) and writes its own 512-byte row of the
+//     K-major activation tile.
+//   * Two CTAs of a cluster form a pair and issue ONE tcgen05.mma.cta_group::2 (M = 256 points = 128 per CTA, N = 256
+//     channels): every CTA stages only its 128 weight rows (half of B), reads its activation tile once per layer, and
+//     never exchanges activations.  Per 128 points and layer the SM moves 256 KB through shared memory instead of 448 KB
+//     and the 4 x 16 KB ring holds a whole layer of its weight half.
+//
+// Roles per CTA (384 threads): warp 0 weight producer (bulk copies of its half), warp 1 MMA issuer (leader CTA) or
+// barrier relay (peer CTA: forwards "my stage landed" to the leader), warp 2 TMEM allocator, warps 4-7 / 8-11 epilogue
+// group of slot 0 / 1.  Barriers the leader waits on (full, kfull, a_ready) collect arrivals from both CTAs; barriers
+// signalled by tcgen05.commit (empty, kempty, acc_full) are multicast to both.
+//
+// Per pair-tile (128 points per CTA) the issuer runs D+3 jobs, as before:
+//   job 0       layer 0    : K = 16 product of the point tile (hi, mid, hi, lo per coordinate, ones) with the K16 image
+//   job 1..D-1  hidden l   : K16 product (shift) + 16 x (256x256x16), A = activation tile, B = weight ring
+//   job D       sdf head   : 16 x (256x16x16), B = heads16 (8 rows per CTA)
+//   job D+1     view layer : K16 product (view direction, shift) + 16 x (256x256x16)
+//   job D+2     post       : compositing MMAs (A = feat^T as MN-major view, B = Wgt; N = 32, each CTA reads its own 16
+//                            columns) + rgb head
+#pragma once
+#include "c3d_common.cuh"
+#include "sm100_ptx.cuh"
+#include "fused_common.cuh"
+
+namespace c3d { namespace pairk {
+
+using namespace c3d::ptx;
+using fused::Args;
+using fused::TILE;
+using fused::ACT_BYTES;
+using fused::ACT_CHUNK;
+
+constexpr int NTHREADS = 384;
+constexpr int STAGE_BYTES = 128 * 128;         // [128 weight rows][64 k] bf16, K-major SWIZZLE_128B
+constexpr int NSTAGE = 4;
+constexpr int RAYS = 16;                       // rays touching one tile (n_samples >= 8)
+constexpr int AUX_BYTES = 4096;                // per slot: point / view tile ([128][16] k16) or Wgt ([16][128] sw128)
+constexpr int K16_BYTES = 4096;                // per slot: this CTA's half of the layer's K16 image ([128 rows][16])
+constexpr int HEADS_BYTES = 4096;              // 4 K-chunks x [8 rows][64 k]: this CTA's half of heads16
+constexpr size_t WIMG_LAYER_BYTES = (size_t)W * W * 2;   // per image and K=256 layer: [kc 4][half 2][16 KB]
+constexpr size_t KIMG_LAYER_BYTES = (size_t)W * 16 * 2;  // per image and layer 0..D: [half 2][4 KB]
+
+constexpr int SM_ACT = 0;
+constexpr int SM_STAGE = SM_ACT + 2 * ACT_BYTES;                 // 131072
+constexpr int SM_K16 = SM_STAGE + NSTAGE * STAGE_BYTES;          // 196608
+constexpr int SM_HEADS = SM_K16 + 2 * K16_BYTES;                 // 204800
+constexpr int SM_AUX = SM_HEADS + HEADS_BYTES;                   // 208896
+constexpr int SM_OM = SM_AUX + 2 * AUX_BYTES;                    // 217088  [slot][128] float
+constexpr int SM_RAYACC = SM_OM + 2 * TILE * 4;                  // 218112  [slot][RAYS*2][8] float
+constexpr int SM_MISC = SM_RAYACC + 2 * RAYS * 2 * 8 * 4;        // 220160
+constexpr int SM_TOTAL = SM_MISC + 256;
+constexpr int SMEM_BYTES = SM_TOTAL + 1024;
+
+struct Misc {
+  uint64_t full[NSTAGE], empty[NSTAGE], kfull[2], kempty[2], a_ready[2], acc_full[2];
+  uint32_t tmem_base;
+  float carry[2];
+#ifdef C3D_KERNEL_PROF
+  long long tl[8];           // timeline of one layer job of slot 0: see C3D_TL
+  int tl_job;
+#endif
+};
+#ifdef C3D_KERNEL_PROF
+#define C3D_TL(i) do { misc->tl[i] = clock64(); } while (0)
+#else
+#define C3D_TL(i) do { } while (0)
+#endif
+
+// ---- static schedule: pair-slot ps handles pair-units ps, ps + n_pairslots, ...; a pair-unit is 2 * unit_rays rays of one
+// image (the leader takes the first unit_rays); Args::units_per_img counts pair-units.
+__device__ __forceinline__ int pu_tiles(const Args& a, int pu) {
+  const int r0 = (pu % a.units_per_img) * 2 * a.unit_rays;
+  const int nr = min(a.unit_rays, a.n_rays - r0);            // the leader's share is never smaller than the peer's
+  return (nr * a.n_samples + TILE - 1) / TILE;
+}
+struct Cursor {
+  int pu, tile, ntiles, total, step;
+  __device__ __forceinline__ void init(const Args& a, int ps, int nps) {
+    total = a.batch * a.units_per_img; step = nps; pu = ps; tile = 0;
+    ntiles = pu < total ? pu_tiles(a, pu) : 0;
+  }
+  __device__ __forceinline__ bool valid() const { return pu < total; }
+  __device__ __forceinline__ void next_tile(const Args& a) {
+    if (++tile >= ntiles) { pu += step; tile = 0; ntiles = pu < total ? pu_tiles(a, pu) : 0; }
+  }
+};
+// Both slots of a pair run the same job index; when their pair-units belong to the same image they also use the same
+// weights, so slot 1 re-reads the ring stages slot 0 consumed instead of streaming the layer a second time.
+__device__ __forceinline__ bool same_weights(const Args& a, const Cursor& c0, const Cursor& c1) {
+  return c0.valid() && c1.valid() && c0.pu / a.units_per_img == c1.pu / a.units_per_img;
+}
+// kind of job j: 0 = layer 0 (K16 only), 1 = K = 256 layer, 2 = sdf head, 3 = post
+__device__ __forceinline__ int job_kind(int j, int D) { return j == 0 ? 0 : (j == D ? 2 : (j == D + 2 ? 3 : 1)); }
+__device__ __forceinline__ int job_film_layer(int j, int D) { return j == 0 ? 0 : (j <= D - 1 ? j : D); }   // index into kimg
+__device__ __forceinline__ int job_w_layer(int j, int D) { return j <= D - 1 ? j - 1 : D - 1; }             // index into wimg
+
+__device__ __forceinline__ void st_bf16(uint32_t smem_addr, float x) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(x));
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(smem_addr), "h"((unsigned short)r) : "memory");
+}
+__device__ __forceinline__ void st_v4(uint32_t smem_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// descriptor of the same layout `bytes` further (start-address field, 16-byte units; no carry out of the field here)
+__device__ __forceinline__ uint64_t desc_at(uint64_t base, uint32_t bytes) { return base + (uint64_t)(bytes >> 4); }
+
+// sin of 16 consecutive channels of one point -> bf16 -> two 16-byte stores into the point's row (units u0, u0 + 1)
+__device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], uint32_t row_addr, int u0, int r7, int dbg = 0) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    float o[8];
+#ifdef C3D_KERNEL_PROF
+    if (dbg & 4) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[g * 8 + i]) * 0.5f;
+    } else
+#endif
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = __sinf(__uint_as_float(v[g * 8 + i]));
+#ifdef C3D_KERNEL_PROF
+    if (dbg & 8) continue;
+#endif
+    st_v4(row_addr + (uint32_t)(((u0 + g) ^ r7) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+          pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  Misc* misc = reinterpret_cast<Misc*>(smem + SM_MISC);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform role index
+  const int lane = threadIdx.x & 31;
+  const int D = a.D, N = a.n_samples;
+  const int JOBS = D + 3;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_pairslots = (int)gridDim.x;          // 2 per cluster
+  const int ps0 = (int)(blockIdx.x >> 1) * 2;      // pair-slots of this cluster: ps0, ps0 + 1
+
+  if (threadIdx.x == 32) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&misc->full[i], leader ? 2 : 1); mbar_init(&misc->empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&misc->kfull[i], leader ? 2 : 1);
+      mbar_init(&misc->kempty[i], 1);
+      mbar_init(&misc->a_ready[i], 8);             // one arrival per epilogue warp of both CTAs (leader's copy is used)
+      mbar_init(&misc->acc_full[i], 1);
+    }
+    misc->carry[0] = misc->carry[1] = 1.0f;
+    fence_mbar_init();
+  }
+  if (warp == 2) { tmem_alloc_pair(&misc->tmem_base, 512); tmem_relinquish_pair(); }
+  {
+    // this CTA's half of heads16: rows rank*8 .. rank*8+7 of every K-chunk (one 1 KB swizzle atom each)
+    const uint8_t* src = a.blob + a.L.rgb16;
+    uint4* dst = reinterpret_cast<uint4*>(smem + SM_HEADS);
+    for (int i = threadIdx.x; i < HEADS_BYTES / 16; i += NTHREADS) {
+      const int kc = i >> 6, u = i & 63;
+      dst[i] = reinterpret_cast<const uint4*>(src + kc * 2048 + rank * 1024)[u];
+    }
+    float* ra = reinterpret_cast<float*>(smem + SM_RAYACC);
+    for (int i = threadIdx.x; i < 2 * RAYS * 2 * 8; i += NTHREADS) ra[i] = 0.f;
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = misc->tmem_base;
+
+  if (warp == 0) {
+   if (elect_one()) {
+    // ============================================================ weight producer (this CTA's halves)
+    Cursor c[2];
+    c[0].init(a, ps0, n_pairslots); c[1].init(a, ps0 + 1, n_pairslots);
+    int jb[2] = {0, 0};
+    uint32_t n = 0, kcnt[2] = {0u, 0u};
+    while (c[0].valid() || c[1].valid()) {
+      const bool shared = same_weights(a, c[0], c[1]);
+      for (int s = 0; s < 2; ++s) {
+        if (!c[s].valid()) continue;
+        const int j = jb[s], kind = job_kind(j, D);
+        const size_t img = (size_t)(c[s].pu / a.units_per_img);
+        if (kind <= 1) {
+          mbar_wait(&misc->kempty[s], (kcnt[s] & 1u) ^ 1u);
+          kcnt[s]++;
+          mbar_arrive_expect_tx(&misc->kfull[s], K16_BYTES);
+          bulk_g2s(smem + SM_K16 + s * K16_BYTES,
+                   a.kimg + (img * (D + 1) + job_film_layer(j, D)) * KIMG_LAYER_BYTES + rank * K16_BYTES, K16_BYTES, &misc->kfull[s]);
+          if (kind == 1 && !(shared && s == 1)) {
+            const uint8_t* wl = a.wimg + (img * D + job_w_layer(j, D)) * WIMG_LAYER_BYTES + rank * STAGE_BYTES;
+            for (int kc = 0; kc < NCHUNK; ++kc, ++n) {
+              const uint32_t st = n % NSTAGE, ph = (n / NSTAGE) & 1u;
+              mbar_wait(&misc->empty[st], ph ^ 1u);
+              mbar_arrive_expect_tx(&misc->full[st], STAGE_BYTES);
+              bulk_g2s(smem + SM_STAGE + st * STAGE_BYTES, wl + (size_t)kc * 2 * STAGE_BYTES, STAGE_BYTES, &misc->full[st]);
+            }
+          }
+        }
+        if (++jb[s] == JOBS) { jb[s] = 0; c[s].next_tile(a); }
+      }
+    }
+   }
+  } else if (warp == 1 && !leader) {
+   if (elect_one()) {
+    // ============================================================ relay: "my half landed" -> leader's full / kfull
+    Cursor c[2];
+    c[0].init(a, ps0, n_pairslots); c[1].init(a, ps0 + 1, n_pairslots);
+    int jb[2] = {0, 0};
+    uint32_t n = 0, kcnt[2] = {0u, 0u};
+    const uint32_t r_full = mapa_u32(smem_u32(&misc->full[0]), 0u), r_kfull = mapa_u32(smem_u32(&misc->kfull[0]), 0u);
+    while (c[0].valid() || c[1].valid()) {
+      const bool shared = same_weights(a, c[0], c[1]);
+      for (int s = 0; s < 2; ++s) {
+        if (!c[s].valid()) continue;
+        const int kind = job_kind(jb[s], D);
+        if (kind <= 1) {
+          mbar_wait(&misc->kfull[s], kcnt[s] & 1u);
+          kcnt[s]++;
+          mbar_arrive_remote(r_kfull + (uint32_t)s * 8u);
+          if (kind == 1 && !(shared && s == 1)) {
+            for (int kc = 0; kc < NCHUNK; ++kc, ++n) {
+              const uint32_t st = n % NSTAGE, ph = (n / NSTAGE) & 1u;
+              mbar_wait(&misc->full[st], ph);
+              mbar_arrive_remote(r_full + st * 8u);
+            }
+          }
+        }
+        if (++jb[s] == JOBS) { jb[s] = 0; c[s].next_tile(a); }
+      }
+    }
+   }
+  } else if (warp == 1) {
+   if (elect_one()) {
+    // ============================================================ MMA issuer (leader CTA, issues for the pair)
+    const uint32_t idesc_l = umma_idesc_bf16(256, 256, 0, 0);      // layers and K16 side products: both K-major
+    const uint32_t idesc_h = umma_idesc_bf16(256, 16, 0, 0);       // heads: B = 8 rows of heads16 per CTA
+    const uint32_t idesc_c = umma_idesc_bf16(256, 32, 1, 0);       // compositing: A = feat^T (MN-major view), B = Wgt
+    const uint32_t act_addr[2] = {smem_u32(smem + SM_ACT), smem_u32(smem + SM_ACT + ACT_BYTES)};
+    const uint32_t stage_base = smem_u32(smem + SM_STAGE);
+    const uint32_t aux_addr[2] = {smem_u32(smem + SM_AUX), smem_u32(smem + SM_AUX + AUX_BYTES)};
+    const uint32_t k16_addr[2] = {smem_u32(smem + SM_K16), smem_u32(smem + SM_K16 + K16_BYTES)};
+    const uint32_t heads_addr = smem_u32(smem + SM_HEADS);
+    Cursor c[2];
+    c[0].init(a, ps0, n_pairslots); c[1].init(a, ps0 + 1, n_pairslots);
+    int jb[2] = {0, 0};
+    uint32_t n = 0, kcnt[2] = {0u, 0u}, acnt[2] = {0u, 0u};
+#ifdef C3D_KERNEL_PROF
+    const bool prof = (a.debug & 2) != 0;
+#else
+    constexpr bool prof = false;
+#endif
+    long long t_ready = 0, t_full = 0, t_issue = 0, t_small = 0, t_mark = clock64(), t_begin = t_mark;
+    long long t_rk[4] = {0, 0, 0, 0};
+#define C3D_PPROF(acc) do { if (prof) { const long long now_ = clock64(); acc += now_ - t_mark; t_mark = now_; } } while (0)
+    uint32_t n_shared = 0;                 // first ring stage of slot 0's layer job when slot 1 re-reads the same weights
+    while (c[0].valid() || c[1].valid()) {
+      const bool shared = same_weights(a, c[0], c[1]);
+      for (int s = 0; s < 2; ++s) {
+        if (!c[s].valid()) continue;
+        const int j = jb[s], kind = job_kind(j, D);
+        const uint32_t tacc = tmem_base + (uint32_t)s * 256u;
+        C3D_PPROF(t_issue);
+#ifdef C3D_KERNEL_PROF
+        const bool tl_on = prof && blockIdx.x == 0 && s == 0 && (acnt[0] == 47u || acnt[0] == 48u);
+        if (tl_on && acnt[0] == 48u) {   // job after the logged one: when did its a_ready show up?
+          mbar_wait_cluster(&misc->a_ready[s], acnt[s] & 1u);
+          C3D_TL(6);
+          printf("c3d timeline slot0 job47 (kind %d): a_ready seen 0 | k16 issued %lld | last mma issued %lld | acc_full seen by epilogue %lld | "
+                 "epilogue stores done %lld | arrive done %lld | next a_ready seen %lld\n", job_kind(47 % JOBS, D), misc->tl[1] - misc->tl[0],
+                 misc->tl[2] - misc->tl[0], misc->tl[3] - misc->tl[0], misc->tl[4] - misc->tl[0], misc->tl[5] - misc->tl[0], misc->tl[6] - misc->tl[0]);
+        }
+#endif
+        mbar_wait_cluster(&misc->a_ready[s], acnt[s] & 1u);
+#ifdef C3D_KERNEL_PROF
+        if (tl_on && acnt[0] == 47u) C3D_TL(0);
+#endif
+        acnt[s]++;
+        if (prof) { const long long now_ = clock64(); t_rk[kind] += now_ - t_mark; }
+        C3D_PPROF(t_ready);
+        tc_fence_after();
+        if (kind <= 1) {
+          mbar_wait_cluster(&misc->kfull[s], kcnt[s] & 1u);
+          kcnt[s]++;
+          C3D_PPROF(t_full);
+          tc_fence_after();
+          umma_bf16_ss_pair(tacc, umma_desc_kmajor_k16(aux_addr[s]), umma_desc_kmajor_k16(k16_addr[s]), idesc_l, 0u);
+          umma_commit_pair(&misc->kempty[s], (uint16_t)0x3);
+#ifdef C3D_KERNEL_PROF
+          if (tl_on && acnt[0] == 48u) C3D_TL(1);
+#endif
+          if (kind == 1) {
+            const bool reuse = shared && s == 1;     // the stages slot 0 just used hold my weights too: no wait, I release them
+            if (s == 0) n_shared = n;
+            for (int kc = 0; kc < NCHUNK; ++kc) {
+              const uint32_t m = reuse ? n_shared + kc : n + kc;
+              const uint32_t st = m % NSTAGE, ph = (m / NSTAGE) & 1u;
+              if (!reuse) {
+                C3D_PPROF(t_issue);
+                mbar_wait_cluster(&misc->full[st], ph);
+                C3D_PPROF(t_full);
+                tc_fence_after();
+              }
+              const uint64_t ad = umma_desc_kmajor_sw128(act_addr[s] + kc * ACT_CHUNK);
+              const uint64_t bd = umma_desc_kmajor_sw128(stage_base + st * STAGE_BYTES);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) umma_bf16_ss_pair(tacc, ad + 2 * kk, bd + 2 * kk, idesc_l, 1u);
+              if (!(shared && s == 0)) umma_commit_pair(&misc->empty[st], (uint16_t)0x3);
+            }
+            if (!reuse) n += NCHUNK;
+          }
+          umma_commit_pair(&misc->acc_full[s], (uint16_t)0x3);
+#ifdef C3D_KERNEL_PROF
+          if (tl_on && acnt[0] == 48u) C3D_TL(2);
+#endif
+          if (kind == 0) C3D_PPROF(t_small);
+        } else {
+          // These narrow MMAs are latency-bound when chained on one accumulator, so consecutive K-steps go to different
+          // partial accumulators (summed by the epilogue): 2 per channel half for the compositing, 4 for the heads.
+          // (the issuing thread is the bottleneck of these jobs: descriptors are base + immediate, loops fully unrolled)
+          if (kind == 3) {                  // compositing: F^T[c][ray] = sum_p feat[p][c] * Wgt[ray][p], per channel half
+            const uint64_t fa = umma_desc_mnmajor_sw128(act_addr[s], ACT_CHUNK), wb = umma_desc_kmajor_sw128(aux_addr[s]);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+                umma_bf16_ss_pair(tacc + (uint32_t)(h * 2 + (ks & 1)) * 32u, desc_at(fa, 2 * h * ACT_CHUNK + ks * 2048),
+                                  desc_at(wb, (ks >> 2) * 2048 + (ks & 3) * 32), idesc_c, ks >= 2);
+          }
+          const uint32_t dcol = kind == 3 ? 128u : 0u;         // heads: sdf (job D) / rgb (job D+2)
+          const uint64_t ha = umma_desc_kmajor_sw128(act_addr[s]), hb = umma_desc_kmajor_sw128(heads_addr);
+#pragma unroll
+          for (int ks = 0; ks < 16; ++ks)
+            umma_bf16_ss_pair(tacc + dcol + (uint32_t)(ks & 3) * 16u, desc_at(ha, (ks >> 2) * ACT_CHUNK + (ks & 3) * 32),
+                              desc_at(hb, (ks >> 2) * 1024 + (ks & 3) * 32), idesc_h, ks >= 4);
+          umma_commit_pair(&misc->acc_full[s], (uint16_t)0x3);
+          C3D_PPROF(t_small);
+        }
+        if (++jb[s] == JOBS) { jb[s] = 0; c[s].next_tile(a); }
+      }
+    }
+    if (prof && (blockIdx.x % 42 == 0)) {
+      C3D_PPROF(t_issue);
+      printf("c3d prof pair mma[blk %d]: total %lld  wait_a_ready %lld (before L0 %lld, layers %lld, sdf %lld, post %lld)  wait_full %lld  issue %lld  issue_small_jobs %lld\n",
+             (int)blockIdx.x, clock64() - t_begin, t_ready, t_rk[0], t_rk[1], t_rk[2], t_rk[3], t_full, t_issue, t_small);
+    }
+   }
+  } else if (warp >= 4) {
+    // ============================================================ epilogue groups (both CTAs)
+    const int s = (warp - 4) >> 2;
+    const int t = (int)threadIdx.x - 128 - s * TILE;     // my point row of the tile = my TMEM lane
+    const int quad = warp & 3;
+    const uint32_t bar_id = 1u + (uint32_t)s;
+    uint8_t* aux = smem + SM_AUX + s * AUX_BYTES;
+    const uint32_t aux_u32 = smem_u32(aux);
+    float* omS = reinterpret_cast<float*>(smem + SM_OM) + s * TILE;
+    float* rayacc = reinterpret_cast<float*>(smem + SM_RAYACC) + s * RAYS * 2 * 8;
+    const uint32_t tacc = tmem_base + (uint32_t)s * 256u + ((uint32_t)(quad * 32) << 16);
+    const float* scal = reinterpret_cast<const float*>(a.blob + a.L.scal);
+    const float bsig = scal[0], brgb0 = scal[1], brgb1 = scal[2], brgb2 = scal[3];
+    const float inv_beta = 1.0f / scal[4];
+    const uint32_t act_u32 = smem_u32(smem + SM_ACT + s * ACT_BYTES);
+    const uint32_t row_u32 = act_u32 + (uint32_t)t * 128u;
+    const int r7 = t & 7;
+    const uint32_t ready_remote = mapa_u32(smem_u32(&misc->a_ready[s]), 0u);
+    // "my part of the tile is written": every thread fences its own stores, one arrival per warp on the leader's barrier
+    auto arrive_ready = [&]() {
+      fence_proxy_async_smem();          // my stores all went to my own CTA's shared memory
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { if (leader) mbar_arrive(&misc->a_ready[s]); else mbar_arrive_remote(ready_remote); }
+    };
+    float carry_f[2] = {0.f, 0.f};                       // partial feature sums of a ray continuing into the next tile
+    uint32_t jobcnt = 0;
+#ifdef C3D_KERNEL_PROF
+    const bool eprof = (a.debug & 2) != 0 && blockIdx.x < 2 && t == 0;
+#else
+    constexpr bool eprof = false;
+#endif
+    long long e_wait = 0, e_epi = 0, e_pt = 0, e_mark = clock64(), e_begin = e_mark;
+#define C3D_PEPROF(acc) do { if (eprof) { const long long now_ = clock64(); acc += now_ - e_mark; e_mark = now_; } } while (0)
+    Cursor cur;
+    cur.init(a, ps0 + s, n_pairslots);
+    if (s == 1 && a.stagger > 0) {                       // desynchronise the two slots (see profiles/r01_fused.md)
+      const long long t0 = clock64();
+      while (clock64() - t0 < a.stagger) { }
+    }
+
+    for (; cur.valid(); ) {
+      const int u = cur.pu;
+      const int img = u / a.units_per_img;
+      const int r0 = (u - img * a.units_per_img) * 2 * a.unit_rays + (int)rank * a.unit_rays;
+      const int nr = max(0, min(a.unit_rays, a.n_rays - r0));   // 0: this CTA idles through the pair-unit
+      const int npts = nr * N;
+      const int ntiles = cur.ntiles;
+      const float near = a.near[img], far = a.far[img];
+      const float nscale = 2.0f / (far - near);
+      carry_f[0] = carry_f[1] = 0.f;
+
+      for (int tile = 0; tile < ntiles; ++tile, cur.next_tile(a)) {
+        // ------------------------------------------------ geometry of my point (nerf_utils.py:17-170)
+        const int q = tile * TILE + t;
+        const bool valid = q < npts;
+        const int qc = valid ? q : max(npts - 1, 0);
+        const int rl = qc / N, k = qc - rl * N;
+        const int rl0 = (tile * TILE) / N;                // first ray touching this tile
+        const size_t gray = (size_t)img * a.n_rays + min(r0 + rl, a.n_rays - 1);
+        float px = 0.f, py = 0.f, pz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, dist = 0.f, zk = 0.f;
+        if (npts == 0) {
+        } else if (a.input_kind == C3D_INPUT_POSES) {
+          const RayGeom rg = make_ray(a.cam_poses + (size_t)img * 12, a.focal[img], a.img_size, r0 + rl, a.static_viewdirs != 0);
+          const float uo = a.ray_offset ? a.ray_offset[gray] : 0.f;
+          zk = sample_depth(near, far, k, N, uo);
+          const float z1 = (k + 1 < N) ? sample_depth(near, far, k + 1, N, uo) : 0.f;
+          px = fmaf(rg.dx, zk, rg.ox); py = fmaf(rg.dy, zk, rg.oy); pz = fmaf(rg.dz, zk, rg.oz);
+          vx = rg.vx; vy = rg.vy; vz = rg.vz;
+          dist = ((k + 1 < N) ? (z1 - zk) : 1e10f) * rg.dnorm;
+        } else {
+          const float* pp = a.pts + (gray * N + k) * 3;
+          px = pp[0]; py = pp[1]; pz = pp[2];
+          const float* vv = a.viewdirs + gray * 3;
+          vx = vv[0]; vy = vv[1]; vz = vv[2];
+          const float* rd = a.rays_d + gray * 3;
+          const float dn = sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]);
+          zk = a.z_vals[gray * N + k];
+          dist = ((k + 1 < N) ? (a.z_vals[gray * N + k + 1] - zk) : 1e10f) * dn;
+        }
+        if (a.z_vals_out && valid) a.z_vals_out[gray * N + k] = zk;
+        const uint32_t aux_row = aux_u32 + (uint32_t)((t >> 3) * 256 + (t & 7) * 16);
+        {
+          // point tile of the K16 products of layers 0..D-1: per coordinate (hi, mid, hi, lo); slots 12, 13 = 1 (shift)
+          const float pn[3] = {px * nscale, py * nscale, pz * nscale};
+          float e[12];
+#pragma unroll
+          for (int jx = 0; jx < 3; ++jx) {
+            const float hi = __bfloat162float(__float2bfloat16_rn(pn[jx]));
+            const float r1 = pn[jx] - hi;
+            const float mid = __bfloat162float(__float2bfloat16_rn(r1));
+            const float lo = __bfloat162float(__float2bfloat16_rn(r1 - mid));
+            e[4 * jx + 0] = hi; e[4 * jx + 1] = mid; e[4 * jx + 2] = hi; e[4 * jx + 3] = lo;
+          }
+          st_v4(aux_row, pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+          st_v4(aux_row + 128, pack_bf16x2(e[8], e[9]), pack_bf16x2(e[10], e[11]), pack_bf16x2(1.0f, 1.0f), 0u);
+        }
+        arrive_ready();
+
+        float sdf = 0.f, wgt = 0.f;
+        // ------------------------------------------------ layers 0..D (D = view layer)
+        for (int l = 0; l <= D; ++l) {
+          if (l == D) {
+            // ---------------------------------------------- sdf head -> alpha -> transmittance (thread = point)
+            mbar_wait(&misc->acc_full[s], jobcnt & 1u);
+            jobcnt++;
+            tc_fence_after();
+            {
+              uint32_t v4[4][4];                     // heads16 rows 4, 5 (hi / lo of sigma_linear.weight), 4 partial sums
+#pragma unroll
+              for (int pp = 0; pp < 4; ++pp) tmem_ld_32x4(tacc + pp * 16 + 4, v4[pp]);
+              tmem_ld_wait();
+              tc_fence_before();
+              sdf = bsig;
+#pragma unroll
+              for (int pp = 0; pp < 4; ++pp) sdf += __uint_as_float(v4[pp][0]) + __uint_as_float(v4[pp][1]);
+            }
+            if (valid) a.sdf[gray * N + k] = sdf;
+            const float sigma = sigmoid_precise(-sdf * inv_beta) * inv_beta;
+            const float alpha = 1.0f - expf(-sigma * dist);
+            const float om = 1.0f - alpha + 1e-10f;
+            omS[t] = valid ? om : 1.0f;
+            // view tile of the view layer's K16 product: slots 0..2 / 3..5 = hi / lo of the view direction, 12, 13 = 1
+            {
+              const float h0 = __bfloat162float(__float2bfloat16_rn(vx)), h1 = __bfloat162float(__float2bfloat16_rn(vy)),
+                          h2 = __bfloat162float(__float2bfloat16_rn(vz));
+              st_v4(aux_row, pack_bf16x2(h0, h1), pack_bf16x2(h2, vx - h0), pack_bf16x2(vy - h1, vz - h2), 0u);
+              st_v4(aux_row + 128, 0u, 0u, pack_bf16x2(1.0f, 1.0f), 0u);
+            }
+            named_bar_sync(bar_id, TILE);
+            const int first_row = t - k;
+            float T = first_row < 0 ? misc->carry[s] : 1.0f;
+            for (int m = max(first_row, 0); m < t; ++m) T *= omS[m];
+            wgt = valid ? alpha * T : 0.f;
+            named_bar_sync(bar_id, TILE);
+            if (t == TILE - 1) misc->carry[s] = (k == N - 1) ? 1.0f : T * om;
+            arrive_ready();
+          }
+          C3D_PEPROF(e_pt);
+          mbar_wait(&misc->acc_full[s], jobcnt & 1u);
+          C3D_PEPROF(e_wait);
+#ifdef C3D_KERNEL_PROF
+          const bool etl = (a.debug & 2) && blockIdx.x == 0 && s == 0 && t == 0 && jobcnt == 47u;
+          if (etl) C3D_TL(3);
+#endif
+          jobcnt++;
+          tc_fence_after();
+          if (l == D) {
+            // the view tile has been consumed: build Wgt[ray slot][point] (bf16, K-major SW128) in its place
+            const int myslot = rl - rl0;
+#pragma unroll
+            for (int jx = 0; jx < RAYS; ++jx)
+              st_bf16(aux_u32 + (uint32_t)((t >> 6) * 2048) + sw128_offset(jx, t & 63), jx == myslot ? wgt : 0.f);
+          }
+          {
+            // my point: 256 channels in 8 double chunks of 32, TMEM loads double-buffered
+            uint32_t v0[16], v1[16];
+            tmem_ld_32x16(tacc, v0);
+#pragma unroll 2
+            for (int cp = 0; cp < 8; ++cp) {               // channels 32 cp .. 32 cp + 31: chunk cp >> 1, units 4 (cp & 1) ..
+              const uint32_t row = row_u32 + (uint32_t)(cp >> 1) * ACT_CHUNK;
+              tmem_ld_wait();
+              tmem_ld_32x16(tacc + cp * 32 + 16, v1);
+              epilogue16(v0, row, (cp & 1) * 4, r7, a.debug);
+              tmem_ld_wait();
+              if (cp < 7) tmem_ld_32x16(tacc + (cp + 1) * 32, v0);
+              epilogue16(v1, row, (cp & 1) * 4 + 2, r7, a.debug);
+            }
+          }
+#ifdef C3D_KERNEL_PROF
+          if (etl) C3D_TL(4);
+#endif
+          arrive_ready();
+#ifdef C3D_KERNEL_PROF
+          if (etl) C3D_TL(5);
+#endif
+          C3D_PEPROF(e_epi);
+        }
+
+        // ------------------------------------------------ post job: composited features (thread = channel) + rgb (thread = point)
+        {
+          mbar_wait(&misc->acc_full[s], jobcnt & 1u);
+          jobcnt++;
+          tc_fence_after();
+          float rgbv[3] = {brgb0, brgb1, brgb2};         // raw rgb of my point: 4 partial sums
+          {
+            uint32_t v4[4][4];
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) tmem_ld_32x4(tacc + 128 + pp * 16, v4[pp]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) {
+              rgbv[0] += __uint_as_float(v4[pp][0]); rgbv[1] += __uint_as_float(v4[pp][1]); rgbv[2] += __uint_as_float(v4[pp][2]);
+            }
+          }
+          const int tile_end = min((tile + 1) * TILE, npts);      // first point index beyond this tile
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t fv[16], fw[16];                     // my CTA's 16 ray-slot columns of channel t + 128 hh, 2 partial sums
+            tmem_ld_32x16(tacc + (uint32_t)(hh * 2) * 32u + rank * 16u, fv);
+            tmem_ld_32x16(tacc + (uint32_t)(hh * 2 + 1) * 32u + rank * 16u, fw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int jx = 0; jx < 16; ++jx) fv[jx] = __float_as_uint(__uint_as_float(fv[jx]) + __uint_as_float(fw[jx]));
+            float* fbase = a.feature_map + ((size_t)img * a.n_rays + min(r0 + rl0, a.n_rays - 1)) * W + t + TILE * hh;
+#pragma unroll
+            for (int jx = 0; jx < RAYS; ++jx) {
+              const int rbeg = (rl0 + jx) * N, rend = rbeg + N;      // point range of ray slot jx inside the unit
+              if (rbeg < tile_end) {                                  // uniform: the slot is in use
+                float fvv = __uint_as_float(fv[jx]);
+                if (jx == 0) fvv += carry_f[hh];
+                if (rend <= tile_end) fbase[(size_t)jx * W] = fvv;    // ray complete
+                if (rend >= tile_end) carry_f[hh] = rend > tile_end ? fvv : 0.f;   // last slot of the tile
+              }
+            }
+          }
+          tmem_ld_wait();
+          tc_fence_before();
+          // rgb / xyz / mask sums of my ray (nerf_utils.py:315,329-336)
+          float vals[6];
+          vals[0] = wgt * sigmoid_precise(rgbv[0]);
+          vals[1] = wgt * sigmoid_precise(rgbv[1]);
+          vals[2] = wgt * sigmoid_precise(rgbv[2]);
+          vals[3] = wgt * px; vals[4] = wgt * py; vals[5] = wgt * pz;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int rid = __shfl_down_sync(0xffffffffu, rl, o);
+            const bool same = (lane + o < 32) && (rid == rl);
+#pragma unroll
+            for (int jx = 0; jx < 6; ++jx) {
+              const float y = __shfl_down_sync(0xffffffffu, vals[jx], o);
+              if (same) vals[jx] += y;
+            }
+          }
+          const int rprev = __shfl_up_sync(0xffffffffu, rl, 1);
+          float* racc = rayacc + (rl & (2 * RAYS - 1)) * 8;
+          if (valid && (lane == 0 || rprev != rl)) {
+#pragma unroll
+            for (int jx = 0; jx < 6; ++jx) atomicAdd(racc + jx, vals[jx]);
+          }
+          named_bar_sync(bar_id, TILE);
+          if (valid && k == N - 1) {
+            const float x = racc[3], y = racc[4], z = racc[5];
+            float* o3 = a.rgb_map + gray * 3;
+            o3[0] = -1.0f + 2.0f * racc[0]; o3[1] = -1.0f + 2.0f * racc[1]; o3[2] = -1.0f + 2.0f * racc[2];
+            float* x3 = a.xyz + gray * 3;
+            x3[0] = x; x3[1] = y; x3[2] = z;
+            a.mask[gray * 2 + 0] = wgt;
+            a.mask[gray * 2 + 1] = -sqrtf(x * x + y * y + z * z);
+#pragma unroll
+            for (int jx = 0; jx < 6; ++jx) racc[jx] = 0.f;
+          }
+        }
+      }  // tiles
+    }    // pair-units
+    if (eprof) {
+      C3D_PEPROF(e_pt);
+      printf("c3d prof pair eg(blk %d slot %d): total %lld  wait_acc_full(layers) %lld  epilogue %lld  other(point stages, sdf/post waits) %lld\n",
+             (int)blockIdx.x, s, clock64() - e_begin, e_wait, e_epi, e_pt);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
+}
+
+}}  // namespace c3d::pairk

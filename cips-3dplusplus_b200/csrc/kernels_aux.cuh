@@ -1,6 +1,7 @@
 // Auxiliary kernels: weight packing, FiLM style preparation, ray generation, standalone compositing.
 #pragma once
 #include "c3d_common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace c3d {
 
@@ -171,6 +172,65 @@ __global__ void __launch_bounds__(256) style_prep_kernel(const uint8_t* __restri
     if (l == 0) first[(size_t)b * W + c] = make_float4(gamma * w0.x, gamma * w0.y, gamma * w0.z, shift);
     if (l == D) view[(size_t)b * W + c] = make_float4(gamma * wv.x, gamma * wv.y, gamma * wv.z, 0.f);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-image weight images of the CTA-pair forward kernel (fused_pair_sm100.cuh): FiLM folded into the GEMM operands.
+//   wimg[b][idx 0..D-1][kc 0..3][half 0..1] : 16 KB stage images [128 rows n][64 k] bf16, K-major SWIZZLE_128B,
+//                                             value bf16(gamma_{b,idx+1}[n] * W_{idx+1}[n][k]),  n = 128 half + row
+//   kimg[b][L 0..D][half 0..1]              : 4 KB K16 images [128 rows n][16 slots], UMMA K-major no-swizzle:
+//        L = 0     slots 4j..4j+3 = (hi, hi, lo, hi) of gamma W0[n][j]   (x point tile (hi, mid, hi, lo))
+//        L = D     slots j and 3+j = bf16(gamma Wview[n][256+j])         (x view tile (hi x3, lo x3))
+//        all L     slots 12, 13 = hi / lo of the shift gamma b + beta    (x the two "ones" slots of either tile)
+// ------------------------------------------------------------------------------------------
+// grid (8 = kc*2 + half, D, batch), block 256: thread = (row, 32-element half of the 64-wide K-chunk)
+__global__ void __launch_bounds__(256) film_weights_kernel(const uint8_t* __restrict__ blob, PackedLayout L,
+                                                            const float2* __restrict__ film, uint8_t* __restrict__ wimg) {
+  const int D = L.D, idx = blockIdx.y, b = blockIdx.z, kc = blockIdx.x >> 1, half = blockIdx.x & 1;
+  const int i = threadIdx.x >> 1, q = threadIdx.x & 1, n = half * 128 + i;
+  const float gamma = film[((size_t)b * (D + 1) + idx + 1) * W + n].x;
+  const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(blob + L.w32) + (size_t)idx * W * W +
+                                                      (size_t)n * W + kc * 64 + q * 32);
+  uint8_t* dst = wimg + (((size_t)b * D + idx) * 8 + blockIdx.x) * 16384 + (size_t)i * 128;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float4 x = src[2 * u], y = src[2 * u + 1];
+    uint4 o;
+    o.x = ptx::pack_bf16x2(gamma * x.x, gamma * x.y); o.y = ptx::pack_bf16x2(gamma * x.z, gamma * x.w);
+    o.z = ptx::pack_bf16x2(gamma * y.x, gamma * y.y); o.w = ptx::pack_bf16x2(gamma * y.z, gamma * y.w);
+    *reinterpret_cast<uint4*>(dst + (((q * 4 + u) ^ (i & 7)) << 4)) = o;
+  }
+}
+
+// grid (D+1, batch), block 256 (thread = output channel n)
+__global__ void __launch_bounds__(256) film_k16_kernel(const uint8_t* __restrict__ blob, PackedLayout L,
+                                                        const float2* __restrict__ film, uint8_t* __restrict__ kimg) {
+  const int D = L.D, l = blockIdx.x, b = blockIdx.y, n = threadIdx.x, half = n >> 7, i = n & 127;
+  const float2 f = film[((size_t)b * (D + 1) + l) * W + n];
+  float s[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s[k] = 0.f;
+  auto bf = [](float x) { return __bfloat162float(__float2bfloat16_rn(x)); };
+  if (l == 0) {
+    const float4 w0 = reinterpret_cast<const float4*>(blob + L.w0)[n];
+    const float w[3] = {f.x * w0.x, f.x * w0.y, f.x * w0.z};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float hi = bf(w[j]), lo = bf(w[j] - hi);
+      s[4 * j + 0] = hi; s[4 * j + 1] = hi; s[4 * j + 2] = lo; s[4 * j + 3] = hi;
+    }
+  }
+  if (l == D) {
+    const float4 wv = reinterpret_cast<const float4*>(blob + L.wvdir)[n];
+    s[0] = s[3] = f.x * wv.x; s[1] = s[4] = f.x * wv.y; s[2] = s[5] = f.x * wv.z;
+  }
+  const float sh = bf(f.y);
+  s[12] = sh; s[13] = f.y - sh;
+  uint8_t* dst = kimg + (((size_t)b * (D + 1) + l) * 2 + half) * 4096 + k16_offset(i, 0);
+  *reinterpret_cast<uint4*>(dst) = make_uint4(ptx::pack_bf16x2(s[0], s[1]), ptx::pack_bf16x2(s[2], s[3]),
+                                              ptx::pack_bf16x2(s[4], s[5]), ptx::pack_bf16x2(s[6], s[7]));
+  *reinterpret_cast<uint4*>(dst + 128) = make_uint4(ptx::pack_bf16x2(s[8], s[9]), ptx::pack_bf16x2(s[10], s[11]),
+                                                    ptx::pack_bf16x2(s[12], s[13]), ptx::pack_bf16x2(s[14], s[15]));
 }
 
 // ------------------------------------------------------------------------------------------

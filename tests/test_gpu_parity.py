@@ -200,11 +200,16 @@ def test_forward_fp32_matches_reference_golden(case):
     assert m.last_launch_count >= 3
 
 
-@pytest.mark.parametrize("cluster", ["1", "2"])
+@pytest.mark.parametrize("cluster", ["pair", "1", "2"])
 @pytest.mark.parametrize("case", CASES)
 def test_forward_bf16_matches_reference_golden(case, cluster, monkeypatch):
-    monkeypatch.setenv("C3D_CLUSTER", cluster)
-    monkeypatch.delenv("C3D_FUSED", raising=False)
+    """bf16 tensor-core forward: the CTA-pair kernel (default) and the single-CTA kernel (C3D_FWD=v3, with and
+    without the cluster weight multicast) against the reference's outputs."""
+    if cluster == "pair":
+        monkeypatch.setenv("C3D_FWD", "pair")
+    else:
+        monkeypatch.setenv("C3D_FWD", "v3")
+        monkeypatch.setenv("C3D_CLUSTER", cluster)
     c, (rgb_map, feat, sdf, mask, xyz), m = _run_points(case, "bf16")
     errs = dict(feat=rel_l2(feat, c["feature_map"]), rgb=rel_l2(rgb_map, c["rgb_map"]), sdf=rel_l2(sdf, c["sdf"]),
                 xyz=rel_l2(xyz, c["xyz"]), depth=float(np.abs(mask[..., 1] - c["mask"][..., 1]).max()))
@@ -212,7 +217,7 @@ def test_forward_bf16_matches_reference_golden(case, cluster, monkeypatch):
     assert errs["feat"] < BF16_REL and errs["rgb"] < BF16_REL, errs
     assert errs["xyz"] < BF16_REL and errs["sdf"] < 5e-2, errs
     assert errs["depth"] < 2e-3, errs
-    assert m.last_launch_count == 2          # style_prep + the fused kernel
+    assert m.last_launch_count == (4 if cluster == "pair" else 2)   # style_prep (+ 2 weight-image kernels) + fused kernel
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
