@@ -234,13 +234,16 @@ static int forward_pair(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
   if (genv && atoi(genv) > 0) grid = (atoi(genv) + 1) & ~1;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(pairk::NTHREADS); cfg.dynamicSmemBytes = pairk::SMEM_BYTES; cfg.stream = st;
+  const char* eenv = getenv("C3D_EGW");
+  const int egw = (eenv && atoi(eenv) == 4) ? 4 : 8;            // epilogue warps per slot
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(pairk::nthreads(egw)); cfg.dynamicSmemBytes = pairk::SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  C3D_CUDA(cudaFuncSetAttribute(pairk::fused_forward_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pairk::SMEM_BYTES));
-  C3D_CUDA(cudaLaunchKernelEx(&cfg, pairk::fused_forward_pair_kernel, a));
+  void (*kern)(const fused::Args) = egw == 8 ? pairk::fused_forward_pair_kernel<8> : pairk::fused_forward_pair_kernel<4>;
+  C3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pairk::SMEM_BYTES));
+  C3D_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   C3D_LAUNCH_CHECK();
   return C3D_OK;
 }

@@ -40,7 +40,10 @@ using fused::TILE;
 using fused::ACT_BYTES;
 using fused::ACT_CHUNK;
 
-constexpr int NTHREADS = 384;
+// epilogue warps per slot (template parameter kEgw): 4 -> a thread owns all 256 channels of its point; 8 -> warps 0-3 of the
+// slot own channels 0..127 and run the per-point stages, warps 4-7 own channels 128..255 (a warp pays 8 issue cycles per
+// MUFU.SIN, so one warp per sub-partition and slot cannot saturate the SFU while it also packs and stores)
+__host__ __device__ constexpr int nthreads(int egw) { return 128 + 2 * egw * 32; }
 constexpr int STAGE_BYTES = 128 * 128;         // [128 weight rows][64 k] bf16, K-major SWIZZLE_128B
 constexpr int NSTAGE = 4;
 constexpr int RAYS = 16;                       // rays touching one tile (n_samples >= 8)
@@ -124,6 +127,28 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
 // descriptor of the same layout `bytes` further (start-address field, 16-byte units; no carry out of the field here)
 __device__ __forceinline__ uint64_t desc_at(uint64_t base, uint32_t bytes) { return base + (uint64_t)(bytes >> 4); }
 
+// Tuning knob, off by default: bit i of C3D_POLY_MASK moves element i of every group of 8 from the SFU (MUFU.SIN) to the
+// FMA pipe (Cody-Waite reduction to [-pi, pi], odd degree-7 minimax polynomial, max abs error 2.5e-4).  Measured on
+// B200 (profiles/r01_fused.md): every non-zero mask is slower (0x88 +1.7 %, 0x92 +3.5 %, 0xAA +8 %), with 4 or 8
+// epilogue warps per slot -- the epilogue is not SFU-throughput bound.
+#ifndef C3D_POLY_MASK
+#define C3D_POLY_MASK 0x00
+#endif
+__device__ __forceinline__ float sin_fma_pipe(float x) {
+  const float t = fmaf(x, 0.15915494309189535f, 12582912.0f);      // round(x / 2pi) in the low mantissa bits
+  const float k = t - 12582912.0f;
+  const float r = fmaf(k, -6.283185307179586f, x);
+  const float r2 = r * r;
+  float p = fmaf(-0.00014507691616902975f, r2, 0.007958060561828354f);
+  p = fmaf(p, r2, -0.16566697968747116f);
+  p = fmaf(p, r2, 0.9992758634237795f);
+  return r * p;
+}
+template <int i>
+__device__ __forceinline__ float siren_sin(float x) {
+  return ((C3D_POLY_MASK >> (i & 7)) & 1) ? sin_fma_pipe(x) : __sinf(x);
+}
+
 // sin of 16 consecutive channels of one point -> bf16 -> two 16-byte stores into the point's row (units u0, u0 + 1)
 __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], uint32_t row_addr, int u0, int r7, int dbg = 0) {
 #pragma unroll
@@ -135,8 +160,11 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], uint32_t row
       for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[g * 8 + i]) * 0.5f;
     } else
 #endif
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = __sinf(__uint_as_float(v[g * 8 + i]));
+    {
+#define C3D_SIN_AT(i) o[i] = siren_sin<i>(__uint_as_float(v[g * 8 + i]))
+      C3D_SIN_AT(0); C3D_SIN_AT(1); C3D_SIN_AT(2); C3D_SIN_AT(3); C3D_SIN_AT(4); C3D_SIN_AT(5); C3D_SIN_AT(6); C3D_SIN_AT(7);
+#undef C3D_SIN_AT
+    }
 #ifdef C3D_KERNEL_PROF
     if (dbg & 8) continue;
 #endif
@@ -145,7 +173,10 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], uint32_t row
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const Args a) {
+template <int kEgw>
+__global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_pair_kernel(const Args a) {
+  constexpr int NTHREADS = nthreads(kEgw);
+  constexpr int CPT = 32 / kEgw;                   // 32-channel groups per epilogue thread: 8 or 4
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   Misc* misc = reinterpret_cast<Misc*>(smem + SM_MISC);
@@ -163,7 +194,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
     for (int i = 0; i < 2; ++i) {
       mbar_init(&misc->kfull[i], leader ? 2 : 1);
       mbar_init(&misc->kempty[i], 1);
-      mbar_init(&misc->a_ready[i], 8);             // one arrival per epilogue warp of both CTAs (leader's copy is used)
+      mbar_init(&misc->a_ready[i], 2 * kEgw);      // one arrival per epilogue warp of both CTAs (leader's copy is used)
       mbar_init(&misc->acc_full[i], 1);
     }
     misc->carry[0] = misc->carry[1] = 1.0f;
@@ -367,8 +398,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
    }
   } else if (warp >= 4) {
     // ============================================================ epilogue groups (both CTAs)
-    const int s = (warp - 4) >> 2;
-    const int t = (int)threadIdx.x - 128 - s * TILE;     // my point row of the tile = my TMEM lane
+    const int s = (warp - 4) / kEgw;
+    const int te = (int)threadIdx.x - 128 - s * kEgw * 32;
+    const int t = te & 127;                              // my point row of the tile = my TMEM lane
+    const int grp = te >> 7;                             // kEgw == 8: channel half of the layer stages
+    const bool ptg = grp == 0;                           // this thread also runs the per-point stages
     const int quad = warp & 3;
     const uint32_t bar_id = 1u + (uint32_t)s;
     uint8_t* aux = smem + SM_AUX + s * AUX_BYTES;
@@ -391,6 +425,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
       if (lane == 0) { if (leader) mbar_arrive(&misc->a_ready[s]); else mbar_arrive_remote(ready_remote); }
     };
     float carry_f[2] = {0.f, 0.f};                       // partial feature sums of a ray continuing into the next tile
+    (void)ptg;
     uint32_t jobcnt = 0;
 #ifdef C3D_KERNEL_PROF
     const bool eprof = (a.debug & 2) != 0 && blockIdx.x < 2 && t == 0;
@@ -426,7 +461,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
         const int rl0 = (tile * TILE) / N;                // first ray touching this tile
         const size_t gray = (size_t)img * a.n_rays + min(r0 + rl, a.n_rays - 1);
         float px = 0.f, py = 0.f, pz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, dist = 0.f, zk = 0.f;
-        if (npts == 0) {
+        if (npts == 0 || !ptg) {
         } else if (a.input_kind == C3D_INPUT_POSES) {
           const RayGeom rg = make_ray(a.cam_poses + (size_t)img * 12, a.focal[img], a.img_size, r0 + rl, a.static_viewdirs != 0);
           const float uo = a.ray_offset ? a.ray_offset[gray] : 0.f;
@@ -445,9 +480,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
           zk = a.z_vals[gray * N + k];
           dist = ((k + 1 < N) ? (a.z_vals[gray * N + k + 1] - zk) : 1e10f) * dn;
         }
-        if (a.z_vals_out && valid) a.z_vals_out[gray * N + k] = zk;
+        if (a.z_vals_out && valid && ptg) a.z_vals_out[gray * N + k] = zk;
         const uint32_t aux_row = aux_u32 + (uint32_t)((t >> 3) * 256 + (t & 7) * 16);
-        {
+        if (ptg) {
           // point tile of the K16 products of layers 0..D-1: per coordinate (hi, mid, hi, lo); slots 12, 13 = 1 (shift)
           const float pn[3] = {px * nscale, py * nscale, pz * nscale};
           float e[12];
@@ -472,6 +507,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
             mbar_wait(&misc->acc_full[s], jobcnt & 1u);
             jobcnt++;
             tc_fence_after();
+            if (ptg) {
             {
               uint32_t v4[4][4];                     // heads16 rows 4, 5 (hi / lo of sigma_linear.weight), 4 partial sums
 #pragma unroll
@@ -501,6 +537,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
             wgt = valid ? alpha * T : 0.f;
             named_bar_sync(bar_id, TILE);
             if (t == TILE - 1) misc->carry[s] = (k == N - 1) ? 1.0f : T * om;
+            }
             arrive_ready();
           }
           C3D_PEPROF(e_pt);
@@ -512,7 +549,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
 #endif
           jobcnt++;
           tc_fence_after();
-          if (l == D) {
+          if (l == D && ptg) {
             // the view tile has been consumed: build Wgt[ray slot][point] (bf16, K-major SW128) in its place
             const int myslot = rl - rl0;
 #pragma unroll
@@ -522,15 +559,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
           {
             // my point: 256 channels in 8 double chunks of 32, TMEM loads double-buffered
             uint32_t v0[16], v1[16];
-            tmem_ld_32x16(tacc, v0);
+            const int cp0 = kEgw == 8 ? grp * CPT : 0;
+            tmem_ld_32x16(tacc + cp0 * 32, v0);
 #pragma unroll 2
-            for (int cp = 0; cp < 8; ++cp) {               // channels 32 cp .. 32 cp + 31: chunk cp >> 1, units 4 (cp & 1) ..
+            for (int cq = 0; cq < CPT; ++cq) {             // channels 32 cp .. 32 cp + 31: chunk cp >> 1, units 4 (cp & 1) ..
+              const int cp = cp0 + cq;
               const uint32_t row = row_u32 + (uint32_t)(cp >> 1) * ACT_CHUNK;
               tmem_ld_wait();
               tmem_ld_32x16(tacc + cp * 32 + 16, v1);
               epilogue16(v0, row, (cp & 1) * 4, r7, a.debug);
               tmem_ld_wait();
-              if (cp < 7) tmem_ld_32x16(tacc + (cp + 1) * 32, v0);
+              if (cq < CPT - 1) tmem_ld_32x16(tacc + (cp + 1) * 32, v0);
               epilogue16(v1, row, (cp & 1) * 4 + 2, r7, a.debug);
             }
           }
@@ -550,7 +589,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
           jobcnt++;
           tc_fence_after();
           float rgbv[3] = {brgb0, brgb1, brgb2};         // raw rgb of my point: 4 partial sums
-          {
+          if (ptg) {
             uint32_t v4[4][4];
 #pragma unroll
             for (int pp = 0; pp < 4; ++pp) tmem_ld_32x4(tacc + 128 + pp * 16, v4[pp]);
@@ -563,6 +602,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
           const int tile_end = min((tile + 1) * TILE, npts);      // first point index beyond this tile
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
+            if (kEgw == 8 && hh != grp) continue;        // 8 warps per slot: one channel half per thread
             uint32_t fv[16], fw[16];                     // my CTA's 16 ray-slot columns of channel t + 128 hh, 2 partial sums
             tmem_ld_32x16(tacc + (uint32_t)(hh * 2) * 32u + rank * 16u, fv);
             tmem_ld_32x16(tacc + (uint32_t)(hh * 2 + 1) * 32u + rank * 16u, fw);
@@ -583,6 +623,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
           }
           tmem_ld_wait();
           tc_fence_before();
+          if (ptg) {
           // rgb / xyz / mask sums of my ray (nerf_utils.py:315,329-336)
           float vals[6];
           vals[0] = wgt * sigmoid_precise(rgbv[0]);
@@ -616,6 +657,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
             a.mask[gray * 2 + 1] = -sqrtf(x * x + y * y + z * z);
 #pragma unroll
             for (int jx = 0; jx < 6; ++jx) racc[jx] = 0.f;
+          }
           }
         }
       }  // tiles
