@@ -259,20 +259,26 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
             for (int h = 0; h < 2; ++h)
               umma_bf16_ss(tacc + (uint32_t)h * 128u, umma_desc_kmajor_k16(wk_addr + h * 4096), bd, idesc_kk, 0u);
           } else {
+            // These narrow MMAs are paced by the issuing thread and by the accumulate dependency, not by the tensor
+            // pipe: descriptors are base + immediate, the loops are fully unrolled, and consecutive K-steps go to
+            // different partial accumulators (2 per channel half for the compositing, 4 for the heads) that the
+            // epilogue sums.
             if (j == D + 2) {               // compositing: F^T[c][ray] = sum_p feat^T[c][p] * Wgt[ray][p]
-#pragma unroll 1
-              for (int h = 0; h < 2; ++h)
-#pragma unroll 2
-                for (int ks = 0; ks < 8; ++ks)
-                  umma_bf16_ss(tacc + (uint32_t)h * 16u,
-                               umma_desc_kmajor_sw128(act_addr[s] + (ks >> 2) * ACT_PBLOCK + h * 16384) + 2 * (ks & 3),
-                               umma_desc_kmajor_sw128(aux_addr[s] + (ks >> 2) * 2048) + 2 * (ks & 3), idesc_c, ks != 0);
+              const uint64_t fa = umma_desc_kmajor_sw128(act_addr[s]), wb = umma_desc_kmajor_sw128(aux_addr[s]);
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                  umma_bf16_ss(tacc + (uint32_t)(h * 2 + (ks & 1)) * 16u,
+                               fa + (uint64_t)(((ks >> 2) * ACT_PBLOCK + h * 16384 + (ks & 3) * 32) >> 4),
+                               wb + (uint64_t)(((ks >> 2) * 2048 + (ks & 3) * 32) >> 4), idesc_c, ks >= 2);
             }
-            const uint32_t dcol = (j == D + 2) ? 32u : 0u;    // heads: sdf (job D) / rgb (job D+2)
-#pragma unroll 2
+            const uint32_t dcol = (j == D + 2) ? 64u : 0u;    // heads: sdf (job D) / rgb (job D+2)
+            const uint64_t ha = umma_desc_mnmajor_sw128(act_addr[s], ACT_PBLOCK), hb = umma_desc_kmajor_sw128(heads_addr);
+#pragma unroll
             for (int ks = 0; ks < 16; ++ks)
-              umma_bf16_ss(tacc + dcol, umma_desc_mnmajor_sw128(act_addr[s] + ks * 2048, ACT_PBLOCK),
-                           umma_desc_kmajor_sw128(heads_addr + (ks >> 2) * 2048) + 2 * (ks & 3), idesc_h, ks != 0);
+              umma_bf16_ss(tacc + dcol + (uint32_t)(ks & 3) * 16u, ha + (uint64_t)((ks * 2048) >> 4),
+                           hb + (uint64_t)(((ks >> 2) * 2048 + (ks & 3) * 32) >> 4), idesc_h, ks >= 4);
           }
           umma_commit(&misc->acc_full[s]);
           jobcnt[s]++;
@@ -391,11 +397,14 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
             tc_fence_after();
             if (pt_role) {
               {
-                uint32_t v4[4];
-                tmem_ld_32x4(tacc + 4, v4);          // heads16 rows 4, 5: hi / lo part of sigma_linear.weight
+                uint32_t v4[4][4];                   // heads16 rows 4, 5 (hi / lo of sigma_linear.weight), 4 partial sums
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) tmem_ld_32x4(tacc + pp * 16 + 4, v4[pp]);
                 tmem_ld_wait();
                 tc_fence_before();
-                sdf = __uint_as_float(v4[0]) + __uint_as_float(v4[1]) + bsig;
+                sdf = bsig;
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) sdf += __uint_as_float(v4[pp][0]) + __uint_as_float(v4[pp][1]);
               }
               if (valid) a.sdf[gray * N + k] = sdf;
               const float sigma = sigmoid_precise(-sdf * inv_beta) * inv_beta;
@@ -471,15 +480,27 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
           mbar_wait(&misc->acc_full[s], jobcnt & 1u);
           jobcnt++;
           tc_fence_after();
-          uint32_t v4[4];
-          tmem_ld_32x4(tacc + 32, v4);                   // raw rgb of my point (point-role threads)
+          float rgbv[3] = {brgb0, brgb1, brgb2};         // raw rgb of my point (point-role threads): 4 partial sums
+          {
+            uint32_t v4[4][4];
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) tmem_ld_32x4(tacc + 64 + pp * 16, v4[pp]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) {
+              rgbv[0] += __uint_as_float(v4[pp][0]); rgbv[1] += __uint_as_float(v4[pp][1]); rgbv[2] += __uint_as_float(v4[pp][2]);
+            }
+          }
           const int tile_end = min((tile + 1) * TILE, npts);      // first point index beyond this tile
 #pragma unroll
           for (int hh = 0; hh < HPT; ++hh) {
             const int h = kEgw == 8 ? (te >> 7) : hh;
-            uint32_t fv[16];
-            tmem_ld_32x16(tacc + (uint32_t)h * 16u, fv);   // composited features of my channel; column = ray slot
+            uint32_t fv[16], fw[16];                     // composited features of my channel; column = ray slot; 2 partial sums
+            tmem_ld_32x16(tacc + (uint32_t)(h * 2) * 16u, fv);
+            tmem_ld_32x16(tacc + (uint32_t)(h * 2 + 1) * 16u, fw);
             tmem_ld_wait();
+#pragma unroll
+            for (int jx = 0; jx < 16; ++jx) fv[jx] = __float_as_uint(__uint_as_float(fv[jx]) + __uint_as_float(fw[jx]));
             float* fbase = a.feature_map + ((size_t)img * a.n_rays + r0 + rl0) * W + t + TILE * h;
 #pragma unroll
             for (int jx = 0; jx < RAYS; ++jx) {
@@ -498,13 +519,13 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
           // rgb / xyz / mask sums of my ray (nerf_utils.py:315,329-336)
           if (kSave && valid) {
             float* ro = a.rgb_pt + (gray * N + k) * 3;
-            ro[0] = __uint_as_float(v4[0]) + brgb0; ro[1] = __uint_as_float(v4[1]) + brgb1; ro[2] = __uint_as_float(v4[2]) + brgb2;
+            ro[0] = rgbv[0]; ro[1] = rgbv[1]; ro[2] = rgbv[2];
             a.w_pt[gray * N + k] = wgt;
           }
           float vals[6];
-          vals[0] = wgt * sigmoid_precise(__uint_as_float(v4[0]) + brgb0);
-          vals[1] = wgt * sigmoid_precise(__uint_as_float(v4[1]) + brgb1);
-          vals[2] = wgt * sigmoid_precise(__uint_as_float(v4[2]) + brgb2);
+          vals[0] = wgt * sigmoid_precise(rgbv[0]);
+          vals[1] = wgt * sigmoid_precise(rgbv[1]);
+          vals[2] = wgt * sigmoid_precise(rgbv[2]);
           vals[3] = wgt * px; vals[4] = wgt * py; vals[5] = wgt * pz;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
