@@ -8,5 +8,6 @@ from .nerf_utils import Render, Camera
 from .patch import use_b200_nerf_branch
 from . import dist
 from .inversion import FlipInversion
+from .gen_maps import gen_maps
 
-__all__ = ["NerfBranch", "Render", "Camera", "use_b200_nerf_branch", "dist", "FlipInversion", "_abi"]
+__all__ = ["NerfBranch", "Render", "Camera", "use_b200_nerf_branch", "dist", "FlipInversion", "gen_maps", "_abi"]

@@ -68,3 +68,50 @@ def test_reference_arm_under_torchrun_env():
     assert line["impl"] == "reference" and line["metric"] == "nerf_branch_rays_per_s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["n_gpus"] == 2
+
+
+class _FakeRenderer:
+    """Stands in for NerfBranch.render on CPU: the host logic of gen_maps (numbering, seeding, file output) is under test."""
+    def __init__(self):
+        self.calls = 0
+
+    def render(self, pose, focal, near, far, styles, img_size, N_samples, static_viewdirs=False, features_nchw=False):
+        self.calls += 1
+        b = pose.shape[0]
+        hw = img_size * img_size
+        assert styles.shape == (b, 3, 256) and focal.shape[0] == b
+        rgb = pose[:, :, 3].reshape(b, 1, 3).expand(b, hw, 3).clone()          # camera origin as a recognisable colour
+        return dict(rgb_map=rgb, mask=torch.zeros(b, hw, 2), feature_map=torch.zeros(b, 256, hw))
+
+
+def _gen_worker(rank, world, port, out_dir, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cips3dpp_b200.gen_maps import gaussian_styles, gen_maps
+    r = _FakeRenderer()
+    got = gen_maps(r, gaussian_styles(2), dict(fov_ang=6, dist_radius=0.12), num_imgs=11, batch_gpu=3, out_dir=out_dir,
+                   rank=rank, world_size=world, img_size=4, N_samples=8, device="cpu")
+    q.put((rank, [i for i, _ in got], r.calls))
+    dist.destroy_process_group()
+
+
+def test_gen_maps_numbering_covers_all_images_gloo_world2(tmp_path):
+    """gen_images.py:57-91 semantics: interleaved numbering, ceil(num/batch) steps on every rank, extras dropped."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gen_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    idx = sorted(i for _, ids, _ in res for i in ids)
+    assert idx == list(range(11))
+    assert all(calls == 2 for _, _, calls in res)                  # ceil(11 / (3 * 2)) steps on both ranks
+    files = sorted(os.listdir(tmp_path))
+    assert files == [f"{i:0>5}.npz" for i in range(11)]
+    import numpy as np
+    z = np.load(os.path.join(tmp_path, files[0]))
+    assert z["thumb"].shape == (4, 4, 3) and z["thumb"].dtype == np.uint8
