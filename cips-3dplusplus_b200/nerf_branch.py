@@ -97,6 +97,20 @@ class _NerfFn(torch.autograd.Function):
         return (None, None, None) + grads
 
 
+class _EikonalGuard(torch.autograd.Function):
+    """Carries the eikonal term in the graph so that differentiating THROUGH it (the training-time double backward of
+    volume_renderer.py:223-224 / nerf_utils.py:220-228) fails loudly instead of silently dropping the term."""
+
+    @staticmethod
+    def forward(ctx, value, *deps):
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        raise NotImplementedError("second-order gradients through the eikonal term are not provided by libc3dpp: "
+                                  "the term can be evaluated and logged, not trained on")
+
+
 class NerfBranch(nn.Module):
     def __init__(self, N_layers_renderer, input_dim=3, hidden_dim=256, style_dim=256, view_dim=3, with_sdf=True,
                  output_features=True, precision="bf16", **kwargs):
@@ -297,9 +311,6 @@ class NerfBranch(nn.Module):
         `N_samples_forward` (ray chunking to bound the unfused path's memory) is accepted and ignored:
         the fused kernel keeps per-point activations on chip.
         """
-        if return_eikonal:
-            raise NotImplementedError("return_eikonal=True (training-time double backward) is outside the "
-                                      "inference/inversion hot path this library covers")
         if styles is None:
             raise ValueError("styles is required")
         lead = pts.shape[:-2]
@@ -310,10 +321,25 @@ class NerfBranch(nn.Module):
         rgb_map, feat, sdf, mask, xyz, _ = self._run(
             _abi.INPUT_POINTS, meta, c(styles, b, self.N_layers_renderer + 1, W), c(pts, b, n_rays, N, 3),
             c(rays_d, b, n_rays, 3), c(viewdirs, b, n_rays, 3), c(z_vals, b, n_rays, N), c(near, b), c(far, b))
+        eik = None
+        if return_eikonal:
+            # d sdf / d pts (nerf_utils.py:220-228): points are independent, so one backward launch with a cotangent of
+            # ones on sdf returns every point's own gradient.  First order only (see _EikonalGuard).
+            args = (c(styles, b, self.N_layers_renderer + 1, W), c(pts, b, n_rays, N, 3), c(rays_d, b, n_rays, 3),
+                    c(viewdirs, b, n_rays, 3), c(z_vals, b, n_rays, N), c(near, b), c(far, b))
+            ones = torch.ones(b, n_rays, N, dtype=torch.float32, device=pts.device)
+            needs = (False, False, False, False, True) + (False,) * 5 + (False,) * len(self._ordered_params())
+            with torch.no_grad():
+                grads = self._launch_backward(_abi.INPUT_POINTS, meta, *args, None, None, ones, None, None, needs)
+            eik = grads[1].reshape(*lead, N, 3)
+            deps = [t for t in (styles, pts) if torch.is_tensor(t) and t.requires_grad] + \
+                [p for p in self.parameters() if p.requires_grad]
+            if torch.is_grad_enabled() and deps:
+                eik = _EikonalGuard.apply(eik, *deps)
         if len(lead) > 2:
             rgb_map, feat, mask, xyz = (t.reshape(*lead, t.shape[-1]) for t in (rgb_map, feat, mask, xyz))
             sdf = sdf.reshape(*lead, N, 1)
-        return rgb_map, feat, sdf, mask, xyz, None
+        return rgb_map, feat, sdf, mask, xyz, eik
 
     def render(self, cam_poses, focal, near, far, styles, img_size=64, N_samples=24, static_viewdirs=False,
                perturb=False, ray_offset=None, features_nchw=False):
@@ -332,6 +358,17 @@ class NerfBranch(nn.Module):
             ro, None, c(near, b), c(far, b))
         return dict(rgb_map=rgb_map, feature_map=feat, sdf=sdf, mask=mask, xyz=xyz, z_vals=z)
 
-    def mlp_init_pass(self, *args, **kwargs):
-        raise NotImplementedError("mlp_init_pass (sphere-init pre-training, volume_renderer.py:569-634) is "
-                                  "training-only and outside this library's scope")
+    def mlp_init_pass(self, cam_poses, focals, img_size, near, far, styles, nerf_cfg):
+        """Sphere-initialisation pass (volume_renderer.py:569-634): sdf of stratified samples (`offset_sampling=False`)
+        and its target `|pts| - (far - near) / 4`; differentiable w.r.t. the renderer parameters (FP32-pipe backward)."""
+        from .nerf_utils import Render
+        rays_o, rays_d, viewdirs = Render.get_rays_in_world(focal=focals, img_size=img_size, c2w=cam_poses)
+        z_vals = Render.get_z_vals(near=near, far=far, rays_d=rays_d, N_samples=nerf_cfg["N_samples"],
+                                   offset_sampling=False)
+        pts = Render.get_points(rays_o, rays_d, z_vals)
+        b = pts.shape[0]
+        sdf = self.forward(pts=pts, rays_d=rays_d.reshape(b, -1, 3), viewdirs=viewdirs.reshape(b, -1, 3),
+                           z_vals=z_vals.reshape(b, -1, z_vals.shape[-1]), near=near, far=far, styles=styles)[2]
+        sdf = sdf.squeeze(-1)
+        target_values = pts.detach().norm(dim=-1) - (far - near).view(-1, 1, 1, 1) / 4
+        return sdf, target_values

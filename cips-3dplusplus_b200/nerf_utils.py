@@ -25,6 +25,47 @@ def _stream():
 
 
 class Render:
+    # The three helpers below are plain PyTorch (a handful of elementwise ops on (b, h, w, .) tensors): the fused kernel
+    # generates rays and samples itself, these exist for callers of the reference's static API (mlp_init_pass, apps).
+    @staticmethod
+    def get_rays_in_world(focal, img_size, c2w, static_viewdirs=False):
+        """nerf_utils.py:17-66 -> rays_o, rays_d, viewdirs, each (b, h, w, 3); rays_d is not normalised."""
+        b, S, dev = c2w.shape[0], int(img_size), c2w.device
+        lin = torch.linspace(0.5, S - 0.5, S, device=dev)
+        yy, xx = torch.meshgrid(lin, lin, indexing="ij")
+        f = focal.reshape(b, 1, 1).to(torch.float32)
+        d_cam = torch.stack([(xx[None] - S / 2) / f, -(yy[None] - S / 2) / f, -torch.ones(b, S, S, device=dev)], -1)
+        rays_d = (d_cam[..., None, :] * c2w[:, None, None, :3, :3]).sum(-1)
+        rays_o = c2w[:, None, None, :3, 3].expand(rays_d.shape)
+        viewdirs = F.normalize(d_cam if static_viewdirs else rays_d, dim=-1)
+        return rays_o, rays_d, viewdirs
+
+    @staticmethod
+    def get_z_vals(near, far, rays_d, N_samples, perturb=True, offset_sampling=True):
+        """nerf_utils.py:68-121 -> z_vals (b, h, w, N): offset sampling (one draw per ray) or stratified sampling."""
+        b, h, w, _ = rays_d.shape
+        dev = rays_d.device
+        near = near.reshape(b, 1, 1, 1).to(torch.float32).expand(b, h, w, 1)
+        far = far.reshape(b, 1, 1, 1).to(torch.float32).expand(b, h, w, 1)
+        hi = 1.0 - 1.0 / N_samples if offset_sampling else 1.0
+        t = torch.linspace(0.0, hi, N_samples, device=dev).view(1, 1, 1, -1)
+        z = near * (1.0 - t) + far * t
+        if perturb:
+            if offset_sampling:
+                upper, lower = torch.cat([z[..., 1:], far], -1), z.detach()
+                t_rand = torch.rand(b, h, w, 1, device=dev)
+            else:
+                mids = 0.5 * (z[..., 1:] + z[..., :-1])
+                upper, lower = torch.cat([mids, z[..., -1:]], -1), torch.cat([z[..., :1], mids], -1)
+                t_rand = torch.rand(z.shape, device=dev)
+            z = lower + (upper - lower) * t_rand
+        return z
+
+    @staticmethod
+    def get_points(rays_o, rays_d, z_vals):
+        """nerf_utils.py:135-170 -> pts (b, h, w, N, 3)."""
+        return rays_o.unsqueeze(-2) + rays_d.unsqueeze(-2) * z_vals.unsqueeze(-1)
+
     @staticmethod
     def prepare_nerf_inputs(focal, img_size, cam_poses, near, far, N_samples, perturb, static_viewdirs=False,
                             **kwargs):

@@ -201,13 +201,49 @@ def param_grads():
         names = [k for k, _ in R.named_parameters()]
         gs = torch.autograd.grad(loss, [p for _, p in R.named_parameters()])
         keep = lambda k, g: g.numel() < 65536 or D <= 2 or "views" in k or k.split(".")[2] in ("1", str(D - 1))   # size
-        np.savez_compressed(os.path.join(HERE, f"pgrads_{name}.npz"),
+        # the eikonal term of the same inputs (nerf_utils.py:220-228), first order
+        pts_e = t("pts").clone()
+        eik = R(pts=pts_e, rays_d=t("rays_d"), viewdirs=t("viewdirs"), z_vals=t("z_vals"), near=t("near"), far=t("far"),
+                styles=t("styles"), return_eikonal=True)[5]
+        np.savez_compressed(os.path.join(HERE, f"pgrads_{name}.npz"), eikonal_term=eik.detach().numpy(),
                             **{k: g.numpy() for k, g in zip(names, gs) if keep(k, g)})
         print(name, {k: float(g.abs().mean()) for k, g in zip(names, gs) if "weight" not in k or "pts_linears.1." in k})
+
+
+def mlp_init_case():
+    """VolumeFeatureRenderer.mlp_init_pass (volume_renderer.py:569-634) on a small image with the stratified-sampling
+    draw pinned (torch.rand is patched to return the stored tensor)."""
+    nu, vr = import_reference()
+    w = np.load(os.path.join(HERE, "weights_seed0.npz"))
+    sd8 = {k: torch.from_numpy(w[k].astype(np.float32)) for k in w.files}
+    D, S, N, b = 2, 8, 12, 2
+    R = vr.VolumeFeatureRenderer(N_layers_renderer=D, input_dim=3, hidden_dim=256, style_dim=256, view_dim=3,
+                                 with_sdf=True, output_features=True)
+    R.load_state_dict(sub_state(sd8, D), strict=True)
+    g = torch.Generator().manual_seed(21)
+    locs = torch.tensor([[0.2, -0.1], [-0.25, 0.1]])
+    c2w, focal, near, far, _ = nu.Camera.generate_camera_params(img_size=S, device="cpu", locations=locs, **FFHQ)
+    styles = 0.6 * torch.randn(b, D + 1, 256, generator=g)
+    t_rand = torch.rand(b, S, S, N, generator=g)
+    real_rand = torch.rand
+    torch.rand = lambda *a, **k: t_rand.clone()
+    try:
+        sdf, target = R.mlp_init_pass(cam_poses=c2w, focals=focal, img_size=S, near=near, far=far, styles=styles,
+                                      nerf_cfg=dict(N_samples=N))
+    finally:
+        torch.rand = real_rand
+    loss = ((sdf - target) ** 2).mean()
+    gs = torch.autograd.grad(loss, [R.network.pts_linears[1].weight, R.network.sigma_linear.weight, R.network.pts_linears[0].gamma.bias])
+    np.savez_compressed(os.path.join(HERE, "mlp_init_pass.npz"), c2w=c2w.numpy(), focal=focal.numpy(), near=near.numpy(),
+                        far=far.numpy(), styles=styles.numpy(), t_rand=t_rand.numpy(), sdf=sdf.detach().numpy(),
+                        target=target.numpy(), loss=np.float32(loss.item()), g_w1=gs[0].numpy(), g_wsigma=gs[1].numpy(),
+                        g_gamma0_bias=gs[2].numpy(), D=np.int32(D), S=np.int32(S), N=np.int32(N))
+    print("mlp_init_pass", sdf.shape, float(loss))
 
 
 if __name__ == "__main__":
     if "--param-grads" in sys.argv:
         param_grads()
+        mlp_init_case()
     else:
         main()

@@ -40,8 +40,7 @@ def test_swap_keeps_state_dict_and_module_contract(ref):
     assert isinstance(G3.renderer, c3d.NerfBranch) and G3.renderer._cache is None
     G3.renderer.requires_grad_(False)
     assert not any(p.requires_grad for p in G3.renderer.parameters())
-    with pytest.raises(NotImplementedError):
-        G3.renderer.mlp_init_pass()
+    assert callable(G3.renderer.mlp_init_pass)                            # model_v3.py:1462 (training only)
 
 
 def _oracle_backed_run(self, kind, meta, styles, a0, a1, a2, a3, near, far):

@@ -242,3 +242,55 @@ def test_inversion_cuda_graph_matches_eager():
     assert le[-1] < 0.8 * le[0]
     assert np.abs(le - lg).max() / le.max() < 2e-3, (le, lg)
     assert rel_l2(graph["w"].cpu().numpy(), eager["w"].cpu().numpy()) < 2e-2
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", GRAD_CASES)
+def test_eikonal_term_matches_reference(case, precision):
+    """return_eikonal=True: d sdf / d pts (nerf_utils.py:220-228) vs the reference's autograd.grad; differentiating
+    through the term (the training-time double backward) must fail loudly."""
+    import os
+    from conftest import GOLDEN
+    c = load_case(case)
+    ref = np.load(os.path.join(GOLDEN, f"pgrads_{case}.npz"))["eikonal_term"]
+    m = _module(int(c["D"]), precision)
+    with torch.no_grad():
+        out = m(pts=_t(c["pts"]), rays_d=_t(c["rays_d"]), viewdirs=_t(c["viewdirs"]), z_vals=_t(c["z_vals"]),
+                near=_t(c["near"]), far=_t(c["far"]), styles=_t(c["styles"]), return_eikonal=True)
+    eik = out[5]
+    assert eik.shape == ref.shape
+    err = rel_l2(eik.cpu().numpy(), ref)
+    print(case, precision, "eikonal rel-L2", err)
+    assert err < (GRAD_REL if precision == "fp32" else GRAD_REL_BF16)
+    assert rel_l2(out[2].cpu().numpy(), c["sdf"]) < (1e-3 if precision == "fp32" else 5e-2)
+    styles = _t(c["styles"], True)
+    out = m(pts=_t(c["pts"]), rays_d=_t(c["rays_d"]), viewdirs=_t(c["viewdirs"]), z_vals=_t(c["z_vals"]),
+            near=_t(c["near"]), far=_t(c["far"]), styles=styles, return_eikonal=True)
+    with pytest.raises(NotImplementedError):
+        ((out[5].norm(dim=-1) - 1) ** 2).mean().backward()
+
+
+def test_mlp_init_pass_matches_reference(monkeypatch):
+    """Sphere-init pass (volume_renderer.py:569-634) with the stratified-sampling draw pinned: sdf, targets, and the
+    gradients of the MSE loss w.r.t. renderer parameters vs the reference (tests/golden/mlp_init_pass.npz)."""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "mlp_init_pass.npz"))
+    m = _module(int(z["D"]), "fp32").requires_grad_(True)
+    t_rand = _t(z["t_rand"])
+    real_rand = torch.rand
+    monkeypatch.setattr(torch, "rand", lambda *a, **k: t_rand.clone())
+    try:
+        sdf, target = m.mlp_init_pass(cam_poses=_t(z["c2w"]), focals=_t(z["focal"]), img_size=int(z["S"]), near=_t(z["near"]),
+                                      far=_t(z["far"]), styles=_t(z["styles"]), nerf_cfg=dict(N_samples=int(z["N"])))
+    finally:
+        monkeypatch.setattr(torch, "rand", real_rand)
+    assert sdf.shape == z["sdf"].shape and target.shape == z["target"].shape
+    assert np.abs(target.cpu().numpy() - z["target"]).max() < 1e-5
+    assert rel_l2(sdf.detach().cpu().numpy(), z["sdf"]) < 1e-3
+    loss = ((sdf - target) ** 2).mean()
+    assert abs(loss.item() - float(z["loss"])) < 2e-3 * float(z["loss"])
+    loss.backward()
+    assert rel_l2(m.network.pts_linears[1].weight.grad.cpu().numpy(), z["g_w1"]) < GRAD_REL
+    assert rel_l2(m.network.sigma_linear.weight.grad.cpu().numpy(), z["g_wsigma"]) < GRAD_REL
+    assert rel_l2(m.network.pts_linears[0].gamma.bias.grad.cpu().numpy(), z["g_gamma0_bias"]) < GRAD_REL

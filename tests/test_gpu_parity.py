@@ -270,9 +270,6 @@ def test_argument_errors_are_reported():
         m(pts=torch.from_numpy(c["pts"]), rays_d=torch.from_numpy(c["rays_d"]), viewdirs=torch.from_numpy(c["viewdirs"]),
           z_vals=torch.from_numpy(c["z_vals"]), near=torch.from_numpy(c["near"]), far=torch.from_numpy(c["far"]),
           styles=torch.from_numpy(c["styles"]))
-    with pytest.raises(NotImplementedError):
-        m(pts=_t(c["pts"]), rays_d=_t(c["rays_d"]), viewdirs=_t(c["viewdirs"]), z_vals=_t(c["z_vals"]),
-          near=_t(c["near"]), far=_t(c["far"]), styles=_t(c["styles"]), return_eikonal=True)
     with pytest.raises(c3d._abi.C3DError, match="n_samples"):      # bf16 path needs N >= 8
         m(pts=_t(c["pts"][:, :, :4]), rays_d=_t(c["rays_d"]), viewdirs=_t(c["viewdirs"]), z_vals=_t(c["z_vals"][:, :, :4]),
           near=_t(c["near"]), far=_t(c["far"]), styles=_t(c["styles"]))
