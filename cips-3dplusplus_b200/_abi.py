@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("C3D_LIB") or os.path.join(HERE, "libc3dpp.so")   # C3D_LIB: A/B builds (bench_tools)
 SRC = os.path.join(HERE, "csrc", "c3d_abi.cu")
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_LAYERS = 16
 MODE_FP32, MODE_BF16 = 0, 1
 INPUT_POSES, INPUT_POINTS = 0, 1
@@ -77,6 +77,8 @@ EXPORTS = {
     "c3d_nerf_forward": (C.c_int, [C.POINTER(FwdParams), _fp]),
     "c3d_backward_workspace_bytes": (C.c_size_t, [C.POINTER(BwdParams)]),
     "c3d_nerf_backward": (C.c_int, [C.POINTER(BwdParams), _fp]),
+    "c3d_eikonal_workspace_bytes": (C.c_size_t, [C.POINTER(BwdParams)]),
+    "c3d_eikonal_backward": (C.c_int, [C.POINTER(BwdParams), _fp, _fp]),
     "c3d_raygen": (C.c_int, [C.POINTER(RaygenParams), _fp]),
     "c3d_style_prep": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, _fp, _fp, _fp]),
     "c3d_composite_forward": (C.c_int, [C.POINTER(CompositeParams), _fp]),

@@ -11,6 +11,7 @@
 #include "fused_pair_sm100.cuh"
 #include "backward.cuh"
 #include "param_grads.cuh"
+#include "eikonal.cuh"
 #include "fused_bwd_sm100.cuh"
 
 namespace c3d {
@@ -858,7 +859,158 @@ static int backward_tc(const c3d_bwd_params* bp, cudaStream_t st) {
 
 }  // extern "C" (helpers above are static)
 
+namespace c3d {
+
+struct EikWs {
+  size_t film, first, view, g_film, chunk, total;
+  int chunk_imgs;
+  size_t c_acc, c_tacc, c_feat, c_rgb, c_sdf, c_h, c_hd, c_g, c_gd;
+};
+static EikWs eik_ws(const c3d_bwd_params* bp) {
+  const c3d_fwd_params* p = &bp->fwd;
+  EikWs w;
+  memset(&w, 0, sizeof(w));
+  size_t o = 0;
+  const size_t b = (size_t)p->batch, P = (size_t)p->n_rays * p->n_samples, D = (size_t)p->D;
+  w.film = o;   o += align_up(b * (D + 1) * W * sizeof(float2), 256);
+  w.first = o;  o += align_up(b * W * sizeof(float4), 256);
+  w.view = o;   o += align_up(b * W * sizeof(float4), 256);
+  w.g_film = o; o += align_up(b * (D + 1) * W * sizeof(float2), 256);
+  w.chunk = o;
+  const size_t per_img = P * W * 4 * (6 * D + 1) + P * 16 + 8192;
+  size_t ci = ((size_t)4 << 30) / per_img;
+  if (ci < 1) ci = 1;
+  if (ci > b) ci = b;
+  w.chunk_imgs = (int)ci;
+  size_t c = 0;
+  auto take = [&](size_t bytes) { const size_t at = c; c += align_up(bytes, 256); return at; };
+  w.c_acc = take(ci * P * D * W * 4); w.c_tacc = take(ci * P * D * W * 4);
+  w.c_feat = take(ci * P * W * 4); w.c_rgb = take(ci * P * 12); w.c_sdf = take(ci * P * 4);
+  w.c_h = take(ci * P * D * W * 4); w.c_hd = take(ci * P * D * W * 4);
+  w.c_g = take(ci * P * D * W * 4); w.c_gd = take(ci * P * D * W * 4);
+  w.total = o + c;
+  return w;
+}
+
+}  // namespace c3d
+
 extern "C" {
+
+size_t c3d_eikonal_workspace_bytes(const c3d_bwd_params* p) {
+  if (!p || p->fwd.batch < 1 || p->fwd.n_rays < 1 || p->fwd.n_samples < 1 || p->fwd.D < 1) return 0;
+  return eik_ws(p).total;
+}
+
+int c3d_eikonal_backward(const c3d_bwd_params* bp, const float* g_eik, c3d_stream_t stream) {
+  g_launches = 0;
+  C3D_CHECK_ARG(bp != nullptr && g_eik != nullptr, "params / g_eik is NULL");
+  const c3d_fwd_params* p = &bp->fwd;
+  C3D_CHECK_ARG(p->abi_version == C3D_ABI_VERSION, "abi_version %d != library %d", p->abi_version, C3D_ABI_VERSION);
+  C3D_CHECK_ARG(p->input_kind == C3D_INPUT_POINTS, "the eikonal path takes C3D_INPUT_POINTS inputs");
+  C3D_CHECK_ARG(p->batch >= 1 && p->n_rays >= 1 && p->n_samples >= 1, "batch / n_rays / n_samples must be >= 1");
+  C3D_CHECK_ARG(p->D >= 1 && p->D <= C3D_MAX_LAYERS, "D=%d outside [1,%d]", p->D, C3D_MAX_LAYERS);
+  C3D_CHECK_ARG((long long)p->batch * p->n_rays * p->n_samples < (1ll << 31), "batch*n_rays*n_samples overflows int32");
+  C3D_CHECK_ARG(p->packed && p->styles && p->near && p->far && p->pts && p->viewdirs, "packed/styles/near/far/pts/viewdirs must be non-NULL");
+  C3D_CHECK_ARG(bp->g_styles || bp->g_params, "nothing to compute: g_styles and g_params are both NULL");
+  const EikWs w = eik_ws(bp);
+  C3D_CHECK_ARG(p->workspace && p->workspace_bytes >= w.total, "workspace too small: %zu < %zu", p->workspace_bytes, w.total);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(p->workspace);
+  uint8_t* ck = ws + w.chunk;
+  const size_t P = (size_t)p->n_rays * p->n_samples, R = (size_t)p->n_rays;
+  const int D = p->D;
+  const PackedLayout L = packed_layout(D);
+  float2* film = reinterpret_cast<float2*>(ws + w.film);
+  float* g_film = reinterpret_cast<float*>(ws + w.g_film);
+  int rc = launch_style_prep(p->packed, D, p->styles, p->batch, reinterpret_cast<float*>(film),
+                             reinterpret_cast<float*>(ws + w.first), reinterpret_cast<float*>(ws + w.view), st);
+  if (rc != C3D_OK) return rc;
+  C3D_CUDA(cudaMemsetAsync(g_film, 0, (size_t)p->batch * (D + 1) * W * sizeof(float2), st));
+  const c3d_param_grads* pg = bp->g_params;
+  if (pg) {
+    for (int l = 0; l < D; ++l) C3D_CUDA(cudaMemsetAsync(pg->pts_weight[l], 0, sizeof(float) * W * (l == 0 ? 3 : W), st));
+    C3D_CUDA(cudaMemsetAsync(pg->views_weight, 0, sizeof(float) * W * (W + 3), st));
+    C3D_CUDA(cudaMemsetAsync(pg->rgb_weight, 0, sizeof(float) * 3 * W, st));
+    C3D_CUDA(cudaMemsetAsync(pg->rgb_bias, 0, sizeof(float) * 3, st));
+    C3D_CUDA(cudaMemsetAsync(pg->sigma_weight, 0, sizeof(float) * W, st));
+    C3D_CUDA(cudaMemsetAsync(pg->sigma_bias, 0, sizeof(float), st));
+    C3D_CUDA(cudaMemsetAsync(pg->sigmoid_beta, 0, sizeof(float), st));
+  }
+  C3D_CUDA(cudaFuncSetAttribute(mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F32_SMEM));
+  C3D_CUDA(cudaFuncSetAttribute(eik_tangent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EIKT_SMEM));
+  C3D_CUDA(cudaFuncSetAttribute(eik_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EIKB_SMEM));
+  for (int i0 = 0; i0 < p->batch; i0 += w.chunk_imgs) {
+    const int ni = (p->batch - i0 < w.chunk_imgs) ? p->batch - i0 : w.chunk_imgs;
+    const float* pts = p->pts + (size_t)i0 * P * 3;
+    // 1. primal forward with saved accumulators
+    MlpF32Args m;
+    m.blob = reinterpret_cast<const uint8_t*>(p->packed); m.L = L;
+    m.film = film + (size_t)i0 * (D + 1) * W;
+    m.first = reinterpret_cast<const float4*>(ws + w.first) + (size_t)i0 * W;
+    m.view = reinterpret_cast<const float4*>(ws + w.view) + (size_t)i0 * W;
+    m.pts = pts; m.viewdirs = p->viewdirs + (size_t)i0 * R * 3; m.near = p->near + i0; m.far = p->far + i0;
+    m.n_samples = p->n_samples; m.pts_per_img = (int)P; m.tiles_per_img = (int)((P + F32_TP - 1) / F32_TP);
+    m.feat = reinterpret_cast<float*>(ck + w.c_feat); m.rgb = reinterpret_cast<float*>(ck + w.c_rgb);
+    m.sdf = reinterpret_cast<float*>(ck + w.c_sdf);
+    m.save_acc = reinterpret_cast<float*>(ck + w.c_acc); m.save_stride = (size_t)ni * P * W;
+    mlp_fp32_kernel<<<(unsigned)(ni * m.tiles_per_img), 256, F32_SMEM, st>>>(m);
+    C3D_LAUNCH_CHECK();
+    // 2. tangent sweep along v, 3. reverse sweep over both chains
+    EikArgs e;
+    memset(&e, 0, sizeof(e));
+    e.blob = m.blob; e.L = L; e.film = m.film; e.first = m.first;
+    e.pts = pts; e.v = g_eik + (size_t)i0 * P * 3; e.near = m.near; e.far = m.far;
+    e.pts_per_img = (int)P; e.tiles_per_img = m.tiles_per_img;
+    e.save_acc = m.save_acc; e.save_stride = m.save_stride; e.save_tacc = reinterpret_cast<float*>(ck + w.c_tacc);
+    e.g_film = g_film + (size_t)i0 * (D + 1) * W * 2;
+    e.dump_h = reinterpret_cast<float*>(ck + w.c_h); e.dump_hd = reinterpret_cast<float*>(ck + w.c_hd);
+    e.dump_g = reinterpret_cast<float*>(ck + w.c_g); e.dump_gd = reinterpret_cast<float*>(ck + w.c_gd);
+    eik_tangent_kernel<<<(unsigned)(ni * e.tiles_per_img), 256, EIKT_SMEM, st>>>(e);
+    C3D_LAUNCH_CHECK();
+    eik_bwd_kernel<<<(unsigned)(ni * e.tiles_per_img), 256, EIKB_SMEM, st>>>(e);
+    C3D_LAUNCH_CHECK();
+    // 4. weight gradients from the dumps
+    if (pg) {
+      const long long np = (long long)ni * P;
+      const int splits = (int)((np + 4095) / 4096 < 74 ? (np + 4095) / 4096 : 74);
+      const int per_cta = (int)(((np + splits - 1) / splits + WG_PC - 1) / WG_PC * WG_PC);
+      for (int l = 1; l < D; ++l) {
+        wgrad_gemm_kernel<<<dim3(4, splits), 256, 0, st>>>(e.dump_g + (size_t)l * e.save_stride, e.dump_h + (size_t)(l - 1) * e.save_stride,
+                                                          np, per_cta, pg->pts_weight[l], W);
+        C3D_LAUNCH_CHECK();
+        wgrad_gemm_kernel<<<dim3(4, splits), 256, 0, st>>>(e.dump_gd + (size_t)l * e.save_stride, e.dump_hd + (size_t)(l - 1) * e.save_stride,
+                                                          np, per_cta, pg->pts_weight[l], W);
+        C3D_LAUNCH_CHECK();
+      }
+      HeadWgradArgs h;
+      memset(&h, 0, sizeof(h));
+      h.pts_per_img = (int)P;
+      const int hs = (int)((P + 2047) / 2048 < 64 ? (P + 2047) / 2048 : 64);
+      h.pts_per_cta = (int)((P + hs - 1) / hs);
+      h.a_cols = 3; h.a_div = 1; h.near = m.near; h.far = m.far; h.out = pg->pts_weight[0]; h.so_j = 1; h.so_c = 3;
+      h.a = pts; h.H = e.dump_g;                       // adj(u_0)^T x
+      head_wgrad_kernel<<<dim3(hs, ni), 256, 0, st>>>(h);
+      C3D_LAUNCH_CHECK();
+      h.a = e.v; h.H = e.dump_gd;                      // adj(ud_0)^T xd
+      head_wgrad_kernel<<<dim3(hs, ni), 256, 0, st>>>(h);
+      C3D_LAUNCH_CHECK();
+      h.a = nullptr; h.a_cols = 1; h.near = h.far = nullptr; h.H = e.dump_hd + (size_t)(D - 1) * e.save_stride;
+      h.out = pg->sigma_weight; h.so_j = W; h.so_c = 1;   // S = w_sigma . hd_{D-1}
+      head_wgrad_kernel<<<dim3(hs, ni), 256, 0, st>>>(h);
+      C3D_LAUNCH_CHECK();
+    }
+  }
+  if (bp->g_styles) {
+    film_bwd_kernel<<<dim3(D + 1, p->batch), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(p->packed), L, g_film, bp->g_styles);
+    C3D_LAUNCH_CHECK();
+  }
+  if (pg) {
+    film_param_bwd_kernel<<<dim3(D + 1, W), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(p->packed), L, *pg, g_film, film,
+                                                           p->styles, p->batch);
+    C3D_LAUNCH_CHECK();
+  }
+  return C3D_OK;
+}
 
 int c3d_composite_backward(const c3d_composite_params* p, c3d_stream_t stream) {
   C3D_CHECK_ARG(p && p->n_rays >= 1, "n_rays must be >= 1");

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) wgrad_gemm_kernel(const float* __restrict
 }
 
 struct HeadWgradArgs {
-  const float* a;      // (imgs * pts_per_img / a_div, a_cols) small left factor
+  const float* a;      // (imgs * pts_per_img / a_div, a_cols) small left factor; NULL: a single column of ones
   int a_cols, a_div;   // a_div = n_samples when `a` is per ray
   const float* H;      // (imgs * pts_per_img, 256)
   int pts_per_img, pts_per_cta;
@@ -83,10 +83,10 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(HeadWgradArgs g) {
   const size_t base = (size_t)img * g.pts_per_img;
   for (int p = p_begin; p < p_end; ++p) {
     const float h = __ldcs(g.H + (base + p) * W + c);
-    const float* ap = g.a + ((base + p) / g.a_div) * g.a_cols;
+    const float* ap = g.a ? g.a + ((base + p) / g.a_div) * g.a_cols : nullptr;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (j < g.a_cols) { const float v = ap[j]; acc[j] = fmaf(v, h, acc[j]); sum[j] += v; }
+      if (j < g.a_cols) { const float v = ap ? ap[j] : 1.0f; acc[j] = fmaf(v, h, acc[j]); sum[j] += v; }
   }
   const float scale = g.near ? 2.0f / (g.far[img] - g.near[img]) : 1.0f;
   if (p_begin < p_end) {

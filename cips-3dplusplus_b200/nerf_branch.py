@@ -97,18 +97,29 @@ class _NerfFn(torch.autograd.Function):
         return (None, None, None) + grads
 
 
-class _EikonalGuard(torch.autograd.Function):
-    """Carries the eikonal term in the graph so that differentiating THROUGH it (the training-time double backward of
-    volume_renderer.py:223-224 / nerf_utils.py:220-228) fails loudly instead of silently dropping the term."""
+class _EikonalFn(torch.autograd.Function):
+    """Eikonal term E = d sdf / d pts (nerf_utils.py:220-228).  forward: one c3d_nerf_backward launch with a cotangent of
+    ones on sdf (points are independent).  backward: c3d_eikonal_backward, the reverse-over-forward sweep that returns
+    dL/d styles and dL/d parameters for a loss on E (the training-time double backward).  No gradient is returned for
+    `pts` (a Hessian-vector product the reference's training never uses: cameras are sampled, not optimised)."""
 
     @staticmethod
-    def forward(ctx, value, *deps):
-        return value.clone()
+    def forward(ctx, module, meta, styles, pts, rays_d, viewdirs, z_vals, near, far, *params):
+        ones = torch.ones(meta[0], meta[1], meta[2], dtype=torch.float32, device=pts.device)
+        needs = (False, False, False, False, True) + (False,) * 5 + (False,) * len(params)
+        grads = module._launch_backward(_abi.INPUT_POINTS, meta, styles, pts, rays_d, viewdirs, z_vals, near, far,
+                                        None, None, ones, None, None, needs)
+        ctx.module, ctx.meta = module, meta
+        ctx.save_for_backward(styles, pts, rays_d, viewdirs, z_vals, near, far)
+        return grads[1]
 
     @staticmethod
-    def backward(ctx, g):
-        raise NotImplementedError("second-order gradients through the eikonal term are not provided by libc3dpp: "
-                                  "the term can be evaluated and logged, not trained on")
+    def backward(ctx, g_eik):
+        styles, pts, rays_d, viewdirs, z_vals, near, far = ctx.saved_tensors
+        needs = ctx.needs_input_grad
+        g_styles, g_params = ctx.module._launch_eikonal_backward(ctx.meta, styles, pts, rays_d, viewdirs, z_vals, near, far,
+                                                                 g_eik, needs[2], needs[9:])
+        return (None, None, g_styles, None, None, None, None, None, None) + tuple(g_params)
 
 
 class NerfBranch(nn.Module):
@@ -289,6 +300,38 @@ class NerfBranch(nn.Module):
             else [None] * (len(needs) - 10)
         return (g_styles, g_a0, g_a1, g_a2, None, None, None) + tuple(g_params)
 
+    def _launch_eikonal_backward(self, meta, styles, pts, rays_d, viewdirs, z_vals, near, far, g_eik, need_styles,
+                                 need_params):
+        """c3d_eikonal_backward: dL/d styles and dL/d parameters for a loss on the eikonal term (FP32 pipe)."""
+        lib = _abi.load()
+        dev = styles.device
+        b, n_rays, N = meta[0], meta[1], meta[2]
+        B = _abi.BwdParams()
+        self._fill_common(B.fwd, _abi.INPUT_POINTS, (b, n_rays, N, 0, False, False), styles, pts, rays_d, viewdirs, z_vals,
+                          near, far)
+        g_eik = g_eik.to(torch.float32).reshape(b, n_rays, N, 3).contiguous()
+        g_styles = torch.empty_like(styles) if need_styles else None
+        B.g_styles = None if g_styles is None else g_styles.data_ptr()
+        want_params = any(need_params)
+        g_params, pg = [None] * len(need_params), None
+        if want_params:
+            g_all = [torch.zeros_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
+                     for p in self._ordered_params()]
+            pg = _abi.ParamGrads()
+            self._fill_param_struct(pg, g_all)
+            B.g_params = C.cast(C.pointer(pg), C.c_void_p)
+            g_params = [g.to(p.dtype) if need else None for g, p, need in zip(g_all, self._ordered_params(), need_params)]
+        if g_styles is None and not want_params:
+            return None, g_params
+        nws = lib.c3d_eikonal_workspace_bytes(B)
+        ws = torch.empty(max(nws, 16), dtype=torch.uint8, device=dev)
+        B.fwd.workspace, B.fwd.workspace_bytes = ws.data_ptr(), nws
+        with torch.cuda.device(dev):
+            _abi.check(lib.c3d_eikonal_backward(B, g_eik.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                       "c3d_eikonal_backward")
+        self.last_launch_count = lib.c3d_last_launch_count()
+        return g_styles, g_params
+
     def _run(self, kind, meta, styles, a0, a1, a2, a3, near, far):
         tensors = [styles, a0, a1, near, far] + [t for t in (a2, a3) if t is not None]
         for t in tensors:
@@ -323,19 +366,10 @@ class NerfBranch(nn.Module):
             c(rays_d, b, n_rays, 3), c(viewdirs, b, n_rays, 3), c(z_vals, b, n_rays, N), c(near, b), c(far, b))
         eik = None
         if return_eikonal:
-            # d sdf / d pts (nerf_utils.py:220-228): points are independent, so one backward launch with a cotangent of
-            # ones on sdf returns every point's own gradient.  First order only (see _EikonalGuard).
+            # d sdf / d pts (nerf_utils.py:220-228), differentiable w.r.t. styles and parameters (see _EikonalFn)
             args = (c(styles, b, self.N_layers_renderer + 1, W), c(pts, b, n_rays, N, 3), c(rays_d, b, n_rays, 3),
                     c(viewdirs, b, n_rays, 3), c(z_vals, b, n_rays, N), c(near, b), c(far, b))
-            ones = torch.ones(b, n_rays, N, dtype=torch.float32, device=pts.device)
-            needs = (False, False, False, False, True) + (False,) * 5 + (False,) * len(self._ordered_params())
-            with torch.no_grad():
-                grads = self._launch_backward(_abi.INPUT_POINTS, meta, *args, None, None, ones, None, None, needs)
-            eik = grads[1].reshape(*lead, N, 3)
-            deps = [t for t in (styles, pts) if torch.is_tensor(t) and t.requires_grad] + \
-                [p for p in self.parameters() if p.requires_grad]
-            if torch.is_grad_enabled() and deps:
-                eik = _EikonalGuard.apply(eik, *deps)
+            eik = _EikonalFn.apply(self, meta, *args, *self._ordered_params()).reshape(*lead, N, 3)
         if len(lead) > 2:
             rgb_map, feat, mask, xyz = (t.reshape(*lead, t.shape[-1]) for t in (rgb_map, feat, mask, xyz))
             sdf = sdf.reshape(*lead, N, 1)

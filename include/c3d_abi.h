@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define C3D_ABI_VERSION 4
+#define C3D_ABI_VERSION 5
 #define C3D_MAX_LAYERS 16
 #define C3D_W 256
 
@@ -188,6 +188,12 @@ int c3d_nerf_forward(const c3d_fwd_params* p, c3d_stream_t stream);
 
 size_t c3d_backward_workspace_bytes(const c3d_bwd_params* p);
 int c3d_nerf_backward(const c3d_bwd_params* p, c3d_stream_t stream);
+
+/* Second-order path of the eikonal regulariser (training; nerf_utils.py:220-228 with create_graph=True): given
+ * g_eik = dL/dE (batch,n_rays,N,3) for E = d sdf / d pts, returns dL/d styles (p->g_styles) and dL/d parameters
+ * (p->g_params); C3D_INPUT_POINTS only, the other gradient pointers and the cotangents in p are ignored. */
+size_t c3d_eikonal_workspace_bytes(const c3d_bwd_params* p);
+int c3d_eikonal_backward(const c3d_bwd_params* p, const float* g_eik, c3d_stream_t stream);
 
 int c3d_raygen(const c3d_raygen_params* p, c3d_stream_t stream);
 /* film: (batch, D+1, 256, 2) = (gamma, gamma*bias+beta); first: (batch,256,4); view: (batch,256,4) */

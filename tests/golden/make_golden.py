@@ -205,7 +205,18 @@ def param_grads():
         pts_e = t("pts").clone()
         eik = R(pts=pts_e, rays_d=t("rays_d"), viewdirs=t("viewdirs"), z_vals=t("z_vals"), near=t("near"), far=t("far"),
                 styles=t("styles"), return_eikonal=True)[5]
-        np.savez_compressed(os.path.join(HERE, f"pgrads_{name}.npz"), eikonal_term=eik.detach().numpy(),
+        # ... and the second-order gradients of an eikonal loss (train_v10-style regulariser) w.r.t. styles and parameters
+        st_e = t("styles").clone().requires_grad_(True)
+        eik2 = R(pts=t("pts").clone(), rays_d=t("rays_d"), viewdirs=t("viewdirs"), z_vals=t("z_vals"), near=t("near"),
+                 far=t("far"), styles=st_e, return_eikonal=True)[5]
+        loss_e = ((eik2.norm(dim=-1) - 1) ** 2).mean()
+        ps = [p for _, p in R.named_parameters()]
+        ge = torch.autograd.grad(loss_e, [st_e] + ps, allow_unused=True)
+        eik_grads = {"eik_g_styles": ge[0].numpy(), "eik_loss": np.float32(loss_e.item())}
+        for k, g_ in zip(names, ge[1:]):
+            if g_ is not None and keep(k, g_):
+                eik_grads["eik_g_" + k] = g_.numpy()
+        np.savez_compressed(os.path.join(HERE, f"pgrads_{name}.npz"), eikonal_term=eik.detach().numpy(), **eik_grads,
                             **{k: g.numpy() for k, g in zip(names, gs) if keep(k, g)})
         print(name, {k: float(g.abs().mean()) for k, g in zip(names, gs) if "weight" not in k or "pts_linears.1." in k})
 

@@ -263,11 +263,40 @@ def test_eikonal_term_matches_reference(case, precision):
     print(case, precision, "eikonal rel-L2", err)
     assert err < (GRAD_REL if precision == "fp32" else GRAD_REL_BF16)
     assert rel_l2(out[2].cpu().numpy(), c["sdf"]) < (1e-3 if precision == "fp32" else 5e-2)
+
+
+@pytest.mark.parametrize("case", GRAD_CASES)
+def test_eikonal_loss_second_order_gradients_match_reference(case):
+    """The training-time double backward: gradients of ((|E| - 1)^2).mean(), E = d sdf / d pts, w.r.t. the styles and
+    every point-layer parameter vs the reference's autograd (create_graph=True), tests/golden/pgrads_*.npz `eik_*`."""
+    import os
+    from conftest import GOLDEN
+    c = load_case(case)
+    ref = np.load(os.path.join(GOLDEN, f"pgrads_{case}.npz"))
+    m = _module(int(c["D"]), "fp32").requires_grad_(True)
     styles = _t(c["styles"], True)
     out = m(pts=_t(c["pts"]), rays_d=_t(c["rays_d"]), viewdirs=_t(c["viewdirs"]), z_vals=_t(c["z_vals"]),
             near=_t(c["near"]), far=_t(c["far"]), styles=styles, return_eikonal=True)
-    with pytest.raises(NotImplementedError):
-        ((out[5].norm(dim=-1) - 1) ** 2).mean().backward()
+    loss = ((out[5].norm(dim=-1) - 1) ** 2).mean()
+    assert abs(loss.item() - float(ref["eik_loss"])) < 1e-3 * float(ref["eik_loss"])
+    loss.backward()
+    assert rel_l2(styles.grad.cpu().numpy(), ref["eik_g_styles"]) < GRAD_REL
+    got = dict(m.named_parameters())
+    worst = ("", 0.0)
+    n = 0
+    for k in ref.files:
+        if not k.startswith("eik_g_network."):
+            continue
+        name = k[len("eik_g_"):]
+        e = rel_l2(got[name].grad.cpu().numpy(), ref[k])
+        worst = max(worst, (name, e), key=lambda t: t[1])
+        assert e < GRAD_REL, (name, e)
+        n += 1
+    assert n >= 8
+    # parameters the eikonal term does not depend on get exact zeros
+    assert float(got["network.views_linears.weight"].grad.abs().max()) == 0.0
+    assert float(got["network.rgb_linear.weight"].grad.abs().max()) == 0.0
+    print(case, "eikonal second-order: worst parameter gradient rel-L2", worst)
 
 
 def test_mlp_init_pass_matches_reference(monkeypatch):
