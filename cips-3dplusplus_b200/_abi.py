@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("C3D_LIB") or os.path.join(HERE, "libc3dpp.so")   # C3D_LIB: A/B builds (bench_tools)
 SRC = os.path.join(HERE, "csrc", "c3d_abi.cu")
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_LAYERS = 16
 MODE_FP32, MODE_BF16 = 0, 1
 INPUT_POSES, INPUT_POINTS = 0, 1
@@ -67,6 +67,13 @@ class CompositeParams(C.Structure):
                             "g_rgb", "g_sdf", "g_features", "g_pts", "g_rays_d", "g_sigmoid_beta")]
 
 
+class ResampleParams(C.Structure):
+    _fields_ = [("n_rays", C.c_int64), ("n_samples", C.c_int32), ("n_importance", C.c_int32),
+                ("sigmoid_beta", C.c_float), ("_pad", C.c_int32)] + \
+        [(n, _fp) for n in ("sigmoid_beta_ptr", "z_vals", "weights", "sdf", "rays_d", "rays_o", "u",
+                            "z_fine", "z_merged", "pts_merged")]
+
+
 EXPORTS = {
     "c3d_abi_version": (C.c_int, []),
     "c3d_last_error": (C.c_char_p, []),
@@ -83,6 +90,7 @@ EXPORTS = {
     "c3d_style_prep": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, _fp, _fp, _fp]),
     "c3d_composite_forward": (C.c_int, [C.POINTER(CompositeParams), _fp]),
     "c3d_composite_backward": (C.c_int, [C.POINTER(CompositeParams), _fp]),
+    "c3d_sample_pdf": (C.c_int, [C.POINTER(ResampleParams), _fp]),
     "c3d_umma_selftest": (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp]),
 }
 

@@ -13,6 +13,7 @@
 #include "param_grads.cuh"
 #include "eikonal.cuh"
 #include "fused_bwd_sm100.cuh"
+#include "resample.cuh"
 
 namespace c3d {
 thread_local char g_err[512] = "";
@@ -407,6 +408,45 @@ int c3d_composite_forward(const c3d_composite_params* p, c3d_stream_t stream) {
   C3D_CHECK_ARG(aligned16(p->features) && aligned16(p->feature_map), "features must be 16-byte aligned");
   C3D_CHECK_ARG(p->sigmoid_beta_ptr || p->sigmoid_beta > 0.f, "sigmoid_beta must be > 0");
   composite_fwd_kernel<<<(unsigned)((p->n_rays + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*p);
+  C3D_LAUNCH_CHECK();
+  return C3D_OK;
+}
+
+int c3d_sample_pdf(const c3d_resample_params* p, c3d_stream_t stream) {
+  C3D_CHECK_ARG(p && p->n_rays >= 1, "n_rays must be >= 1");
+  C3D_CHECK_ARG(p->n_samples >= 3 && p->n_samples <= resample::MAX_N, "n_samples=%d outside [3,%d]", p->n_samples,
+                resample::MAX_N);
+  C3D_CHECK_ARG(p->n_importance >= 1 && p->n_importance <= resample::MAX_K, "n_importance=%d outside [1,%d]",
+                p->n_importance, resample::MAX_K);
+  C3D_CHECK_ARG(p->z_vals, "z_vals must be non-NULL");
+  C3D_CHECK_ARG(p->weights || (p->sdf && p->rays_d), "either weights, or sdf and rays_d, must be given");
+  C3D_CHECK_ARG(p->weights || p->sigmoid_beta_ptr || p->sigmoid_beta > 0.f, "sigmoid_beta must be > 0");
+  C3D_CHECK_ARG(p->z_fine || p->z_merged || p->pts_merged, "no output requested");
+  C3D_CHECK_ARG(!p->pts_merged || (p->rays_o && p->rays_d), "pts_merged needs rays_o and rays_d");
+  C3D_CHECK_ARG(aligned16(p->z_vals) && aligned16(p->weights) && aligned16(p->sdf) && aligned16(p->rays_d) &&
+                aligned16(p->rays_o) && aligned16(p->u) && aligned16(p->z_fine) && aligned16(p->z_merged) &&
+                aligned16(p->pts_merged), "all pointers must be 16-byte aligned");
+  c3d_resample_params q = *p;
+  if (q.weights) q.sdf = nullptr;
+  if (!q.pts_merged) q.rays_o = nullptr;
+  if (q.weights && !q.pts_merged) q.rays_d = nullptr;
+  static int rb_env = -1;
+  if (rb_env < 0) { const char* e = getenv("C3D_RESAMPLE_RB"); rb_env = e ? atoi(e) : 0; }
+  C3D_CHECK_ARG(rb_env % 4 == 0, "C3D_RESAMPLE_RB must be a multiple of 4");
+  const resample::Layout L = resample::make_layout(q.n_samples, q.n_importance, q.u != nullptr, q.rays_o != nullptr,
+                                                   q.rays_d != nullptr, q.z_fine != nullptr, q.z_merged != nullptr,
+                                                   q.pts_merged != nullptr, rb_env);
+  const size_t smem = (size_t)L.total * sizeof(float);
+  C3D_CHECK_ARG(smem <= 200 * 1024, "resampling chunk does not fit shared memory (%zu bytes)", smem);
+  C3D_CUDA(cudaFuncSetAttribute(resample::sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long n_chunks = (q.n_rays + L.RB - 1) / L.RB;
+  C3D_CHECK_ARG(n_chunks < (1ll << 31), "too many rays");
+  int dev = 0, sms = 148;
+  C3D_CUDA(cudaGetDevice(&dev));
+  C3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+  const unsigned grid = (unsigned)(n_chunks < (long long)sms * per_sm ? n_chunks : (long long)sms * per_sm);
+  resample::sample_pdf_kernel<<<grid, resample::THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(q, L, (int)n_chunks);
   C3D_LAUNCH_CHECK();
   return C3D_OK;
 }

@@ -392,6 +392,39 @@ class NerfBranch(nn.Module):
             ro, None, c(near, b), c(far, b))
         return dict(rgb_map=rgb_map, feature_map=feat, sdf=sdf, mask=mask, xyz=xyz, z_vals=z)
 
+    def render_hierarchical(self, cam_poses, focal, near, far, styles, img_size=64, N_samples=24, N_importance=24,
+                            static_viewdirs=False, perturb=False, ray_offset=None, u=None, features_nchw=False):
+        """EXTENSION, off by default (the reference renders in one pass; BASELINE.json's north star asks for a
+        `sample_pdf` + fine pass): coarse pass (`render`, no grad) -> `Render.importance_depths` (c3d_sample_pdf: PDF from
+        the coarse compositing weights, N_importance new depths, ascending union) -> second pass over the N_samples +
+        N_importance merged depths with the same network (pi-GAN style; the point MLP is pointwise, so evaluating the
+        union equals merging the coarse and fine outputs).  The new depths are constants of the fine pass; gradients flow
+        through the fine pass to styles, parameters and -- through the rays -- to cam_poses / focal.
+        Returns the fine pass's dict of maps (`z_vals` = merged depths) with the coarse pass's dict under "coarse"."""
+        from .nerf_utils import Render
+        if N_samples + N_importance > 256:
+            raise ValueError("N_samples + N_importance must be <= 256")
+        b, n_rays, N2 = cam_poses.shape[0], img_size * img_size, N_samples + N_importance
+        c = lambda t, *s: t.to(torch.float32).reshape(*s).contiguous()
+        with torch.no_grad():
+            coarse = self.render(cam_poses, focal, near, far, styles, img_size=img_size, N_samples=N_samples,
+                                 static_viewdirs=static_viewdirs, perturb=perturb, ray_offset=ray_offset)
+        rays_o, rays_d, viewdirs = Render.get_rays_in_world(focal=focal, img_size=img_size, c2w=cam_poses,
+                                                            static_viewdirs=static_viewdirs)
+        rays_o, rays_d, viewdirs = (t.reshape(b, n_rays, 3) for t in (rays_o, rays_d, viewdirs))
+        geom_grad = torch.is_grad_enabled() and (cam_poses.requires_grad or focal.requires_grad)
+        imp = Render.importance_depths(coarse["z_vals"], N_importance, sdf=coarse["sdf"], rays_d=rays_d,
+                                       sigmoid_beta=self.sigmoid_beta, rays_o=rays_o, u=u, perturb=perturb,
+                                       return_pts=not geom_grad)
+        z = imp["z_merged"]
+        pts = Render.get_points(rays_o, rays_d, z) if geom_grad else imp["pts"]
+        meta = (b, n_rays, N2, 0, False, bool(features_nchw))
+        rgb_map, feat, sdf, mask, xyz, _ = self._run(
+            _abi.INPUT_POINTS, meta, c(styles, b, self.N_layers_renderer + 1, W), c(pts, b, n_rays, N2, 3),
+            c(rays_d, b, n_rays, 3), c(viewdirs, b, n_rays, 3), z, c(near, b), c(far, b))
+        return dict(rgb_map=rgb_map, feature_map=feat, sdf=sdf, mask=mask, xyz=xyz, z_vals=z, z_fine=imp["z_fine"],
+                    coarse=coarse)
+
     def mlp_init_pass(self, cam_poses, focals, img_size, near, far, styles, nerf_cfg):
         """Sphere-initialisation pass (volume_renderer.py:569-634): sdf of stratified samples (`offset_sampling=False`)
         and its target `|pts| - (far - near) / 4`; differentiable w.r.t. the renderer parameters (FP32-pipe backward)."""

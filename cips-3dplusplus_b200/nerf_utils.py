@@ -131,6 +131,65 @@ class Render:
         return rs(rgb_map), rs(feature_map), rs(xyz), rs(mask), None
 
 
+    @staticmethod
+    def importance_depths(z_vals, N_importance, weights=None, sdf=None, rays_d=None, sigmoid_beta=None, rays_o=None,
+                          u=None, perturb=False, return_pts=False):
+        """EXTENSION (no reference counterpart: the reference renders in one pass) -> c3d_sample_pdf (CUDA).
+
+        Canonical NeRF hierarchical sampling: PDF over the mid-points of the coarse depths from the interior
+        compositing weights, `N_importance` new depths by inverse-CDF sampling (`u`: draws in [0,1] of shape
+        (..., N_importance); None -> evenly spaced, or uniform random when `perturb`), and the ascending union.
+        The weights are either given (`weights`, (..., N)) or derived in-kernel from `sdf` (..., N[,1]), `rays_d` and
+        `sigmoid_beta` exactly as `volume_integration` derives them.  Nothing here is differentiable (the new depths
+        are constants of the fine pass, as in NeRF / pi-GAN).  Returns dict(z_fine, z_merged[, pts])."""
+        if z_vals.device.type != "cuda":
+            raise RuntimeError("Render.importance_depths needs CUDA tensors (no CPU fallback)")
+        lib = _abi.load()
+        lead, N, K, dev = z_vals.shape[:-1], z_vals.shape[-1], int(N_importance), z_vals.device
+        R = int(math.prod(lead))
+        f = dict(dtype=torch.float32, device=dev)
+        keep = {"z": _c(z_vals.detach(), R, N)}
+        P = _abi.ResampleParams()
+        P.n_rays, P.n_samples, P.n_importance = R, N, K
+        if weights is not None:
+            keep["w"] = _c(weights.detach(), R, N)
+            P.weights = keep["w"].data_ptr()
+        else:
+            if sdf is None or rays_d is None or sigmoid_beta is None:
+                raise ValueError("give either `weights`, or `sdf`, `rays_d` and `sigmoid_beta`")
+            keep["sdf"] = _c(sdf.detach(), R, N)
+            P.sdf = keep["sdf"].data_ptr()
+            if torch.is_tensor(sigmoid_beta):
+                keep["sb"] = _c(sigmoid_beta.detach(), 1)
+                P.sigmoid_beta_ptr = keep["sb"].data_ptr()
+            else:
+                P.sigmoid_beta = float(sigmoid_beta)
+        if rays_d is not None:
+            keep["d"] = _c(rays_d.detach(), R, 3)
+            P.rays_d = keep["d"].data_ptr()
+        if return_pts:
+            if rays_o is None or rays_d is None:
+                raise ValueError("return_pts needs rays_o and rays_d")
+            keep["o"] = _c(rays_o.detach().expand(*lead, 3), R, 3)
+            P.rays_o = keep["o"].data_ptr()
+        if u is None and perturb:
+            u = torch.rand(R, K, **f)
+        if u is not None:
+            keep["u"] = _c(u.detach(), R, K)
+            P.u = keep["u"].data_ptr()
+        P.z_vals = keep["z"].data_ptr()
+        z_fine, z_merged = torch.empty(R, K, **f), torch.empty(R, N + K, **f)
+        pts = torch.empty(R, N + K, 3, **f) if return_pts else None
+        P.z_fine, P.z_merged = z_fine.data_ptr(), z_merged.data_ptr()
+        P.pts_merged = None if pts is None else pts.data_ptr()
+        with torch.cuda.device(dev):
+            _abi.check(lib.c3d_sample_pdf(P, _stream()), "c3d_sample_pdf")
+        out = dict(z_fine=z_fine.reshape(*lead, K), z_merged=z_merged.reshape(*lead, N + K))
+        if pts is not None:
+            out["pts"] = pts.reshape(*lead, N + K, 3)
+        return out
+
+
 class Camera:
     @staticmethod
     def generate_camera_params(img_size, device, batch=1, locations=None, sweep=False, uniform=False,

@@ -11,6 +11,8 @@
  *   c3d_style_prep        FiLMSiren.gamma / .beta LinearLayers exp/cips3d/volume_renderer.py:66-67,77-81
  *   c3d_composite_forward Render.volume_integration            exp/cips3d/nerf_utils.py:230-338
  *   c3d_composite_backward autograd of volume_integration
+ *   c3d_sample_pdf        (extension, no reference counterpart: the reference renders in one pass; canonical NeRF
+ *                         hierarchical sampling for the weights of Render.volume_integration nerf_utils.py:267-307)
  *   c3d_pack_weights      (new) re-lays the reference state_dict (volume_renderer.py:107-115,183)
  *                         into the kernel's packed blob; re-derivable from the fp32 state dict
  *
@@ -32,7 +34,7 @@
 extern "C" {
 #endif
 
-#define C3D_ABI_VERSION 5
+#define C3D_ABI_VERSION 6
 #define C3D_MAX_LAYERS 16
 #define C3D_W 256
 
@@ -177,6 +179,27 @@ typedef struct c3d_composite_params {
   float* g_rgb; float* g_sdf; float* g_features; float* g_pts; float* g_rays_d; float* g_sigmoid_beta;
 } c3d_composite_params;
 
+/* EXTENSION (off by default; the reference has no importance resampling -- parity unpinned, oracle:
+ * oracle/nerf_oracle.py::importance_depths).  Per ray: PDF over the mid-points of the N coarse depths from the interior
+ * compositing weights (+1e-5), K new depths by inverse-CDF sampling, the ascending union of both and its points. */
+typedef struct c3d_resample_params {
+  int64_t n_rays;            /* total rays */
+  int32_t n_samples;         /* N coarse samples per ray, 3..256 */
+  int32_t n_importance;      /* K new samples per ray, 1..256 */
+  float sigmoid_beta;        /* used when weights == NULL and sigmoid_beta_ptr == NULL */
+  int32_t _pad;
+  const float* sigmoid_beta_ptr; /* device scalar or NULL */
+  const float* z_vals;       /* (n_rays,N) ascending coarse depths */
+  const float* weights;      /* (n_rays,N) compositing weights, or NULL: derived from sdf as volume_integration does */
+  const float* sdf;          /* (n_rays,N), used when weights == NULL */
+  const float* rays_d;       /* (n_rays,3): required when weights == NULL (|d| scales the spacing) or pts_merged != NULL */
+  const float* rays_o;       /* (n_rays,3): required when pts_merged != NULL */
+  const float* u;            /* (n_rays,K) draws in [0,1], or NULL: K evenly spaced values (eval / unperturbed) */
+  float* z_fine;             /* (n_rays,K) new depths in the order of u, or NULL */
+  float* z_merged;           /* (n_rays,N+K) ascending union, or NULL */
+  float* pts_merged;         /* (n_rays,N+K,3) rays_o + rays_d * z_merged, or NULL */
+} c3d_resample_params;
+
 int c3d_abi_version(void);
 const char* c3d_last_error(void);
 
@@ -201,6 +224,9 @@ int c3d_style_prep(const void* packed, int32_t D, const float* styles, int32_t b
                    float* view, c3d_stream_t stream);
 int c3d_composite_forward(const c3d_composite_params* p, c3d_stream_t stream);
 int c3d_composite_backward(const c3d_composite_params* p, c3d_stream_t stream);
+
+/* Inverse-CDF importance resampling; at least one output must be non-NULL.  One kernel launch. */
+int c3d_sample_pdf(const c3d_resample_params* p, c3d_stream_t stream);
 
 /* Launch statistics of the most recent c3d_nerf_forward on this thread (kernel launches it made). */
 int c3d_last_launch_count(void);
