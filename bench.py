@@ -176,6 +176,20 @@ def side_measurements(m, params, devt, D, N, dev, timed):
                                "frac": nbytes / (ms * 1e-3) / 1e9 / hbm, "rays": R, "ms": ms,
                                "bytes_per_ray": 1056 * N + 1152, "rays_per_s": R / (ms * 1e-3)}
     del rgb, sdf, feat, z, rd, pts
+    # (1b) importance resampling (EXTENSION, off in the headline path): c3d_sample_pdf on one step's rays, weights derived
+    # from the sdf, outputs z_fine + merged depths + fine-pass points; algorithmic bytes 8N + 24 + 4K + 16(N+K) per ray
+    Rr, K = 256 * IMG * IMG, N
+    zc = 0.88 + 0.24 * (torch.arange(N, device=dev)[None] + torch.rand(Rr, 1, device=dev, generator=g)) / N
+    sdf_c = (1.0 + 0.1 * torch.rand(Rr, 1, device=dev, generator=g) - zc) * 2.0
+    rd, ro = torch.randn(Rr, 3, device=dev, generator=g), torch.randn(Rr, 3, device=dev, generator=g)
+    ms, _, _ = timed(lambda: c3d.Render.importance_depths(zc, K, sdf=sdf_c, rays_d=rd, rays_o=ro, sigmoid_beta=beta,
+                                                          return_pts=True), 10, 3)
+    bpr = 8 * N + 24 + 4 * K + 16 * (N + K)
+    out["resample_kernel"] = {"bound": "hbm", "achieved": bpr * Rr / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                              "frac": bpr * Rr / (ms * 1e-3) / 1e9 / hbm, "rays": Rr, "ms": ms, "bytes_per_ray": bpr,
+                              "n_samples": N, "n_importance": K, "rays_per_s": Rr / (ms * 1e-3),
+                              "kernel": "sample_pdf_lane_kernel"}
+    del zc, sdf_c, rd, ro
     nb = min(8, devt[0].shape[0])
     tp = {k: torch.from_numpy(v).to(dev) for k, v in params.items()}
     a = [t[:nb] for t in devt]

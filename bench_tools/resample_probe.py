@@ -54,7 +54,7 @@ def main():
             print(json.dumps({"kernel": "sample_pdf_kernel", "case": name, "rays": Rn, "N": N, "K": K, "ms": round(med, 4),
                               "ms_min": round(mn, 4), "bytes_per_ray": bpr, "GBps": round(bpr * Rn / med / 1e6, 1),
                               "frac_hbm": round(bpr * Rn / med / 1e6 / peak, 3), "rays_per_s": round(Rn / med * 1e3),
-                              "rb": os.environ.get("C3D_RESAMPLE_RB", "auto")}), flush=True)
+                              "variant": os.environ.get("C3D_RESAMPLE", "auto")}), flush=True)
     if a.render:
         for D, b in ((8, 256), (2, 256)):
             m = c3d.NerfBranch(D, precision="bf16").to(dev).eval().requires_grad_(False)

@@ -430,6 +430,30 @@ int c3d_sample_pdf(const c3d_resample_params* p, c3d_stream_t stream) {
   if (q.weights) q.sdf = nullptr;
   if (!q.pts_merged) q.rays_o = nullptr;
   if (q.weights && !q.pts_merged) q.rays_d = nullptr;
+  // lanes = rays when 128 (or 64) rays' working sets fit shared memory twice per SM, else lanes = samples
+  // (C3D_RESAMPLE=warp|lane forces one of them for A/B runs)
+  {
+    const char* e = getenv("C3D_RESAMPLE");
+    const bool force_warp = e && strcmp(e, "warp") == 0;
+    for (int tpb = 128; tpb >= 64 && !force_warp; tpb >>= 1) {
+      const resample::LaneLayout LL = resample::make_lane_layout(q.n_samples, q.n_importance, q.pts_merged != nullptr, tpb);
+      const size_t smem = (size_t)LL.total * sizeof(float);
+      if (smem > 110 * 1024) continue;
+      const long long blocks = (q.n_rays + tpb - 1) / tpb;
+      C3D_CHECK_ARG(blocks < (1ll << 31), "too many rays");
+      cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+      if (tpb == 128) {
+        C3D_CUDA(cudaFuncSetAttribute(resample::sample_pdf_lane_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        resample::sample_pdf_lane_kernel<128><<<(unsigned)blocks, 128, smem, st>>>(q, LL);
+      } else {
+        C3D_CUDA(cudaFuncSetAttribute(resample::sample_pdf_lane_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        resample::sample_pdf_lane_kernel<64><<<(unsigned)blocks, 64, smem, st>>>(q, LL);
+      }
+      C3D_LAUNCH_CHECK();
+      return C3D_OK;
+    }
+    C3D_CHECK_ARG(!(e && strcmp(e, "lane") == 0), "C3D_RESAMPLE=lane: the working set does not fit shared memory");
+  }
   static int rb_env = -1;
   if (rb_env < 0) { const char* e = getenv("C3D_RESAMPLE_RB"); rb_env = e ? atoi(e) : 0; }
   C3D_CHECK_ARG(rb_env % 4 == 0, "C3D_RESAMPLE_RB must be a multiple of 4");

@@ -254,5 +254,212 @@ __global__ void __launch_bounds__(THREADS) sample_pdf_kernel(c3d_resample_params
   if (threadIdx.x == 0) ptx::bulk_wait_group0();
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Lane-per-ray variant (default when a ray's working set is small, e.g. the N = K = 24 configuration): with 24 samples
+// a warp-per-ray scan leaves lanes idle and pays the shuffle / control overhead once per ray; here a thread owns a ray
+// and runs the prefix product, the CDF, a fixed-length binary search and an in-place backward merge serially in shared memory (~4x fewer issued
+// instructions per ray).  Rows are staged in shared memory with an ODD stride, so the 32 rays of a warp hit 32
+// different banks; global traffic stays fully coalesced: the block's input / output spans are contiguous and are moved
+// by flat 16-byte / 4-byte accesses, with (row, column) recovered by a multiply-high division.
+// Summation order here is the reference's own (sequential cumprod / cumsum).
+// ------------------------------------------------------------------------------------------
+struct LaneLayout {
+  int TPB;                      // rays (= threads) per block
+  int Sz, Sk, Sm;               // odd row strides (floats) of the weight / CDF, new-depth and depth (merged) rows
+  int zm, w, fine, geom, total;
+  uint32_t magN, magK, magNK;   // ceil(2^32 / d): e / d == __umulhi(e, mag) for the e < 2^17 used here
+};
+__host__ inline LaneLayout make_lane_layout(int N, int K, bool want_pts, int tpb) {
+  LaneLayout L;
+  L.TPB = tpb;
+  L.Sz = N | 1; L.Sk = K | 1; L.Sm = (N + K) | 1;
+  int o = 0;
+  L.zm = o;     o += tpb * L.Sm;            // coarse depths in the first N slots; the union is merged in place from the back
+  L.w = o;      o += tpb * L.Sz;
+  L.fine = o;   o += tpb * L.Sk;
+  L.geom = o;   o += want_pts ? tpb * 6 : 0;
+  L.total = o;
+  auto mag = [](int d) { return (uint32_t)((0x100000000ull + (uint64_t)d - 1) / (uint64_t)d); };
+  L.magN = mag(N); L.magK = mag(K); L.magNK = mag(N + K);
+  return L;
+}
+
+// branch-free upper bound with a trip count that depends on n only: number of a[0..n) <= x
+__device__ __forceinline__ int count_le_fixed(const float* __restrict__ a, int n, float x) {
+  int base = 0, len = n;
+  while (len > 1) {
+    const int half = len >> 1;
+    base += a[base + half - 1] <= x ? half : 0;
+    len -= half;
+  }
+  return base + (a[base] <= x ? 1 : 0);
+}
+
+template <int TPB>
+__global__ void __launch_bounds__(TPB) sample_pdf_lane_kernel(c3d_resample_params p, LaneLayout L) {
+  extern __shared__ __align__(128) float smem[];
+  const int tid = threadIdx.x;
+  const int N = p.n_samples, K = p.n_importance, NK = N + K, M = N - 1;
+  const long long r0 = (long long)blockIdx.x * TPB;
+  const int nr = (int)((p.n_rays - r0) < TPB ? (p.n_rays - r0) : TPB);
+  const bool from_sdf = p.weights == nullptr;
+  const bool want_union = p.z_merged != nullptr || p.pts_merged != nullptr;
+  const float* gw = (from_sdf ? p.sdf : p.weights) + r0 * N;
+  const float* gz = p.z_vals + r0 * N;
+
+  // ---- stage the block's rows: flat coalesced reads, scattered into odd-stride rows
+  {
+    const int n_in = nr * N;
+    const int n4 = n_in >> 2;                                  // the span starts 16-byte aligned (r0 * N * 4, TPB % 4 == 0)
+    const float4* gz4 = reinterpret_cast<const float4*>(gz);
+    const float4* gw4 = reinterpret_cast<const float4*>(gw);
+    for (int i = tid; i < n4; i += TPB) {
+      const float4 a = __ldcs(gz4 + i), b = __ldcs(gw4 + i);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      int row = (int)__umulhi((uint32_t)(4 * i), L.magN), col = 4 * i - row * N;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        smem[L.zm + row * L.Sm + col] = av[c];
+        smem[L.w + row * L.Sz + col] = bv[c];
+        if (++col == N) { col = 0; ++row; }
+      }
+    }
+    for (int e = 4 * n4 + tid; e < n_in; e += TPB) {
+      const int row = (int)__umulhi((uint32_t)e, L.magN), col = e - row * N;
+      smem[L.zm + row * L.Sm + col] = gz[e];
+      smem[L.w + row * L.Sz + col] = gw[e];
+    }
+    if (p.u) {                                                   // draws land in the rows the samples will replace
+      const float* gu = p.u + r0 * K;
+      for (int e = tid; e < nr * K; e += TPB) {
+        const int row = (int)__umulhi((uint32_t)e, L.magK), col = e - row * K;
+        smem[L.fine + row * L.Sk + col] = __ldcs(gu + e);
+      }
+    }
+    if (p.pts_merged)
+      for (int e = tid; e < nr * 3; e += TPB) {
+        const int row = e / 3, c = e - 3 * row;
+        smem[L.geom + row * 6 + c] = p.rays_o[r0 * 3 + e];
+        smem[L.geom + row * 6 + 3 + c] = p.rays_d[r0 * 3 + e];
+      }
+  }
+  __syncthreads();
+
+  float* __restrict__ zr = smem + L.zm + tid * L.Sm;           // z[0..N), later the merged union [0..N+K)
+  float* __restrict__ wr = smem + L.w + tid * L.Sz;            // weights, then cdf[j] in wr[j]
+  float* __restrict__ fr = smem + L.fine + tid * L.Sk;         // u_j (when given) until sample j replaces it
+  bool sorted = true;
+  if (tid < nr) {
+    // ---- compositing weights from the sdf (nerf_utils.py:267-307): sequential cumprod, the reference's order
+    if (from_sdf) {
+      const float beta = p.sigmoid_beta_ptr ? *p.sigmoid_beta_ptr : p.sigmoid_beta;
+      const float inv_beta = 1.0f / beta;
+      const float* d = p.rays_d + (r0 + tid) * 3;
+      const float dnorm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      float T = 1.0f, znext = zr[0];
+#pragma unroll 4
+      for (int k = 0; k < N; ++k) {
+        const float zk = znext;
+        znext = k + 1 < N ? zr[k + 1] : 0.f;
+        const float dist = (k + 1 < N ? znext - zk : 1e10f) * dnorm;
+        const float alpha = alpha_from_sdf<true>(wr[k], inv_beta, dist);
+        wr[k] = alpha * T;
+        T *= 1.0f - alpha + 1e-10f;
+      }
+    }
+    // ---- PDF of the interior weights (+1e-5), CDF with a leading zero written over the weights
+    float wsum = 0.f;
+    for (int j = 1; j <= N - 2; ++j) wsum += wr[j] + 1e-5f;
+    float c = 0.f;
+    wr[0] = 0.f;
+#pragma unroll 4
+    for (int j = 1; j <= N - 2; ++j) { c += (wr[j] + 1e-5f) / wsum; wr[j] = c; }
+    // ---- inverse CDF: searchsorted(cdf, u, right=True) with a fixed trip count, linear interpolation in the bin
+    const bool has_u = p.u != nullptr;
+    const float ustep = K > 1 ? 1.0f / (float)(K - 1) : 0.f;
+    float prev = -1e30f;
+#pragma unroll 2
+    for (int j = 0; j < K; ++j) {
+      const float uj = has_u ? fr[j] : (j == K - 1 && K > 1 ? 1.0f : (float)j * ustep);
+      const int inds = count_le_fixed(wr, M, uj);
+      const int below = inds - 1 > 0 ? inds - 1 : 0;
+      const int above = inds < M - 1 ? inds : M - 1;
+      const float cb = wr[below], ca = wr[above];
+      const float bb = 0.5f * (zr[below + 1] + zr[below]), ba = 0.5f * (zr[above + 1] + zr[above]);
+      float denom = ca - cb;
+      denom = denom < 1e-5f ? 1.0f : denom;
+      const float v = bb + ((uj - cb) / denom) * (ba - bb);
+      fr[j] = v;
+      sorted = sorted && (prev <= v);
+      prev = v;
+    }
+  }
+  // Draws in arbitrary order give new depths in arbitrary order: z_fine keeps that order (written out first), then the
+  // ray's new depths are sorted in place for the merge.  Block-uniform decision, the common (ascending) case skips it.
+  bool fine_stored = false;
+  if (want_union && __syncthreads_or(tid < nr && !sorted)) {
+    if (p.z_fine) {
+      float* out = p.z_fine + r0 * K;
+      for (int e = tid; e < nr * K; e += TPB) {
+        const int row = (int)__umulhi((uint32_t)e, L.magK), col = e - row * K;
+        __stcs(out + e, smem[L.fine + row * L.Sk + col]);
+      }
+      fine_stored = true;
+      __syncthreads();
+    }
+    if (tid < nr && !sorted)
+      for (int j = 1; j < K; ++j) {                              // insertion sort of one small row
+        const float v = fr[j];
+        int i = j - 1;
+        while (i >= 0 && fr[i] > v) { fr[i + 1] = fr[i]; --i; }
+        fr[i + 1] = v;
+      }
+  }
+  // ---- ascending union, merged from the back into the depth row (ties: coarse first, i.e. new depth taken first here)
+  if (want_union && tid < nr) {
+    const float NEG = -3.0e38f;
+    int i = N - 1, j = K - 1;
+    float zi = zr[i], fj = fr[j];
+    for (int o = NK - 1; o >= 0; --o) {
+      const bool tf = fj >= zi;
+      zr[o] = tf ? fj : zi;
+      j -= tf ? 1 : 0;
+      i -= tf ? 0 : 1;
+      const float fn = fr[j > 0 ? j : 0], zn = zr[i > 0 ? i : 0];
+      fj = tf ? (j >= 0 ? fn : NEG) : fj;
+      zi = tf ? zi : (i >= 0 ? zn : NEG);
+    }
+  }
+  __syncthreads();
+
+  // ---- flat coalesced writes of the block's output spans
+  if (p.z_fine && !fine_stored) {
+    float* out = p.z_fine + r0 * K;
+    for (int e = tid; e < nr * K; e += TPB) {
+      const int row = (int)__umulhi((uint32_t)e, L.magK), col = e - row * K;
+      __stcs(out + e, smem[L.fine + row * L.Sk + col]);
+    }
+  }
+  if (p.z_merged) {
+    float* out = p.z_merged + r0 * NK;
+    for (int e = tid; e < nr * NK; e += TPB) {
+      const int row = (int)__umulhi((uint32_t)e, L.magNK), col = e - row * NK;
+      __stcs(out + e, smem[L.zm + row * L.Sm + col]);
+    }
+  }
+  if (p.pts_merged) {
+    float* out = p.pts_merged + r0 * NK * 3;
+    for (int e = tid; e < nr * NK; e += TPB) {                 // one point per thread: 12 contiguous bytes
+      const int row = (int)__umulhi((uint32_t)e, L.magNK), col = e - row * NK;
+      const float zv = smem[L.zm + row * L.Sm + col];
+      const float* g = smem + L.geom + row * 6;
+      __stcs(out + 3 * e + 0, fmaf(g[3], zv, g[0]));
+      __stcs(out + 3 * e + 1, fmaf(g[4], zv, g[1]));
+      __stcs(out + 3 * e + 2, fmaf(g[5], zv, g[2]));
+    }
+  }
+}
+
 }  // namespace resample
 }  // namespace c3d

@@ -41,8 +41,12 @@ SHAPES = [(1, 24, 24), (7, 24, 24), (64, 24, 24), (1000, 24, 24), (4099, 24, 24)
 
 @pytest.mark.parametrize("R,N,K", SHAPES)
 @pytest.mark.parametrize("u_mode", ["det", "sorted", "random"])
-def test_sample_pdf_given_weights(R, N, K, u_mode):
+@pytest.mark.parametrize("variant", ["auto", "warp"])
+def test_sample_pdf_given_weights(R, N, K, u_mode, variant, monkeypatch):
+    """Both kernels: lanes = rays (the default whenever the rows of 64+ rays fit shared memory) and lanes = samples."""
     import cips3dpp_b200 as c3d
+    if variant != "auto":
+        monkeypatch.setenv("C3D_RESAMPLE", variant)
     z, w = make_rays(R, N, seed=R + N + K, peaked=(R % 2 == 0))
     rng = np.random.default_rng(K)
     u = None
@@ -64,9 +68,12 @@ def test_sample_pdf_given_weights(R, N, K, u_mode):
 
 
 @pytest.mark.parametrize("R,N,K", [(500, 24, 24), (101, 128, 64), (64, 40, 216)])
-def test_sample_pdf_weights_from_sdf(R, N, K):
+@pytest.mark.parametrize("variant", ["auto", "warp"])
+def test_sample_pdf_weights_from_sdf(R, N, K, variant, monkeypatch):
     """weights == NULL: the kernel derives w = alpha * T from the sdf exactly as volume_integration does."""
     import cips3dpp_b200 as c3d
+    if variant != "auto":
+        monkeypatch.setenv("C3D_RESAMPLE", variant)
     rng = np.random.default_rng(R)
     z, _ = make_rays(R, N, seed=R)
     # a surface crossing somewhere along the ray (sdf changes sign), or none
