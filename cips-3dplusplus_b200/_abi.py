@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("C3D_LIB") or os.path.join(HERE, "libc3dpp.so")   # C3D_LIB: A/B builds (bench_tools)
 SRC = os.path.join(HERE, "csrc", "c3d_abi.cu")
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_LAYERS = 16
 MODE_FP32, MODE_BF16 = 0, 1
 INPUT_POSES, INPUT_POINTS = 0, 1
@@ -50,7 +50,8 @@ class FwdParams(C.Structure):
 class BwdParams(C.Structure):
     _fields_ = [("fwd", FwdParams)] + \
         [(n, _fp) for n in ("g_rgb_map", "g_feature_map", "g_mask", "g_xyz", "g_sdf",
-                            "g_styles", "g_pts", "g_rays_d", "g_viewdirs", "g_cam_poses", "g_focal", "g_params")]
+                            "g_styles", "g_pts", "g_rays_d", "g_viewdirs", "g_cam_poses", "g_focal", "g_params")] + \
+        [("fwd_saved", C.c_int32), ("_pad", C.c_int32)]
 
 
 class RaygenParams(C.Structure):
@@ -84,6 +85,7 @@ EXPORTS = {
     "c3d_nerf_forward": (C.c_int, [C.POINTER(FwdParams), _fp]),
     "c3d_backward_workspace_bytes": (C.c_size_t, [C.POINTER(BwdParams)]),
     "c3d_nerf_backward": (C.c_int, [C.POINTER(BwdParams), _fp]),
+    "c3d_nerf_forward_save": (C.c_int, [C.POINTER(BwdParams), _fp]),
     "c3d_eikonal_workspace_bytes": (C.c_size_t, [C.POINTER(BwdParams)]),
     "c3d_eikonal_backward": (C.c_int, [C.POINTER(BwdParams), _fp, _fp]),
     "c3d_raygen": (C.c_int, [C.POINTER(RaygenParams), _fp]),

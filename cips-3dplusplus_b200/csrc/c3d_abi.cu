@@ -605,7 +605,7 @@ static BwdTcWs bwd_tc_ws(const c3d_bwd_params* bp) {
                          (poses ? P * 16 + R * 24 : 0) + 8192;
   size_t ci = ((size_t)4 << 30) / per_img;
   if (ci < 1) ci = 1;
-  if (ci > b) ci = b;
+  if (ci > b || bp->fwd_saved) ci = b;          // saved forward: the whole batch is one chunk that lives until the backward
   w.chunk_imgs = (int)ci;
   size_t c = 0;
   auto take = [&](size_t bytes) { const size_t at = c; c += align_up(bytes, 256); return at; };
@@ -659,18 +659,23 @@ extern "C" {
 
 size_t c3d_backward_workspace_bytes(const c3d_bwd_params* p) {
   if (!p || p->fwd.batch < 1 || p->fwd.n_rays < 1 || p->fwd.n_samples < 1 || p->fwd.D < 1) return 0;
+  if (p->fwd_saved && !bwd_uses_tensor_path(p)) return 0;       // saved forward: tensor-core path only
   return bwd_uses_tensor_path(p) ? bwd_tc_ws(p).total : bwd_ws(p).total;
 }
 
 static int backward_simt(const c3d_bwd_params* bp, cudaStream_t st);
-static int backward_tc(const c3d_bwd_params* bp, cudaStream_t st);
+static int backward_tc(const c3d_bwd_params* bp, cudaStream_t st, int phases);
 
 int c3d_nerf_backward(const c3d_bwd_params* bp, c3d_stream_t stream) {
   g_launches = 0;
   int rc = validate_bwd(bp);
   if (rc != C3D_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return bwd_uses_tensor_path(bp) ? backward_tc(bp, st) : backward_simt(bp, st);
+  if (bp->fwd_saved) {
+    C3D_CHECK_ARG(bp->fwd_saved == 1 && bwd_uses_tensor_path(bp), "fwd_saved is only valid on the tensor-core backward path");
+    return backward_tc(bp, st, 2);
+  }
+  return bwd_uses_tensor_path(bp) ? backward_tc(bp, st, 3) : backward_simt(bp, st);
 }
 
 static int backward_simt(const c3d_bwd_params* bp, cudaStream_t st) {
@@ -824,7 +829,10 @@ static int backward_simt(const c3d_bwd_params* bp, cudaStream_t st) {
   return C3D_OK;
 }
 
-static int backward_tc(const c3d_bwd_params* bp, cudaStream_t st) {
+// phases: 1 = forward half (style tables, rays, save-mode forward), 2 = backward half, 3 = both per chunk (recompute).
+// With bp->fwd_saved the workspace holds the whole batch as one chunk: c3d_nerf_forward_save runs phase 1 writing the
+// caller's output tensors, c3d_nerf_backward then runs phase 2 on the tiles that forward left in the workspace.
+static int backward_tc(const c3d_bwd_params* bp, cudaStream_t st, int phases) {
   int rc;
   const c3d_fwd_params* p = &bp->fwd;
   const BwdTcWs w = bwd_tc_ws(bp);
@@ -834,14 +842,17 @@ static int backward_tc(const c3d_bwd_params* bp, cudaStream_t st) {
   const int D = p->D;
   const PackedLayout L = packed_layout(D);
   const bool poses = p->input_kind == C3D_INPUT_POSES;
+  const bool user_out = bp->fwd_saved && (phases & 1);       // the forward half produces the caller's outputs
   float2* film = reinterpret_cast<float2*>(ws + w.film);
   float4* first = reinterpret_cast<float4*>(ws + w.first);
   float4* view = reinterpret_cast<float4*>(ws + w.view);
   float* g_film = reinterpret_cast<float*>(ws + w.g_film);
-  rc = launch_style_prep(p->packed, D, p->styles, p->batch, reinterpret_cast<float*>(film), reinterpret_cast<float*>(first),
-                         reinterpret_cast<float*>(view), st);
-  if (rc != C3D_OK) return rc;
-  C3D_CUDA(cudaMemsetAsync(g_film, 0, (size_t)p->batch * (D + 1) * W * sizeof(float2), st));
+  if (phases & 1) {
+    rc = launch_style_prep(p->packed, D, p->styles, p->batch, reinterpret_cast<float*>(film), reinterpret_cast<float*>(first),
+                           reinterpret_cast<float*>(view), st);
+    if (rc != C3D_OK) return rc;
+  }
+  if (phases & 2) C3D_CUDA(cudaMemsetAsync(g_film, 0, (size_t)p->batch * (D + 1) * W * sizeof(float2), st));
   const float* beta_ptr = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p->packed) + L.scal) + 4;
   for (int i0 = 0; i0 < p->batch; i0 += w.chunk_imgs) {
     const int ni = (p->batch - i0 < w.chunk_imgs) ? p->batch - i0 : w.chunk_imgs;
@@ -856,31 +867,50 @@ static int backward_tc(const c3d_bwd_params* bp, cudaStream_t st) {
       rg.ray_offset = p->ray_offset ? p->ray_offset + (size_t)i0 * R : nullptr;
       rg.pts = reinterpret_cast<float*>(ck + w.c_pts); rg.rays_d = reinterpret_cast<float*>(ck + w.c_rd);
       rg.viewdirs = reinterpret_cast<float*>(ck + w.c_vd); rg.z_vals = reinterpret_cast<float*>(ck + w.c_z);
-      const long long n = (long long)ni * R;
-      raygen_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(rg);
-      C3D_LAUNCH_CHECK();
+      if (phases & 1) {
+        const long long n = (long long)ni * R;
+        raygen_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(rg);
+        C3D_LAUNCH_CHECK();
+      }
       q.pts = rg.pts; q.rays_d = rg.rays_d; q.viewdirs = rg.viewdirs; q.z_vals = rg.z_vals;
     } else {
       q.pts = p->pts + (size_t)i0 * P * 3; q.rays_d = p->rays_d + (size_t)i0 * R * 3;
       q.viewdirs = p->viewdirs + (size_t)i0 * R * 3; q.z_vals = p->z_vals + (size_t)i0 * P;
     }
-    q.rgb_map = reinterpret_cast<float*>(ck + w.c_orgb); q.feature_map = reinterpret_cast<float*>(ck + w.c_ofeat);
-    q.mask = reinterpret_cast<float*>(ck + w.c_omask); q.xyz = reinterpret_cast<float*>(ck + w.c_oxyz);
+    const bool nchw = p->feat_layout == C3D_FEAT_NCHW;
+    q.feat_layout = C3D_FEAT_NHWC;
+    q.rgb_map = user_out ? p->rgb_map : reinterpret_cast<float*>(ck + w.c_orgb);
+    q.feature_map = (user_out && !nchw) ? p->feature_map : reinterpret_cast<float*>(ck + w.c_ofeat);
+    q.mask = user_out ? p->mask : reinterpret_cast<float*>(ck + w.c_omask);
+    q.xyz = user_out ? p->xyz : reinterpret_cast<float*>(ck + w.c_oxyz);
     q.sdf = reinterpret_cast<float*>(ck + w.c_sdfpt); q.z_vals_out = nullptr;
     float* g_pts = (!poses && bp->g_pts) ? bp->g_pts + (size_t)i0 * P * 3 : reinterpret_cast<float*>(ck + w.c_gpts);
     float* g_rd = (!poses && bp->g_rays_d) ? bp->g_rays_d + (size_t)i0 * R * 3 : reinterpret_cast<float*>(ck + w.c_grd);
     float* g_vd = (!poses && bp->g_viewdirs) ? bp->g_viewdirs + (size_t)i0 * R * 3 : reinterpret_cast<float*>(ck + w.c_gvd);
-    C3D_CUDA(cudaMemsetAsync(g_vd, 0, (size_t)ni * R * 12, st));
     const float* gF = bp->g_feature_map ? bp->g_feature_map + (size_t)i0 * R * W : nullptr;
-    // 1. forward on the tensor cores, keeping bf16 acc / cos tiles per layer and per-point rgb / weights
     fused::Args a;
     fused_fill_args(a, &q, film + (size_t)i0 * (D + 1) * W, first + (size_t)i0 * W, view + (size_t)i0 * W);
     a.save_acc = reinterpret_cast<__nv_bfloat16*>(ck + w.c_acc); a.save_cos = reinterpret_cast<__nv_bfloat16*>(ck + w.c_cos);
     a.save_feat = reinterpret_cast<__nv_bfloat16*>(ck + w.c_feat);
     a.rgb_pt = reinterpret_cast<float*>(ck + w.c_rgbpt); a.w_pt = reinterpret_cast<float*>(ck + w.c_wpt);
     a.g_feature_map = gF;
-    rc = fused_launch(a, 1, st);
-    if (rc != C3D_OK) return rc;
+    if (phases & 1) {
+      // 1. forward on the tensor cores, keeping bf16 acc / cos tiles per layer and per-point rgb / weights
+      rc = fused_launch(a, 1, st);
+      if (rc != C3D_OK) return rc;
+      if (user_out) {                               // single chunk (i0 == 0): hand the remaining outputs to the caller
+        C3D_CUDA(cudaMemcpyAsync(p->sdf, q.sdf, (size_t)ni * P * 4, cudaMemcpyDeviceToDevice, st));
+        if (poses && p->z_vals_out)
+          C3D_CUDA(cudaMemcpyAsync(p->z_vals_out, q.z_vals, (size_t)ni * P * 4, cudaMemcpyDeviceToDevice, st));
+        if (nchw) {
+          dim3 grid((unsigned)((p->n_rays + 31) / 32), W / 32, (unsigned)ni);
+          nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, st>>>(q.feature_map, p->feature_map, p->n_rays);
+          C3D_LAUNCH_CHECK();
+        }
+      }
+    }
+    if (!(phases & 2)) continue;
+    C3D_CUDA(cudaMemsetAsync(g_vd, 0, (size_t)ni * R * 12, st));
     // 2. d(volume_integration): needs g_feature_map . feat per point
     float* gdot = reinterpret_cast<float*>(ck + w.c_gdot);
     if (gF) {
@@ -914,11 +944,29 @@ static int backward_tc(const c3d_bwd_params* bp, cudaStream_t st) {
       C3D_LAUNCH_CHECK();
     }
   }
-  if (bp->g_styles) {
+  if ((phases & 2) && bp->g_styles) {
     film_bwd_kernel<<<dim3(D + 1, p->batch), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(p->packed), L, g_film, bp->g_styles);
     C3D_LAUNCH_CHECK();
   }
   return C3D_OK;
+}
+
+int c3d_nerf_forward_save(const c3d_bwd_params* bp, c3d_stream_t stream) {
+  g_launches = 0;
+  C3D_CHECK_ARG(bp && bp->fwd_saved == 1, "c3d_nerf_forward_save needs fwd_saved == 1");
+  C3D_CHECK_ARG(bwd_uses_tensor_path(bp), "the saved-forward path exists for the tensor-core backward only "
+                                          "(bf16 mode, n_samples >= 8, no parameter gradients)");
+  const c3d_fwd_params* p = &bp->fwd;
+  C3D_CHECK_ARG(p->rgb_map && p->feature_map && p->sdf && p->mask && p->xyz, "all five output pointers are required");
+  C3D_CHECK_ARG(aligned16(p->rgb_map) && aligned16(p->feature_map) && aligned16(p->sdf) && aligned16(p->mask) &&
+                aligned16(p->xyz) && aligned16(p->z_vals_out), "output pointers must be 16-byte aligned");
+  const int layout = p->feat_layout;
+  C3D_CHECK_ARG(layout == C3D_FEAT_NHWC || layout == C3D_FEAT_NCHW, "bad feat_layout %d", layout);
+  c3d_bwd_params b = *bp;                      // validate_bwd checks the backward's own (NHWC cotangent) convention
+  b.fwd.feat_layout = C3D_FEAT_NHWC;
+  int rc = validate_bwd(&b);
+  if (rc != C3D_OK) return rc;
+  return backward_tc(bp, reinterpret_cast<cudaStream_t>(stream), 1);
 }
 
 }  // extern "C" (helpers above are static)

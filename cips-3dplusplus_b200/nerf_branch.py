@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -79,7 +80,14 @@ class _NerfFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, kind, meta, styles, a0, a1, a2, a3, near, far, *params):
         # kind POINTS: a0..a3 = pts, rays_d, viewdirs, z_vals ; kind POSES: a0, a1, a2 = cam_poses, focal, ray_offset
-        outs = module._launch_forward(kind, meta, styles, a0, a1, a2, a3, near, far)
+        # A step that will be differentiated runs the save-mode forward once and keeps its workspace for the backward
+        # (no recomputation) when that fits the memory budget; otherwise plain forward + chunked recomputation.
+        saved = None if any(p.requires_grad for p in params) else \
+            module._launch_forward_save(kind, meta, styles, a0, a1, a2, a3, near, far)
+        if saved is not None:
+            outs, ctx.saved_ws = saved
+        else:
+            outs, ctx.saved_ws = module._launch_forward(kind, meta, styles, a0, a1, a2, a3, near, far), None
         ctx.module, ctx.kind, ctx.meta = module, kind, meta
         ctx.save_for_backward(styles, a0, a1, a2 if a2 is not None else styles.new_empty(0),
                               a3 if a3 is not None else styles.new_empty(0), near, far)
@@ -93,7 +101,8 @@ class _NerfFn(torch.autograd.Function):
         a2 = a2 if ctx.has[0] else None
         a3 = a3 if ctx.has[1] else None
         grads = ctx.module._launch_backward(ctx.kind, ctx.meta, styles, a0, a1, a2, a3, near, far,
-                                            g_rgb, g_feat, g_sdf, g_mask, g_xyz, ctx.needs_input_grad)
+                                            g_rgb, g_feat, g_sdf, g_mask, g_xyz, ctx.needs_input_grad,
+                                            saved_ws=ctx.saved_ws)
         return (None, None, None) + grads
 
 
@@ -252,8 +261,43 @@ class NerfBranch(nn.Module):
         self.last_launch_count = lib.c3d_last_launch_count()
         return rgb_map, feat, sdf, mask, xyz, z_out
 
+    def _launch_forward_save(self, kind, meta, styles, a0, a1, a2, a3, near, far):
+        """c3d_nerf_forward_save: the forward of a differentiated step, run once in save mode.  Returns (outputs, workspace)
+        or None when the path does not apply (fp32 mode, n_samples < 8, C3D_BWD=simt) or the whole-batch workspace exceeds
+        the budget `C3D_SAVE_FWD_GB` (default 48 GiB of the 180 GB; 0 disables)."""
+        if self.precision != "bf16":
+            return None
+        budget = float(os.environ.get("C3D_SAVE_FWD_GB", "48")) * (1 << 30)
+        if budget <= 0:
+            return None
+        lib = _abi.load()
+        b, n_rays, N, img_size, static_viewdirs, nchw = meta
+        dev = styles.device
+        B = _abi.BwdParams()
+        self._fill_common(B.fwd, kind, meta, styles, a0, a1, a2, a3, near, far)
+        B.fwd_saved = 1
+        nws = lib.c3d_backward_workspace_bytes(B)
+        if nws == 0 or nws > budget:
+            return None
+        f = dict(dtype=torch.float32, device=dev)
+        rgb_map = torch.empty(b, n_rays, 3, **f)
+        feat = torch.empty((b, W, n_rays) if nchw else (b, n_rays, W), **f)
+        sdf = torch.empty(b, n_rays, N, 1, **f)
+        mask = torch.empty(b, n_rays, 2, **f)
+        xyz = torch.empty(b, n_rays, 3, **f)
+        z_out = torch.empty(b, n_rays, N, **f) if kind == _abi.INPUT_POSES else None
+        P = B.fwd
+        P.rgb_map, P.feature_map, P.sdf, P.mask, P.xyz = (t.data_ptr() for t in (rgb_map, feat, sdf, mask, xyz))
+        P.z_vals_out = z_out.data_ptr() if z_out is not None else None
+        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        P.workspace, P.workspace_bytes = ws.data_ptr(), nws
+        with torch.cuda.device(dev):
+            _abi.check(lib.c3d_nerf_forward_save(B, torch.cuda.current_stream().cuda_stream), "c3d_nerf_forward_save")
+        self.last_launch_count = lib.c3d_last_launch_count()
+        return (rgb_map, feat, sdf, mask, xyz, z_out), ws
+
     def _launch_backward(self, kind, meta, styles, a0, a1, a2, a3, near, far, g_rgb, g_feat, g_sdf, g_mask, g_xyz,
-                         needs):
+                         needs, saved_ws=None):
         """c3d_nerf_backward: recomputes the forward in fp32 and returns gradients for styles and the geometric
         inputs (POINTS: pts, rays_d, viewdirs; POSES: cam_poses, focal)."""
         lib = _abi.load()
@@ -289,8 +333,12 @@ class NerfBranch(nn.Module):
             pg = _abi.ParamGrads()
             self._fill_param_struct(pg, g_params)
             B.g_params = C.cast(C.pointer(pg), C.c_void_p)
-        nws = lib.c3d_backward_workspace_bytes(B)
-        ws = torch.empty(max(nws, 16), dtype=torch.uint8, device=dev)
+        if saved_ws is not None:                                     # tiles left by c3d_nerf_forward_save: no recomputation
+            B.fwd_saved = 1
+            nws, ws = saved_ws.numel(), saved_ws
+        else:
+            nws = lib.c3d_backward_workspace_bytes(B)
+            ws = torch.empty(max(nws, 16), dtype=torch.uint8, device=dev)
         B.fwd.workspace, B.fwd.workspace_bytes = ws.data_ptr(), nws
         with torch.cuda.device(dev):
             _abi.check(lib.c3d_nerf_backward(B, torch.cuda.current_stream().cuda_stream), "c3d_nerf_backward")

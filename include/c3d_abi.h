@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define C3D_ABI_VERSION 6
+#define C3D_ABI_VERSION 7
 #define C3D_MAX_LAYERS 16
 #define C3D_W 256
 
@@ -141,6 +141,11 @@ typedef struct c3d_bwd_params {
   float* g_focal;            /* POSES: (batch) */
   const c3d_param_grads* g_params; /* HOST pointer or NULL: also return the gradients of the renderer's parameters
                                       (training; runs the FP32-pipe backward in either mode) */
+  int32_t fwd_saved;         /* 0: the backward recomputes the forward in chunks of <= 4 GiB of workspace (default).
+                                1: the workspace holds the whole batch; c3d_nerf_forward_save filled it (and produced the
+                                   forward outputs), c3d_nerf_backward on the SAME workspace then skips the recomputation.
+                                   Tensor-core path only (bf16 mode, n_samples >= 8, g_params == NULL). */
+  int32_t _pad;
 } c3d_bwd_params;
 
 typedef struct c3d_raygen_params {
@@ -211,6 +216,10 @@ int c3d_nerf_forward(const c3d_fwd_params* p, c3d_stream_t stream);
 
 size_t c3d_backward_workspace_bytes(const c3d_bwd_params* p);
 int c3d_nerf_backward(const c3d_bwd_params* p, c3d_stream_t stream);
+/* Forward of a step that will be differentiated (flip inversion, projector_v9.py:1100-1143): same outputs as
+ * c3d_nerf_forward, computed once by the save-mode kernel into a workspace of c3d_backward_workspace_bytes(p) bytes
+ * (p->fwd_saved == 1) that the caller keeps until it calls c3d_nerf_backward with the same p (+ cotangents). */
+int c3d_nerf_forward_save(const c3d_bwd_params* p, c3d_stream_t stream);
 
 /* Second-order path of the eikonal regulariser (training; nerf_utils.py:220-228 with create_graph=True): given
  * g_eik = dL/dE (batch,n_rays,N,3) for E = d sdf / d pts, returns dL/d styles (p->g_styles) and dL/d parameters

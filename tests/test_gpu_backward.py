@@ -160,6 +160,8 @@ def test_parameter_gradients_match_reference_autograd(case, precision):
     got = dict(m.named_parameters())
     worst = ("", 0.0)
     for k in ref.files:
+        if k.startswith("eik"):                     # eikonal goldens of the same file: test_eikonal_* below
+            continue
         e = rel_l2(got[k].grad.cpu().numpy(), ref[k])
         worst = max(worst, (k, e), key=lambda t: t[1])
         assert got[k].grad.shape == ref[k].shape
@@ -323,3 +325,53 @@ def test_mlp_init_pass_matches_reference(monkeypatch):
     assert rel_l2(m.network.pts_linears[1].weight.grad.cpu().numpy(), z["g_w1"]) < GRAD_REL
     assert rel_l2(m.network.sigma_linear.weight.grad.cpu().numpy(), z["g_wsigma"]) < GRAD_REL
     assert rel_l2(m.network.pts_linears[0].gamma.bias.grad.cpu().numpy(), z["g_gamma0_bias"]) < GRAD_REL
+
+
+@pytest.mark.parametrize("entry,nchw", [("poses", False), ("poses", True), ("points", False)])
+def test_saved_forward_matches_recompute(entry, nchw, monkeypatch):
+    """bf16 mode, step that will be differentiated: the save-mode forward (c3d_nerf_forward_save, workspace kept for the
+    backward) gives the outputs of the plain forward and the gradients of the recompute path (C3D_SAVE_FWD_GB=0)."""
+    c = load_case("ffhq_d2_n24")
+    m = _module(2, "bf16")
+    S, N, b = 32, 24, 3
+    g = torch.Generator(device="cpu").manual_seed(5)
+    styles0 = _t(np.repeat(c["styles"], b, 0)) + 0.1 * torch.randn(b, 3, 256, generator=g).to(_dev())
+    pose0 = _t(np.repeat(c["c2w"], b, 0)) + 0.01 * torch.randn(b, 3, 4, generator=g).to(_dev())
+    focal0 = _t(np.repeat(c["focal"].reshape(1), b, 0)) * S / 64
+    near, far = _t(np.repeat(c["near"], b, 0)), _t(np.repeat(c["far"], b, 0))
+    res = {}
+    for mode in ("saved", "recompute"):
+        monkeypatch.setenv("C3D_SAVE_FWD_GB", "48" if mode == "saved" else "0")
+        styles, pose, focal = (t.detach().clone().requires_grad_(True) for t in (styles0, pose0, focal0))
+        if entry == "poses":
+            out = m.render(pose, focal, near, far, styles, img_size=S, N_samples=N, features_nchw=nchw)
+            launches = m.last_launch_count
+            outs = [out[k] for k in ("rgb_map", "feature_map", "sdf", "mask", "xyz", "z_vals")]
+            leaves = [styles, pose, focal]
+        else:
+            import cips3dpp_b200 as c3d
+            with torch.no_grad():
+                pts, rays_d, viewdirs, z = c3d.Render.prepare_nerf_inputs(focal=focal, img_size=S, cam_poses=pose, near=near,
+                                                                          far=far, N_samples=N, perturb=False)
+            pts, rays_d, viewdirs = (t.reshape(b, S * S, *t.shape[3:]).requires_grad_(True) for t in (pts, rays_d, viewdirs))
+            o = m(pts=pts, rays_d=rays_d, viewdirs=viewdirs, z_vals=z.reshape(b, S * S, N), near=near, far=far, styles=styles)
+            launches = m.last_launch_count
+            outs = list(o[:5])
+            leaves = [styles, pts, rays_d, viewdirs]
+        gen = torch.Generator(device="cpu").manual_seed(9)
+        loss = sum((o * torch.randn(o.shape, generator=gen).to(_dev())).sum() * (0.05 if i == 1 else 1.0)
+                   for i, o in enumerate(outs[:5]))
+        grads = torch.autograd.grad(loss, leaves)
+        res[mode] = ([o.detach().cpu().numpy() for o in outs], [g_.cpu().numpy() for g_ in grads], launches, m.last_launch_count)
+    with torch.no_grad():
+        monkeypatch.setenv("C3D_SAVE_FWD_GB", "48")
+        plain = m.render(pose0, focal0, near, far, styles0, img_size=S, N_samples=N, features_nchw=nchw)
+    if entry == "poses":
+        for k, o in zip(("rgb_map", "feature_map", "sdf", "mask", "xyz", "z_vals"), res["saved"][0]):
+            assert rel_l2(o, plain[k].cpu().numpy()) < 1e-5, k
+    for a, r in zip(res["saved"][0], res["recompute"][0]):
+        assert a.shape == r.shape and rel_l2(a, r) < 1e-5
+    for a, r in zip(res["saved"][1], res["recompute"][1]):
+        assert rel_l2(a, r) < 1e-4
+    # the saved backward launches no forward kernel: fewer launches than the recompute backward
+    assert res["saved"][3] < res["recompute"][3]
