@@ -32,16 +32,16 @@ with torch.no_grad():
     e1.record(); torch.cuda.synchronize()
 print(json.dumps(dict(D=D, targets=n, images=2 * n, precision=prec, ms_fwd_bwd=ms, ms_fwd=e0.elapsed_time(e1) / K,
                       images_per_s=2 * n / (ms * 1e-3))))
-# the whole optimisation step (camera glue, forward, loss, backward, clipping, Adam) eagerly and as a CUDA graph
+# the whole optimisation step (camera glue, forward, loss, backward, clipping, Adam) eagerly and as a CUDA graph,
+# 200 steps (BASELINE configs[4]), device time from the CUDA events FlipInversion.run records around its loop
 tg = tgt[0::2].contiguous()
 w0 = torch.zeros(1, D + 1, 256, device=dev)
 inv.num_steps = 3
 inv.run(tg, w0)                                                      # warm: optimiser / allocator first-use costs
+inv.num_steps = int(os.environ.get("STEPS", "200"))
 for graph in (False, True):
-    t = {}
-    for steps in (10, 60):
-        inv.num_steps = steps
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        inv.run(tg, w0, cuda_graph=graph)
-        torch.cuda.synchronize(); t[steps] = time.perf_counter() - t0
-    print(json.dumps(dict(full_step_cuda_graph=graph, ms_per_step=(t[60] - t[10]) / 50 * 1e3, setup_s=t[10])))
+    r = inv.run(tg, w0, cuda_graph=graph)
+    torch.cuda.synchronize()
+    ms = r["events"][0].elapsed_time(r["events"][1]) / inv.num_steps
+    print(json.dumps(dict(full_step_cuda_graph=graph, steps=inv.num_steps, ms_per_step=ms, images_per_s=2 * n / (ms * 1e-3),
+                          save_fwd_gb=os.environ.get("C3D_SAVE_FWD_GB", "48"), final_loss=float(r["losses"][-1]))))

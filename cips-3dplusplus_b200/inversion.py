@@ -50,7 +50,9 @@ class FlipInversion:
         return out["rgb_map"].reshape(n * 2, S, S, 3).permute(0, 3, 1, 2)
 
     def run(self, targets, w_init, azim_init=None, elev_init=None, callback=None, cuda_graph=False):
-        """targets (n, 3, S, S) in [-1, 1]; w_init (1 or n, D+1, 256).  Returns dict(w, azim, elev, losses).
+        """targets (n, 3, S, S) in [-1, 1]; w_init (1 or n, D+1, 256).  Returns dict(w, azim, elev, losses, events); `events` is a
+        pair of CUDA events around the optimisation loop (after a synchronize, `events[0].elapsed_time(events[1]) /
+        num_steps` is the device time per step).
 
         `cuda_graph=True` captures one whole optimisation step (camera glue, forward, loss, backward, clipping,
         both Adam updates) into a CUDA graph and replays it `num_steps` times; only the two learning rates are
@@ -105,6 +107,8 @@ class FlipInversion:
                 loss_static = one_step()
             lrs = torch.tensor([[lr_ramp(s, self.num_steps, l0) for l0 in (self.lr_latent, self.lr_cam)]
                                 for s in range(self.num_steps)], dtype=torch.float32).to(dev)
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
             for step in range(self.num_steps):
                 lr_w.copy_(lrs[step, 0])
                 lr_c.copy_(lrs[step, 1])
@@ -112,8 +116,11 @@ class FlipInversion:
                 losses.append(loss_static.clone())
                 if callback is not None:
                     callback(step, losses[-1])
-            return dict(w=w.detach(), azim=azim.detach(), elev=elev.detach(), losses=torch.stack(losses))
+            ev[1].record()
+            return dict(w=w.detach(), azim=azim.detach(), elev=elev.detach(), losses=torch.stack(losses), events=ev)
 
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
         for step in range(self.num_steps):
             for opt, lr0 in ((opt_w, self.lr_latent), (opt_c, self.lr_cam)):
                 for g in opt.param_groups:
@@ -121,4 +128,5 @@ class FlipInversion:
             losses.append(one_step())
             if callback is not None:
                 callback(step, losses[-1])
-        return dict(w=w.detach(), azim=azim.detach(), elev=elev.detach(), losses=torch.stack(losses))
+        ev[1].record()
+        return dict(w=w.detach(), azim=azim.detach(), elev=elev.detach(), losses=torch.stack(losses), events=ev)
