@@ -30,7 +30,11 @@ int fail(int code, const char* fmt, ...) {
 #ifndef C3D_FWD_DEFAULT_PAIR
 #define C3D_FWD_DEFAULT_PAIR 0
 #endif
+// density-only pass: none of the four map outputs is requested (only sdf / z_vals_out)
+static bool fwd_sdf_only(const c3d_fwd_params* p) { return !p->rgb_map && !p->feature_map && !p->mask && !p->xyz; }
+
 static bool fwd_uses_pair(const c3d_fwd_params* p) {
+  if (fwd_sdf_only(p)) return false;
   const char* e = getenv("C3D_FWD");
   bool pair = C3D_FWD_DEFAULT_PAIR != 0;
   if (e && strcmp(e, "v3") == 0) pair = false;
@@ -91,7 +95,8 @@ static int validate_fwd(const c3d_fwd_params* p) {
   C3D_CHECK_ARG(p->D >= 1 && p->D <= C3D_MAX_LAYERS, "D=%d outside [1,%d]", p->D, C3D_MAX_LAYERS);
   C3D_CHECK_ARG((long long)p->batch * p->n_rays * p->n_samples < (1ll << 31), "batch*n_rays*n_samples overflows int32");
   C3D_CHECK_ARG(p->packed && p->styles && p->near && p->far, "packed/styles/near/far must be non-NULL");
-  C3D_CHECK_ARG(p->rgb_map && p->feature_map && p->sdf && p->mask && p->xyz, "all five output pointers are required");
+  C3D_CHECK_ARG(p->sdf && ((p->rgb_map && p->feature_map && p->mask && p->xyz) || fwd_sdf_only(p)),
+                "outputs: sdf plus either all of rgb_map / feature_map / mask / xyz, or none of them (density-only pass)");
   if (p->input_kind == C3D_INPUT_POSES) {
     C3D_CHECK_ARG(p->cam_poses && p->focal, "POSES input needs cam_poses and focal");
     C3D_CHECK_ARG(p->img_size >= 1 && p->n_rays == p->img_size * p->img_size, "n_rays=%d != img_size^2 (%d)", p->n_rays, p->img_size);
@@ -165,6 +170,7 @@ static void fused_fill_args(fused::Args& a, const c3d_fwd_params* p, const float
   a.pts = p->pts; a.rays_d = p->rays_d; a.viewdirs = p->viewdirs; a.z_vals = p->z_vals;
   a.rgb_map = p->rgb_map; a.feature_map = p->feature_map; a.sdf = p->sdf; a.mask = p->mask; a.xyz = p->xyz;
   a.z_vals_out = p->z_vals_out;
+  a.sdf_only = fwd_sdf_only(p) ? 1 : 0;
   { const char* d = getenv("C3D_DEBUG"); a.debug = d ? atoi(d) : 0; }
 }
 
@@ -300,6 +306,7 @@ static int forward_fp32(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
     m.save_acc = nullptr; m.save_stride = 0;
     mlp_fp32_kernel<<<(unsigned)(ni * m.tiles_per_img), 256, F32_SMEM, st>>>(m);
     C3D_LAUNCH_CHECK();
+    if (fwd_sdf_only(p)) continue;                 // density-only pass: no compositing
     c3d_composite_params c;
     memset(&c, 0, sizeof(c));
     c.n_rays = (int64_t)ni * R; c.n_samples = p->n_samples; c.n_feat = W;
@@ -373,7 +380,8 @@ int c3d_nerf_forward(const c3d_fwd_params* p, c3d_stream_t stream) {
                          reinterpret_cast<float*>(ws + w.first), reinterpret_cast<float*>(ws + w.view), st);
   if (rc != C3D_OK) return rc;
   float* feat_out = p->feature_map;
-  if (p->feat_layout == C3D_FEAT_NCHW) {
+  const bool nchw = p->feat_layout == C3D_FEAT_NCHW && !fwd_sdf_only(p);
+  if (nchw) {
     C3D_CHECK_ARG(p->workspace_bytes >= c3d_workspace_bytes(p), "workspace too small for NCHW staging");
     feat_out = reinterpret_cast<float*>(ws + w.total);
   }
@@ -381,7 +389,7 @@ int c3d_nerf_forward(const c3d_fwd_params* p, c3d_stream_t stream) {
   q.feature_map = feat_out;
   rc = (p->mode == C3D_MODE_BF16) ? forward_bf16(&q, w, st) : forward_fp32(&q, w, st, feat_out);
   if (rc != C3D_OK) return rc;
-  if (p->feat_layout == C3D_FEAT_NCHW) {
+  if (nchw) {
     dim3 grid((p->n_rays + 31) / 32, W / 32, p->batch);
     nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, st>>>(feat_out, p->feature_map, p->n_rays);
     C3D_LAUNCH_CHECK();

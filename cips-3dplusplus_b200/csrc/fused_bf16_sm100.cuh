@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform role index
   const int lane = threadIdx.x & 31;
   const int D = a.D, N = a.n_samples;
-  const int JOBS = D + 3;
+  const int JOBS = a.sdf_only ? D + 1 : D + 3;         // density-only pass: jobs 0..D (layer 0, hidden layers, sdf head)
   const int nslots = 2 * gridDim.x;
   const uint32_t cta_rank = kCluster > 1 ? cluster_ctarank() : 0u;
 
@@ -407,6 +407,7 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
                 for (int pp = 0; pp < 4; ++pp) sdf += __uint_as_float(v4[pp][0]) + __uint_as_float(v4[pp][1]);
               }
               if (valid) a.sdf[gray * N + k] = sdf;
+              if (!a.sdf_only) {
               const float sigma = sigmoid_precise(-sdf * inv_beta) * inv_beta;
               const float alpha = 1.0f - expf(-sigma * dist);
               const float om = 1.0f - alpha + 1e-10f;
@@ -422,7 +423,9 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
               named_bar_sync(bar_id, TILE);
               if (t == TILE - 1) misc->carry[s] = (k == N - 1) ? 1.0f : T * om;
               fence_proxy_async_smem();
+              }
             }
+            if (a.sdf_only) break;                   // density-only pass: the tile ends with the sdf head
             mbar_arrive(&misc->a_ready[s]);
           }
           C3D_EPROF(e_pt);
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
         }
 
         // ------------------------------------------------ post job: composited features (thread = channel) + rgb (thread = point)
-        {
+        if (!a.sdf_only) {
           mbar_wait(&misc->acc_full[s], jobcnt & 1u);
           jobcnt++;
           tc_fence_after();

@@ -21,6 +21,8 @@ struct Args {
   const float* cam_poses; const float* focal; const float* near; const float* far; const float* ray_offset;
   const float* pts; const float* rays_d; const float* viewdirs; const float* z_vals;
   float* rgb_map; float* feature_map; float* sdf; float* mask; float* xyz; float* z_vals_out;
+  int sdf_only;  // density-only pass (coarse pass of the two-pass render): the tile ends after the sdf head -- no view layer,
+                 // no rgb head, no compositing; only `sdf` (and `z_vals_out`) are written
   int debug;   // bit 0: producer skips the weight copies (timing experiments only; results are garbage)
   int stagger;                                // CTA-pair kernel: slot 1 starts this many cycles after slot 0
   const uint8_t* wimg; const uint8_t* kimg;   // CTA-pair kernel: per-image FiLM-folded weight images (film_weights_kernel)

@@ -238,20 +238,24 @@ class NerfBranch(nn.Module):
             P.cam_poses, P.focal = a0.data_ptr(), a1.data_ptr()
             P.ray_offset = a2.data_ptr() if a2 is not None else None
 
-    def _launch_forward(self, kind, meta, styles, a0, a1, a2, a3, near, far):
+    def _launch_forward(self, kind, meta, styles, a0, a1, a2, a3, near, far, density_only=False):
         lib = _abi.load()
         b, n_rays, N, img_size, static_viewdirs, nchw = meta
         dev = styles.device
         f = dict(dtype=torch.float32, device=dev)
-        rgb_map = torch.empty(b, n_rays, 3, **f)
-        feat = torch.empty((b, W, n_rays) if nchw else (b, n_rays, W), **f)
         sdf = torch.empty(b, n_rays, N, 1, **f)
-        mask = torch.empty(b, n_rays, 2, **f)
-        xyz = torch.empty(b, n_rays, 3, **f)
         z_out = torch.empty(b, n_rays, N, **f) if kind == _abi.INPUT_POSES else None
         P = _abi.FwdParams()
         self._fill_common(P, kind, meta, styles, a0, a1, a2, a3, near, far)
-        P.rgb_map, P.feature_map, P.sdf, P.mask, P.xyz = (t.data_ptr() for t in (rgb_map, feat, sdf, mask, xyz))
+        if density_only:                                            # map pointers stay NULL: the kernel stops after the sdf head
+            rgb_map = feat = mask = xyz = None
+            P.sdf = sdf.data_ptr()
+        else:
+            rgb_map = torch.empty(b, n_rays, 3, **f)
+            feat = torch.empty((b, W, n_rays) if nchw else (b, n_rays, W), **f)
+            mask = torch.empty(b, n_rays, 2, **f)
+            xyz = torch.empty(b, n_rays, 3, **f)
+            P.rgb_map, P.feature_map, P.sdf, P.mask, P.xyz = (t.data_ptr() for t in (rgb_map, feat, sdf, mask, xyz))
         P.z_vals_out = z_out.data_ptr() if z_out is not None else None
         nws = lib.c3d_workspace_bytes(P)
         ws = torch.empty(max(nws, 16), dtype=torch.uint8, device=dev)
@@ -424,10 +428,11 @@ class NerfBranch(nn.Module):
         return rgb_map, feat, sdf, mask, xyz, eik
 
     def render(self, cam_poses, focal, near, far, styles, img_size=64, N_samples=24, static_viewdirs=False,
-               perturb=False, ray_offset=None, features_nchw=False):
+               perturb=False, ray_offset=None, features_nchw=False, density_only=False):
         """Fused fast path = Render.prepare_nerf_inputs (nerf_utils.py:172-218) + forward, rays generated
         in-kernel.  cam_poses (b,3,4), focal/near/far (b,1,1) or (b,).  Returns a dict of maps; `z_vals`
-        are the sample depths the kernel used."""
+        are the sample depths the kernel used.  `density_only=True` (no autograd) stops after the sdf head and returns
+        only `sdf` and `z_vals` -- the coarse pass of `render_hierarchical`."""
         b = cam_poses.shape[0]
         n_rays = img_size * img_size
         c = lambda t, *s: t.to(torch.float32).reshape(*s).contiguous()
@@ -435,19 +440,28 @@ class NerfBranch(nn.Module):
             ray_offset = torch.rand(b, img_size, img_size, 1, device=cam_poses.device)   # nerf_utils.py:110
         ro = None if ray_offset is None else c(ray_offset, b, n_rays)
         meta = (b, n_rays, N_samples, img_size, bool(static_viewdirs), bool(features_nchw))
-        rgb_map, feat, sdf, mask, xyz, z = self._run(
-            _abi.INPUT_POSES, meta, c(styles, b, self.N_layers_renderer + 1, W), c(cam_poses, b, 3, 4), c(focal, b),
-            ro, None, c(near, b), c(far, b))
+        args = (_abi.INPUT_POSES, meta, c(styles, b, self.N_layers_renderer + 1, W), c(cam_poses, b, 3, 4), c(focal, b),
+                ro, None, c(near, b), c(far, b))
+        if density_only:
+            if any(t.device.type != "cuda" for t in (styles, cam_poses)):
+                raise RuntimeError("NerfBranch needs CUDA tensors: there is no CPU fallback")
+            with torch.no_grad():
+                out = self._launch_forward(*args, density_only=True)
+            return dict(sdf=out[2], z_vals=out[5])
+        rgb_map, feat, sdf, mask, xyz, z = self._run(*args)
         return dict(rgb_map=rgb_map, feature_map=feat, sdf=sdf, mask=mask, xyz=xyz, z_vals=z)
 
     def render_hierarchical(self, cam_poses, focal, near, far, styles, img_size=64, N_samples=24, N_importance=24,
-                            static_viewdirs=False, perturb=False, ray_offset=None, u=None, features_nchw=False):
+                            static_viewdirs=False, perturb=False, ray_offset=None, u=None, features_nchw=False,
+                            coarse_maps=False):
         """EXTENSION, off by default (the reference renders in one pass; BASELINE.json's north star asks for a
         `sample_pdf` + fine pass): coarse pass (`render`, no grad) -> `Render.importance_depths` (c3d_sample_pdf: PDF from
         the coarse compositing weights, N_importance new depths, ascending union) -> second pass over the N_samples +
         N_importance merged depths with the same network (pi-GAN style; the point MLP is pointwise, so evaluating the
         union equals merging the coarse and fine outputs).  The new depths are constants of the fine pass; gradients flow
         through the fine pass to styles, parameters and -- through the rays -- to cam_poses / focal.
+        The coarse pass only has to produce densities, so by default it is a density-only launch (the kernel stops after the
+        sdf head: no view layer, rgb head or compositing); `coarse_maps=True` renders its maps too.
         Returns the fine pass's dict of maps (`z_vals` = merged depths) with the coarse pass's dict under "coarse"."""
         from .nerf_utils import Render
         if N_samples + N_importance > 256:
@@ -456,7 +470,8 @@ class NerfBranch(nn.Module):
         c = lambda t, *s: t.to(torch.float32).reshape(*s).contiguous()
         with torch.no_grad():
             coarse = self.render(cam_poses, focal, near, far, styles, img_size=img_size, N_samples=N_samples,
-                                 static_viewdirs=static_viewdirs, perturb=perturb, ray_offset=ray_offset)
+                                 static_viewdirs=static_viewdirs, perturb=perturb, ray_offset=ray_offset,
+                                 density_only=not coarse_maps)
         rays_o, rays_d, viewdirs = Render.get_rays_in_world(focal=focal, img_size=img_size, c2w=cam_poses,
                                                             static_viewdirs=static_viewdirs)
         rays_o, rays_d, viewdirs = (t.reshape(b, n_rays, 3) for t in (rays_o, rays_d, viewdirs))

@@ -114,7 +114,8 @@ typedef struct c3d_fwd_params {
   const float* rays_d;       /* (batch,n_rays,3) */
   const float* viewdirs;     /* (batch,n_rays,3) */
   const float* z_vals;       /* (batch,n_rays,N) */
-  /* outputs */
+  /* outputs.  sdf is always written; rgb_map / feature_map / mask / xyz are either all given or all NULL -- the latter is
+   * a density-only pass (the coarse pass of the optional two-pass render): the kernel stops after the sdf head. */
   float* rgb_map;            /* (batch,n_rays,3) */
   float* feature_map;        /* (batch,n_rays,256) or (batch,256,n_rays) */
   float* sdf;                /* (batch,n_rays,N)  [reference shape (b,hw,N,1)] */

@@ -124,7 +124,7 @@ def test_render_hierarchical_fp32_matches_oracle(case, N, K):
     with torch.no_grad():
         out = m.render_hierarchical(_t(c["c2w"]), _t(c["focal"]), _t(c["near"]), _t(c["far"]), _t(c["styles"]),
                                     img_size=64, N_samples=N, N_importance=K,
-                                    static_viewdirs=bool(c["static_viewdirs"]))
+                                    static_viewdirs=bool(c["static_viewdirs"]), coarse_maps=True)
     params = dict(load_weights(D), sigmoid_beta=np.asarray(c["sigmoid_beta"], np.float32).reshape(1))
     idx = c["ray_idx"].astype(np.int64)
     fine, coarse = O.render_hierarchical(params, c["c2w"], c["focal"], c["near"], c["far"], c["styles"], 64, N, K,
@@ -183,3 +183,35 @@ def test_render_hierarchical_gradients_flow_through_fine_pass():
     assert rel_l2(out["feature_map"].detach().cpu().numpy(), ref[1].detach().cpu().numpy()) < 1e-3
     assert rel_l2(styles.grad.cpu().numpy(), styles2.grad.cpu().numpy()) < 1e-3
     assert rel_l2(pose.grad.cpu().numpy(), pose2.grad.cpu().numpy()) < 1e-3
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", ["ffhq_d2_n24", "ffhq_d8_n24", "cars_d6_n24"])
+def test_density_only_pass_matches_full_render(case, precision):
+    """The coarse pass of the two-pass render stops after the sdf head: same sdf and depths as the full render, no maps;
+    the two-pass result does not depend on which coarse pass produced the densities."""
+    c = load_case(case)
+    m = _module(int(c["D"]), precision, c["sigmoid_beta"])
+    args = (_t(c["c2w"]), _t(c["focal"]), _t(c["near"]), _t(c["far"]), _t(c["styles"]))
+    kw = dict(img_size=64, N_samples=int(c["N"]), static_viewdirs=bool(c["static_viewdirs"]))
+    with torch.no_grad():
+        full = m.render(*args, **kw)
+        dens = m.render(*args, density_only=True, **kw)
+        a = m.render_hierarchical(*args, N_importance=24, **kw)
+        b = m.render_hierarchical(*args, N_importance=24, coarse_maps=True, **kw)
+    assert set(dens) == {"sdf", "z_vals"} and set(a["coarse"]) == {"sdf", "z_vals"}
+    assert torch.equal(dens["z_vals"], full["z_vals"])
+    assert torch.equal(dens["sdf"], full["sdf"])               # same kernel, same arithmetic up to the sdf head
+    assert torch.equal(a["z_vals"], b["z_vals"]) and torch.equal(a["feature_map"], b["feature_map"])
+    assert "feature_map" in b["coarse"]
+
+
+def test_density_only_needs_consistent_outputs():
+    import cips3dpp_b200 as c3d
+    lib = c3d._abi.load()
+    P = c3d._abi.FwdParams()
+    P.abi_version, P.mode, P.input_kind, P.batch, P.n_rays, P.n_samples, P.D, P.img_size = c3d._abi.ABI_VERSION, 1, 0, 1, 16, 24, 2, 4
+    t = torch.zeros(64, device=_dev())
+    P.packed = P.styles = P.near = P.far = P.cam_poses = P.focal = t.data_ptr()
+    P.sdf, P.rgb_map = t.data_ptr(), t.data_ptr()               # one map without the others
+    assert lib.c3d_nerf_forward(P, None) == -1 and b"density-only" in lib.c3d_last_error()
