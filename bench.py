@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the NeRF-branch hot path (BASELINE.json metric: rays/s & images/s at 64x64).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c4|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c2d2|c3|c4|c1|c5]
 
 One "step" = one pass of the hot path over one batch: BASELINE.json configs[1] -- FFHQ v10 NeRF branch
 (D=8, N=24 samples, 64x64 rays), 32 latents x 8-pose yaw sweep = 256 images, bf16, random-init weights,
@@ -35,6 +35,10 @@ CONFIGS = {
                desc="CompCars v10 NeRF branch 64x64, D=6, N=24, batch 32 (BASELINE configs[3])"),
     "c1": dict(D=8, N=24, latents=1, sweep=1, fov=6.0, radius=0.12, azim=0.0, elev=0.0,
                desc="FFHQ v10 NeRF branch 64x64, D=8, N=24, batch 1 (BASELINE configs[0])"),
+    # flip inversion: a step = one optimisation step (forward + backward through the NeRF branch + Adam) over 16 targets
+    # and their flips (32 images of 64x64 rays) per GPU; see run_inversion
+    "c5": dict(D=2, N=24, latents=16, sweep=2, fov=6.0, radius=0.12, azim=0.3, elev=0.15,
+               desc="flip inversion step, D=2, N=24, 16 synthetic targets + flips = 32 images per GPU (BASELINE configs[4] shape)"),
 }
 IMG = 64
 
@@ -148,6 +152,88 @@ def run_reference(args, cfg, rank, world):
     }))
 
 
+def run_inversion(args, cfg, rank, world, local_rank):
+    """--config c5: one JSON line for the flip-inversion step (cips3dpp_b200.FlipInversion, stage 1 of projector_v9.py:
+    862-1166).  value = rays/s through forward + backward + optimiser with targets resident (whole step replayed as a CUDA
+    graph, CUDA events around the replay loop); e2e = eager steps that copy the targets host -> device and read the loss
+    back every step; roofline = algorithmic 2 F FLOPs (forward + input-gradient GEMMs) of the step / its time."""
+    import torch
+    import torch.distributed as dist
+    import cips3dpp_b200 as c3d
+    from oracle import nerf_oracle as O
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    D, N, n_t = cfg["D"], cfg["N"], cfg["latents"]
+    m = c3d.NerfBranch(D, precision=args.precision)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in O.init_params(D, seed=0).items()}, strict=True)
+    m = m.to(dev).eval().requires_grad_(False)
+    g = torch.Generator().manual_seed(5 + rank)
+    host_t = (torch.rand(n_t, 3, IMG, IMG, generator=g) * 2 - 1).pin_memory()
+    tgt = host_t.to(dev)
+    w0 = torch.zeros(1, D + 1, 256, device=dev)
+    inv = c3d.FlipInversion(m, img_size=IMG, N_samples=N, num_steps=max(args.warmup, 3))
+    inv.run(tgt, w0)                                                  # warm-up (eager), then the graph path once
+    inv.run(tgt, w0, cuda_graph=True)
+    wq = torch.zeros(n_t, D + 1, 256, device=dev, requires_grad=True)       # count this library's launches of one step
+    aq = torch.zeros(n_t, 2, 1, device=dev, requires_grad=True)
+    th = inv.render_thumbs(wq, aq, aq.detach().clone().requires_grad_(True))
+    launches = m.last_launch_count
+    th.sum().backward()
+    launches += m.last_launch_count
+    inv.num_steps = args.steps
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sync()
+    r = inv.run(tgt, w0, cuda_graph=True)
+    sync()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    ms_step = r["events"][0].elapsed_time(r["events"][1]) / args.steps
+    r2 = inv.run(tgt, w0, host_targets=host_t)
+    sync()
+    ms_e2e = r2["events"][0].elapsed_time(r2["events"][1]) / args.steps
+    if world > 1:
+        t = torch.tensor([ms_step, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, ms_e2e = float(t[0]), float(t[1])
+    if rank == 0:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+            os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        imgs = 2 * n_t
+        rays = imgs * IMG * IMG
+        flops = 2 * O.flops_per_point(D) * rays * N
+        print(json.dumps({
+            "metric": "nerf_branch_rays_per_s", "value": world * rays / (ms_step * 1e-3), "unit": "rays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "images_per_s": world * imgs / (ms_step * 1e-3),
+            "config": {"workload": cfg["desc"], "images_per_gpu": imgs, "rays_per_image": IMG * IMG, "samples_per_ray": N,
+                       "layers": D, "step": "forward + backward (styles, cameras) + clipping + Adam, CUDA-graph replay",
+                       "l2": "not flushed: the step's working set (saved tiles, 0.3 GB per image) is far larger than L2",
+                       "final_loss": float(r["losses"][-1])},
+            "e2e": {"value": world * rays / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(host_t.numel() * 4), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches * args.steps),
+            "roofline": {"bound": "tensor", "achieved": flops / (ms_step * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": flops / (ms_step * 1e-3) / 1e12 / peak_tf, "traffic": None,
+                         "kernel": "whole step (fused_forward_kernel<save> + fused_backward_kernel dominate)",
+                         "flops_per_launch": flops,
+                         "peak_source": "measured sustained (MEASURED_PEAKS.json)" if peaks else "fallback"},
+            "clocks": sampler.summary(),
+        }))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def side_measurements(m, params, devt, D, N, dev, timed):
     """Two side lines SURVEY.md section 8(d) asks for, at N=1 only, outside the headline timed region:
     (1) the standalone compositing kernel against the HBM roofline on reference-layout inputs
@@ -228,6 +314,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, cfg, rank, world)
+        return
+    if args.config == "c5":
+        run_inversion(args, cfg, rank, world, local_rank)
         return
 
     import torch

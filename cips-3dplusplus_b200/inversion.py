@@ -49,7 +49,7 @@ class FlipInversion:
                                    static_viewdirs=self.static_viewdirs)
         return out["rgb_map"].reshape(n * 2, S, S, 3).permute(0, 3, 1, 2)
 
-    def run(self, targets, w_init, azim_init=None, elev_init=None, callback=None, cuda_graph=False):
+    def run(self, targets, w_init, azim_init=None, elev_init=None, callback=None, cuda_graph=False, host_targets=None):
         """targets (n, 3, S, S) in [-1, 1]; w_init (1 or n, D+1, 256).  Returns dict(w, azim, elev, losses, events); `events` is a
         pair of CUDA events around the optimisation loop (after a synchronize, `events[0].elapsed_time(events[1]) /
         num_steps` is the device time per step).
@@ -57,7 +57,10 @@ class FlipInversion:
         `cuda_graph=True` captures one whole optimisation step (camera glue, forward, loss, backward, clipping,
         both Adam updates) into a CUDA graph and replays it `num_steps` times; only the two learning rates are
         written from the host between replays.  It needs frozen renderer weights, a capturable `loss_fn`, and is
-        refused together with a cross-rank shared latent (the all-reduce stays outside graphs)."""
+        refused together with a cross-rank shared latent (the all-reduce stays outside graphs).
+
+        `host_targets` (pinned host tensor shaped like `targets`, eager mode only) makes every step end to end: the step's
+        targets are copied host -> device and its loss is read back to the host (what bench.py's `e2e` times)."""
         dev, n = targets.device, targets.shape[0]
         tgt = torch.stack([targets, targets.flip(-1)], 1).reshape(n * 2, *targets.shape[1:])
         nw = 1 if self.shared_latent else n
@@ -121,11 +124,18 @@ class FlipInversion:
 
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
+        if host_targets is not None and cuda_graph:
+            raise ValueError("host_targets is an eager-mode option")
         for step in range(self.num_steps):
             for opt, lr0 in ((opt_w, self.lr_latent), (opt_c, self.lr_cam)):
                 for g in opt.param_groups:
                     g["lr"] = lr_ramp(step, self.num_steps, lr0)
+            if host_targets is not None:
+                t = host_targets.to(dev, non_blocking=True)
+                tgt.copy_(torch.stack([t, t.flip(-1)], 1).reshape(tgt.shape))
             losses.append(one_step())
+            if host_targets is not None:
+                losses[-1].item()                                    # device -> host read of the step's result
             if callback is not None:
                 callback(step, losses[-1])
         ev[1].record()
