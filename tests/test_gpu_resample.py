@@ -215,3 +215,27 @@ def test_density_only_needs_consistent_outputs():
     P.packed = P.styles = P.near = P.far = P.cam_poses = P.focal = t.data_ptr()
     P.sdf, P.rgb_map = t.data_ptr(), t.data_ptr()               # one map without the others
     assert lib.c3d_nerf_forward(P, None) == -1 and b"density-only" in lib.c3d_last_error()
+
+
+def test_render_hierarchical_perturbed_and_wide():
+    """Training-style sampling (random per-ray offset in the coarse pass, random draws for the new depths) and a wide
+    fine pass (24 + 104 = 128 merged samples): finite maps, ascending merged depths inside [near, far], reproducible
+    under the same seed."""
+    c = load_case("ffhq_d2_n24")
+    m = _module(2, "bf16")
+    args = (_t(c["c2w"]), _t(c["focal"]), _t(c["near"]), _t(c["far"]), _t(c["styles"]))
+    outs = []
+    for _ in range(2):
+        torch.manual_seed(21)
+        with torch.no_grad():
+            outs.append(m.render_hierarchical(*args, img_size=32, N_samples=24, N_importance=104, perturb=True))
+    a, b = outs
+    z = a["z_vals"]
+    assert z.shape == (1, 1024, 128) and torch.isfinite(a["feature_map"]).all() and torch.isfinite(a["rgb_map"]).all()
+    assert (z.diff(dim=-1) >= 0).all()
+    assert z.min() >= float(c["near"].min()) - 1e-6 and z.max() <= float(c["far"].max()) + 1e-6
+    assert torch.equal(a["z_vals"], b["z_vals"]) and torch.equal(a["feature_map"], b["feature_map"])
+    with torch.no_grad():
+        torch.manual_seed(22)
+        other = m.render_hierarchical(*args, img_size=32, N_samples=24, N_importance=104, perturb=True)
+    assert not torch.equal(other["z_vals"], a["z_vals"])
