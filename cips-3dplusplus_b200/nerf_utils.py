@@ -132,6 +132,15 @@ class Render:
 
 
     @staticmethod
+    def get_eikonal_term(pts, sdf):
+        """nerf_utils.py:220-228: d sdf / d pts by autograd, for `sdf` produced from `pts` (requires_grad) by
+        `NerfBranch.forward`.  First order only -- the custom backward is not differentiable a second time; the training
+        regulariser (a loss on this term) goes through `NerfBranch.forward(return_eikonal=True)` instead, whose double
+        backward is a dedicated kernel (c3d_eikonal_backward)."""
+        return torch.autograd.grad(outputs=sdf, inputs=pts, grad_outputs=torch.ones_like(sdf), retain_graph=True,
+                                   only_inputs=True)[0]
+
+    @staticmethod
     def importance_depths(z_vals, N_importance, weights=None, sdf=None, rays_d=None, sigmoid_beta=None, rays_o=None,
                           u=None, perturb=False, return_pts=False):
         """EXTENSION (no reference counterpart: the reference renders in one pass) -> c3d_sample_pdf (CUDA).
@@ -193,10 +202,11 @@ class Render:
 class Camera:
     @staticmethod
     def generate_camera_params(img_size, device, batch=1, locations=None, sweep=False, uniform=False,
-                               azim_range=0.3, elev_range=0.15, fov_ang=6, dist_radius=0.12):
+                               azim_range=0.3, elev_range=0.15, fov_ang=6, dist_radius=0.12, up=None):
         """nerf_utils.py:343-436: camera on the unit sphere looking at the origin.
 
         Returns extrinsics (b,3,4), focal (b,1,1), near (b,1,1), far (b,1,1), viewpoint (b,2).
+        `up` (b,3) or (1,3): the up vector of `generate_camera_params_v1` (nerf_utils.py:466-560); None = (0,1,0).
         """
         def rng(r):
             return (r[0], r[1]) if isinstance(r, (list, tuple)) else (-r, r)
@@ -230,8 +240,11 @@ class Camera:
         cam_dir = torch.stack([torch.cos(elev) * torch.sin(azim), torch.sin(elev), torch.cos(elev) * torch.cos(azim)],
                               dim=1).view(-1, 3)
         cam_loc = dist * cam_dir
-        up = torch.zeros(n, 3, device=device)                    # (0, 1, 0), built without a host copy (graph-capturable)
-        up[:, 1] = 1.0
+        if up is None:
+            up = torch.zeros(n, 3, device=device)                # (0, 1, 0), built without a host copy (graph-capturable)
+            up[:, 1] = 1.0
+        else:
+            up = up.to(device=device, dtype=torch.float32).reshape(-1, 3).expand(n, 3)
         z_ax = F.normalize(cam_dir, eps=1e-5)
         x_ax = F.normalize(torch.cross(up, z_ax, dim=1), eps=1e-5)
         y_ax = F.normalize(torch.cross(z_ax, x_ax, dim=1), eps=1e-5)
@@ -241,3 +254,37 @@ class Camera:
         rot = torch.stack([x_ax, y_ax, z_ax], dim=2)              # columns are the camera axes
         extrinsics = torch.cat([rot, cam_loc[:, :, None]], dim=-1)
         return extrinsics, focal, near, far, viewpoint
+
+    @staticmethod
+    def generate_camera_params_v1(img_size, device, batch=1, locations=None, sweep=False, uniform=False, azim_range=0.3,
+                                  elev_range=0.15, fov_ang=6, dist_radius=0.12, up=None):
+        """nerf_utils.py:466-560 (used by render_video_web_v10.py:1636): `generate_camera_params` with a caller-given up
+        vector."""
+        return Camera.generate_camera_params(img_size, device, batch=batch, locations=locations, sweep=sweep, uniform=uniform,
+                                             azim_range=azim_range, elev_range=elev_range, fov_ang=fov_ang,
+                                             dist_radius=dist_radius, up=up)
+
+    @staticmethod
+    def get_camera2world(cam2world, trans, homo=False):
+        """nerf_utils.py:439-463: axis-angle rotation (..., 3) + translation (..., 3) -> extrinsics (..., 3, 4) or, with
+        `homo`, (..., 4, 4).  The reference calls pytorch3d's `axis_angle_to_matrix`; the same map (Rodrigues' formula,
+        series expansion near zero) is written out here so the helper has no third-party dependency."""
+        assert cam2world.shape[:-1] == trans.shape[:-1]
+        prefix = cam2world.shape[:-1]
+        theta = cam2world.norm(dim=-1, keepdim=True)
+        small = theta < 1e-4
+        t2 = theta * theta
+        a = torch.where(small, 1.0 - t2 / 6.0, torch.sin(theta) / theta.clamp_min(1e-30))               # sin(t)/t
+        b = torch.where(small, 0.5 - t2 / 24.0, (1.0 - torch.cos(theta)) / t2.clamp_min(1e-30))        # (1-cos t)/t^2
+        x, y, z = cam2world.unbind(-1)
+        zero = torch.zeros_like(x)
+        K = torch.stack([zero, -z, y, z, zero, -x, -y, x, zero], -1).reshape(*prefix, 3, 3)
+        eye = torch.eye(3, dtype=cam2world.dtype, device=cam2world.device).expand(*prefix, 3, 3)
+        rot = eye + a[..., None] * K + b[..., None] * (K @ K)
+        ext = torch.cat([rot, trans.reshape(*prefix, 3, 1)], dim=-1)
+        if homo:
+            last = torch.zeros(*prefix, 1, 4, dtype=ext.dtype, device=ext.device)
+            last[..., 0, 3] = 1.0
+            ext = torch.cat([ext, last], dim=-2)
+        return ext
+

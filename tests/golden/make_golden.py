@@ -14,6 +14,7 @@ Outputs (committed):
                       cases reuse layers 0..D-1 + views/rgb/sigma heads of the same dict)
   case_*.npz          inputs (256-ray subsets of a 64x64 image) and reference outputs
   camera.npz          Camera.generate_camera_params + prepare_nerf_inputs checks
+  camera_v1.npz       `--camera-v1`: Camera.generate_camera_params_v1 with caller-given up vectors
   pgrads_*.npz        `--param-grads`: gradients w.r.t. every renderer parameter for the two *_grads cases, computed
                       by the reference's autograd on the committed case inputs / cotangents (fp32; at D=8 the
                       256x256 matrices are kept for layers 1 and 7 only, to bound the fixture size)
@@ -178,6 +179,18 @@ def main():
         cam.update({f"{tag}_locations": locs_t.numpy(), f"{tag}_c2w": c2w.numpy(), f"{tag}_focal": focal.numpy(),
                     f"{tag}_near": near.numpy(), f"{tag}_far": far.numpy()})
     np.savez_compressed(os.path.join(HERE, "camera.npz"), **cam)
+    camera_v1(nu)
+
+
+def camera_v1(nu=None):
+    """Camera.generate_camera_params_v1 (caller-given up vector, nerf_utils.py:466-560) -> camera_v1.npz."""
+    if nu is None:
+        nu, _ = import_reference()
+    locs = torch.tensor([[0.0, 0.0], [0.4, -0.2], [-2.5, 0.3], [3.0, 0.05]], dtype=torch.float32)
+    ups = torch.tensor([[0.0, 1.0, 0.0], [0.1, 0.9, -0.2], [0.0, 0.0, 1.0], [-0.3, 1.0, 0.3]], dtype=torch.float32)
+    c2w, focal, near, far, vp = nu.Camera.generate_camera_params_v1(img_size=64, device="cpu", locations=locs, up=ups, **CARS)
+    np.savez_compressed(os.path.join(HERE, "camera_v1.npz"), locations=locs.numpy(), up=ups.numpy(), c2w=c2w.numpy(),
+                        focal=focal.numpy(), near=near.numpy(), far=far.numpy(), viewpoint=vp.numpy())
 
 
 def param_grads():
@@ -256,5 +269,7 @@ if __name__ == "__main__":
     if "--param-grads" in sys.argv:
         param_grads()
         mlp_init_case()
+    elif "--camera-v1" in sys.argv:
+        camera_v1()
     else:
         main()

@@ -122,3 +122,38 @@ def test_camera_mirror_matches_oracle_on_cpu():
     ext = c3d.Camera.generate_camera_params(64, "cpu", locations=loc)[0]
     ext.sum().backward()
     assert loc.grad is not None and loc.grad.abs().sum() > 0
+
+
+def test_camera_v1_matches_reference_golden():
+    """Camera.generate_camera_params_v1 (caller-given up vector, nerf_utils.py:466-560) vs the reference's own output
+    (tests/golden/camera_v1.npz, written by make_golden.py --camera-v1)."""
+    import cips3dpp_b200 as c3d
+    g = np.load(os.path.join(ROOT, "tests", "golden", "camera_v1.npz"))
+    out = c3d.Camera.generate_camera_params_v1(64, "cpu", locations=torch.from_numpy(g["locations"]),
+                                               up=torch.from_numpy(g["up"]), fov_ang=15, dist_radius=0.3)
+    for a, k in zip(out, ("c2w", "focal", "near", "far", "viewpoint")):
+        np.testing.assert_allclose(a.numpy(), g[k], atol=2e-6, rtol=1e-6)
+    base = c3d.Camera.generate_camera_params(64, "cpu", locations=torch.from_numpy(g["locations"]), fov_ang=15, dist_radius=0.3)
+    v1 = c3d.Camera.generate_camera_params_v1(64, "cpu", locations=torch.from_numpy(g["locations"]), fov_ang=15, dist_radius=0.3)
+    assert all(torch.equal(a, b) for a, b in zip(base, v1))
+
+
+def test_get_camera2world_matches_rotation_vectors():
+    """Camera.get_camera2world (nerf_utils.py:439-463; the reference delegates to pytorch3d's axis_angle_to_matrix, absent
+    here): Rodrigues' formula against scipy's rotation-vector conversion, including tiny and near-pi angles."""
+    from scipy.spatial.transform import Rotation
+    import cips3dpp_b200 as c3d
+    rng = np.random.default_rng(0)
+    rv = rng.normal(0, 1.5, (64, 3))
+    rv[0] = 0.0
+    rv[1] = [1e-7, -2e-7, 5e-8]
+    rv[2] = np.array([0.6, 0.0, 0.8]) * (np.pi - 1e-3)
+    tr = rng.normal(0, 1, (64, 3))
+    ext = c3d.Camera.get_camera2world(torch.from_numpy(rv), torch.from_numpy(tr), homo=True).numpy()
+    assert ext.shape == (64, 4, 4)
+    np.testing.assert_allclose(ext[:, :3, :3], Rotation.from_rotvec(rv).as_matrix(), atol=1e-12)
+    np.testing.assert_allclose(ext[:, :3, 3], tr)
+    np.testing.assert_array_equal(ext[:, 3], np.broadcast_to([0.0, 0.0, 0.0, 1.0], (64, 4)))
+    e32 = c3d.Camera.get_camera2world(torch.from_numpy(rv).float().reshape(8, 8, 3), torch.from_numpy(tr).float().reshape(8, 8, 3))
+    assert e32.shape == (8, 8, 3, 4)
+    np.testing.assert_allclose(e32.reshape(64, 3, 4)[:, :, :3].numpy(), Rotation.from_rotvec(rv).as_matrix(), atol=2e-6)

@@ -375,3 +375,16 @@ def test_saved_forward_matches_recompute(entry, nchw, monkeypatch):
         assert rel_l2(a, r) < 1e-4
     # the saved backward launches no forward kernel: fewer launches than the recompute backward
     assert res["saved"][3] < res["recompute"][3]
+
+
+def test_static_get_eikonal_term_matches_return_eikonal():
+    """Render.get_eikonal_term (nerf_utils.py:220-228, first order) == the term NerfBranch.forward(return_eikonal=True) returns."""
+    import cips3dpp_b200 as c3d
+    c = load_case("ffhq_d2_n24_grads")
+    m = _module(2, "fp32")
+    pts = _t(c["pts"], True)
+    out = m(pts=pts, rays_d=_t(c["rays_d"]), viewdirs=_t(c["viewdirs"]), z_vals=_t(c["z_vals"]), near=_t(c["near"]),
+            far=_t(c["far"]), styles=_t(c["styles"]), return_eikonal=True)
+    e2 = c3d.Render.get_eikonal_term(pts, out[2])
+    assert e2.shape == out[5].shape
+    assert rel_l2(e2.cpu().numpy(), out[5].detach().cpu().numpy()) < 1e-5
