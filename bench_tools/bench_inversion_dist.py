@@ -1,6 +1,6 @@
 """BASELINE configs[4] shape: flip inversion of 16 targets (+ flips = 32 images per step), sharded over the ranks of a
 torchrun launch (targets are independent: no data-path collective).  Reports the max-over-ranks time per optimisation
-step (CUDA-graph replay of camera glue + forward + loss + backward + clipping + Adam)."""
+step (CUDA-graph replay of camera glue + forward + loss + backward + clipping + Adam; CUDA events around the loop)."""
 import json
 import os
 import sys
@@ -30,15 +30,13 @@ tgt = tgt_all[lo:hi].to(dev)
 w0 = torch.zeros(1, D + 1, 256, device=dev)
 inv = c3d.FlipInversion(m, img_size=64, N_samples=24, num_steps=10)
 inv.run(tgt, w0, cuda_graph=True)                                   # warm-up: allocator, capture path
-t = {}
-for s_ in (20, 20 + steps):
-    inv.num_steps = s_
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    out = inv.run(tgt, w0, cuda_graph=True)
-    torch.cuda.synchronize(); t[s_] = time.perf_counter() - t0
-ms = (t[20 + steps] - t[20]) / steps * 1e3
+inv.num_steps = steps
+if world > 1:
+    dist.barrier()
+torch.cuda.synchronize()
+out = inv.run(tgt, w0, cuda_graph=True)
+torch.cuda.synchronize()
+ms = out["events"][0].elapsed_time(out["events"][1]) / steps         # device time of the replay loop (CUDA events)
 x = torch.tensor([ms], device=dev, dtype=torch.float64)
 if world > 1:
     dist.all_reduce(x, op=dist.ReduceOp.MAX)
