@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("C3D_LIB") or os.path.join(HERE, "libc3dpp.so")   # C3D_LIB: A/B builds (bench_tools)
 SRC = os.path.join(HERE, "csrc", "c3d_abi.cu")
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_LAYERS = 16
 MODE_FP32, MODE_BF16 = 0, 1
 INPUT_POSES, INPUT_POINTS = 0, 1
@@ -75,6 +75,12 @@ class ResampleParams(C.Structure):
                             "z_fine", "z_merged", "pts_merged")]
 
 
+class AdamParams(C.Structure):
+    _fields_ = [("n_tensors", C.c_int32), ("group", C.c_int32 * 8), ("numel", C.c_int64 * 8), ("param", _fp * 8),
+                ("grad", _fp * 8), ("exp_avg", _fp * 8), ("exp_avg_sq", _fp * 8), ("lr", _fp * 2), ("step", _fp),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("max_norm", C.c_float), ("grad_norm", _fp)]
+
+
 EXPORTS = {
     "c3d_abi_version": (C.c_int, []),
     "c3d_last_error": (C.c_char_p, []),
@@ -92,6 +98,8 @@ EXPORTS = {
     "c3d_style_prep": (C.c_int, [_fp, C.c_int32, _fp, C.c_int32, _fp, _fp, _fp, _fp]),
     "c3d_composite_forward": (C.c_int, [C.POINTER(CompositeParams), _fp]),
     "c3d_composite_backward": (C.c_int, [C.POINTER(CompositeParams), _fp]),
+    "c3d_camera_params": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, _fp, C.c_float, C.c_float, _fp, _fp, _fp, _fp, _fp, _fp]),
+    "c3d_adam_clip_step": (C.c_int, [C.POINTER(AdamParams), _fp]),
     "c3d_sample_pdf": (C.c_int, [C.POINTER(ResampleParams), _fp]),
     "c3d_umma_selftest": (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp]),
 }

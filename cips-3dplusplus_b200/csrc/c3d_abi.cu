@@ -14,6 +14,7 @@
 #include "eikonal.cuh"
 #include "fused_bwd_sm100.cuh"
 #include "resample.cuh"
+#include "inversion_aux.cuh"
 
 namespace c3d {
 thread_local char g_err[512] = "";
@@ -479,6 +480,39 @@ int c3d_sample_pdf(const c3d_resample_params* p, c3d_stream_t stream) {
   const int per_sm = smem <= 110 * 1024 ? 2 : 1;
   const unsigned grid = (unsigned)(n_chunks < (long long)sms * per_sm ? n_chunks : (long long)sms * per_sm);
   resample::sample_pdf_kernel<<<grid, resample::THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(q, L, (int)n_chunks);
+  C3D_LAUNCH_CHECK();
+  return C3D_OK;
+}
+
+int c3d_camera_params(const float* azim, const float* elev, int32_t n, int32_t img_size, const float* fov_ang, float fov_scalar,
+                      float dist_radius, float* cam_poses, float* focal, float* near, float* far, float* jac,
+                      c3d_stream_t stream) {
+  C3D_CHECK_ARG(n >= 1 && img_size >= 1, "n and img_size must be >= 1");
+  C3D_CHECK_ARG(azim && elev && cam_poses && focal && near && far, "azim/elev and the four outputs must be non-NULL");
+  C3D_CHECK_ARG(fov_ang || fov_scalar > 0.f, "fov must be > 0");
+  invaux::camera_kernel<<<(unsigned)((n + 63) / 64), 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      azim, elev, n, (float)img_size, fov_ang, fov_scalar, dist_radius, cam_poses, focal, near, far, jac);
+  C3D_LAUNCH_CHECK();
+  return C3D_OK;
+}
+
+int c3d_adam_clip_step(const c3d_adam_params* p, c3d_stream_t stream) {
+  C3D_CHECK_ARG(p && p->n_tensors >= 1 && p->n_tensors <= invaux::ADAM_MAX_TENSORS, "n_tensors outside [1,%d]",
+                invaux::ADAM_MAX_TENSORS);
+  C3D_CHECK_ARG(p->step && p->lr[0] && p->lr[1], "step and both learning-rate scalars must be non-NULL");
+  C3D_CHECK_ARG(p->beta1 >= 0.f && p->beta1 < 1.f && p->beta2 >= 0.f && p->beta2 < 1.f && p->eps > 0.f, "bad Adam constants");
+  invaux::AdamArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_tensors = p->n_tensors;
+  for (int t = 0; t < p->n_tensors; ++t) {
+    C3D_CHECK_ARG(p->group[t] == 0 || p->group[t] == 1, "tensor %d: group must be 0 or 1", t);
+    C3D_CHECK_ARG(p->numel[t] >= 1 && p->param[t] && p->grad[t] && p->exp_avg[t] && p->exp_avg_sq[t], "tensor %d: NULL pointer or empty", t);
+    a.group[t] = p->group[t]; a.numel[t] = p->numel[t]; a.param[t] = p->param[t]; a.grad[t] = p->grad[t];
+    a.exp_avg[t] = p->exp_avg[t]; a.exp_avg_sq[t] = p->exp_avg_sq[t];
+  }
+  a.lr[0] = p->lr[0]; a.lr[1] = p->lr[1]; a.step = p->step;
+  a.beta1 = p->beta1; a.beta2 = p->beta2; a.eps = p->eps; a.max_norm = p->max_norm; a.grad_norm = p->grad_norm;
+  invaux::adam_clip_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   C3D_LAUNCH_CHECK();
   return C3D_OK;
 }

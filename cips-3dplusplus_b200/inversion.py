@@ -11,12 +11,55 @@ Targets are independent, so ranks take disjoint targets and no gradient all-redu
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 
 import torch
 
+from . import _abi
 from . import dist as c3d_dist
 from .nerf_utils import Camera
+
+
+class _FusedClipAdam:
+    """Gradient-norm clipping + Adam for the step's few small tensors in ONE launch (c3d_adam_clip_step): group 0 = the
+    latents, group 1 = the cameras, each clipped on its own norm and stepped with its own learning rate (projector_v9.py:
+    1016-1030, 1150-1153 uses two torch optimisers and two clip_grad_norm_ calls: ~40 launches per step).  Learning rates
+    and the step counter live on the device, so the update is CUDA-graph capturable."""
+
+    def __init__(self, groups, betas=(0.9, 0.999), eps=1e-8, max_norm=10.0):
+        self.tensors = [(t, g) for g, ts in enumerate(groups) for t in ts]
+        dev = self.tensors[0][0].device
+        self.m = [torch.zeros_like(t) for t, _ in self.tensors]
+        self.v = [torch.zeros_like(t) for t, _ in self.tensors]
+        self.lr = torch.zeros(2, device=dev)
+        self.step_count = torch.zeros((), device=dev)
+        self.betas, self.eps, self.max_norm = betas, eps, max_norm
+
+    def step(self):
+        lib = _abi.load()
+        P = _abi.AdamParams()
+        P.n_tensors = len(self.tensors)
+        keep = []
+        for i, (t, g) in enumerate(self.tensors):
+            if t.grad is None or not t.is_contiguous():
+                raise RuntimeError("fused update needs contiguous parameters with gradients")
+            grad = t.grad if t.grad.is_contiguous() else t.grad.contiguous()
+            keep.append(grad)
+            P.group[i], P.numel[i] = g, t.numel()
+            P.param[i], P.grad[i], P.exp_avg[i], P.exp_avg_sq[i] = t.data_ptr(), grad.data_ptr(), self.m[i].data_ptr(), \
+                self.v[i].data_ptr()
+        P.lr[0], P.lr[1] = self.lr.data_ptr(), self.lr.data_ptr() + 4
+        P.step = self.step_count.data_ptr()
+        P.beta1, P.beta2, P.eps, P.max_norm = self.betas[0], self.betas[1], self.eps, self.max_norm
+        dev = self.lr.device
+        with torch.cuda.device(dev):
+            _abi.check(lib.c3d_adam_clip_step(P, torch.cuda.current_stream().cuda_stream), "c3d_adam_clip_step")
+
+    def reset(self):
+        for t in self.m + self.v:
+            t.zero_()
+        self.step_count.zero_()
 
 
 def lr_ramp(step, num_steps, lr0, rampdown=0.25, rampup=0.05):
@@ -33,11 +76,12 @@ def thumb_mse(thumb, target):
 
 class FlipInversion:
     def __init__(self, renderer, img_size=64, N_samples=24, cam_cfg=None, lr_latent=0.02, lr_cam=0.01, num_steps=200,
-                 loss_fn=thumb_mse, clip=10.0, shared_latent=False, static_viewdirs=True):
+                 loss_fn=thumb_mse, clip=10.0, shared_latent=False, static_viewdirs=True, fused_update=True):
         self.renderer, self.img_size, self.N = renderer, img_size, N_samples
         self.cam_cfg = dict(fov_ang=6, dist_radius=0.12) if cam_cfg is None else dict(cam_cfg)
         self.lr_latent, self.lr_cam, self.num_steps = lr_latent, lr_cam, num_steps
         self.loss_fn, self.clip, self.shared_latent, self.static_viewdirs = loss_fn, clip, shared_latent, static_viewdirs
+        self.fused_update = fused_update      # clipping + both Adam updates as one kernel (CUDA tensors); False: torch.optim
 
     def render_thumbs(self, w, azim, elev):
         """w (n, D+1, 256); azim, elev (n, 2, 1) -> thumbs (n*2, 3, S, S), differentiable."""
@@ -70,26 +114,38 @@ class FlipInversion:
         multi_rank = self.shared_latent and torch.distributed.is_available() and torch.distributed.is_initialized()
         if cuda_graph and multi_rank:
             raise ValueError("cuda_graph=True cannot be combined with a latent shared across ranks")
-        if cuda_graph:                                               # learning rates live on the device
-            lr_w, lr_c = torch.zeros((), device=dev), torch.zeros((), device=dev)
-            opt_w = torch.optim.Adam([w], betas=(0.9, 0.999), lr=lr_w, capturable=True)
-            opt_c = torch.optim.Adam([azim, elev], betas=(0.9, 0.999), lr=lr_c, capturable=True)
+        if host_targets is not None and cuda_graph:
+            raise ValueError("host_targets is an eager-mode option")
+        fused = self.fused_update and dev.type == "cuda"
+        device_lr = fused or cuda_graph                              # learning rates live on the device
+        if fused:
+            upd = _FusedClipAdam([[w], [azim, elev]], betas=(0.9, 0.999), max_norm=self.clip)
+            lr_dev = upd.lr
+        elif cuda_graph:
+            lr_dev = torch.zeros(2, device=dev)
+            opt_w = torch.optim.Adam([w], betas=(0.9, 0.999), lr=lr_dev[0], capturable=True)
+            opt_c = torch.optim.Adam([azim, elev], betas=(0.9, 0.999), lr=lr_dev[1], capturable=True)
         else:
             opt_w = torch.optim.Adam([w], betas=(0.9, 0.999), lr=self.lr_latent)
             opt_c = torch.optim.Adam([azim, elev], betas=(0.9, 0.999), lr=self.lr_cam)
+        if device_lr:
+            lrs = torch.tensor([[lr_ramp(s, self.num_steps, l0) for l0 in (self.lr_latent, self.lr_cam)]
+                                for s in range(self.num_steps)], dtype=torch.float32).to(dev)
 
         def one_step():
             thumbs = self.render_thumbs(w.expand(n, -1, -1) if self.shared_latent else w, azim, elev)
             loss = self.loss_fn(thumbs, tgt)
-            opt_w.zero_grad(set_to_none=True)
-            opt_c.zero_grad(set_to_none=True)
+            w.grad = azim.grad = elev.grad = None
             loss.backward()
             if multi_rank:
                 c3d_dist.allreduce_grads([w.grad])
-            torch.nn.utils.clip_grad_norm_([w], self.clip)
-            torch.nn.utils.clip_grad_norm_([azim, elev], self.clip)
-            opt_w.step()
-            opt_c.step()
+            if fused:
+                upd.step()                                           # both clippings + both Adam updates: one launch
+            else:
+                torch.nn.utils.clip_grad_norm_([w], self.clip)
+                torch.nn.utils.clip_grad_norm_([azim, elev], self.clip)
+                opt_w.step()
+                opt_c.step()
             return loss.detach()
 
         losses = []
@@ -100,40 +156,34 @@ class FlipInversion:
                 for _ in range(2):
                     one_step()
             torch.cuda.current_stream(dev).wait_stream(side)
-            for opt in (opt_w, opt_c):                               # forget the warm-up in the Adam moments
-                for st in opt.state.values():
-                    for v in st.values():
-                        if torch.is_tensor(v):
-                            v.zero_()
+            if fused:                                                # forget the warm-up in the Adam moments
+                upd.reset()
+            else:
+                for opt in (opt_w, opt_c):
+                    for st in opt.state.values():
+                        for v in st.values():
+                            if torch.is_tensor(v):
+                                v.zero_()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 loss_static = one_step()
-            lrs = torch.tensor([[lr_ramp(s, self.num_steps, l0) for l0 in (self.lr_latent, self.lr_cam)]
-                                for s in range(self.num_steps)], dtype=torch.float32).to(dev)
-            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            ev[0].record()
-            for step in range(self.num_steps):
-                lr_w.copy_(lrs[step, 0])
-                lr_c.copy_(lrs[step, 1])
-                graph.replay()
-                losses.append(loss_static.clone())
-                if callback is not None:
-                    callback(step, losses[-1])
-            ev[1].record()
-            return dict(w=w.detach(), azim=azim.detach(), elev=elev.detach(), losses=torch.stack(losses), events=ev)
-
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
-        if host_targets is not None and cuda_graph:
-            raise ValueError("host_targets is an eager-mode option")
         for step in range(self.num_steps):
-            for opt, lr0 in ((opt_w, self.lr_latent), (opt_c, self.lr_cam)):
-                for g in opt.param_groups:
-                    g["lr"] = lr_ramp(step, self.num_steps, lr0)
+            if device_lr:
+                lr_dev.copy_(lrs[step])
+            else:
+                for opt, lr0 in ((opt_w, self.lr_latent), (opt_c, self.lr_cam)):
+                    for g in opt.param_groups:
+                        g["lr"] = lr_ramp(step, self.num_steps, lr0)
             if host_targets is not None:
                 t = host_targets.to(dev, non_blocking=True)
                 tgt.copy_(torch.stack([t, t.flip(-1)], 1).reshape(tgt.shape))
-            losses.append(one_step())
+            if cuda_graph:
+                graph.replay()
+                losses.append(loss_static.clone())
+            else:
+                losses.append(one_step())
             if host_targets is not None:
                 losses[-1].item()                                    # device -> host read of the step's result
             if callback is not None:

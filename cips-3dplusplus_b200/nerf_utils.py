@@ -199,6 +199,37 @@ class Render:
         return out
 
 
+class _CameraFn(torch.autograd.Function):
+    """(azim, elev) -> camera-to-world poses in one launch (c3d_camera_params); the kernel also returns the Jacobian
+    d pose / d (azim, elev) by forward-mode differentiation, so the backward is a 12x2 contraction per camera."""
+
+    @staticmethod
+    def forward(ctx, azim, elev, img_size, fov, dist_radius):
+        lib = _abi.load()
+        n, dev = azim.numel(), azim.device
+        f = dict(dtype=torch.float32, device=dev)
+        az, el = _c(azim, n), _c(elev, n)
+        pose, jac = torch.empty(n, 3, 4, **f), torch.empty(n, 12, 2, **f)
+        focal, near, far = torch.empty(n, 1, 1, **f), torch.empty(n, 1, 1, **f), torch.empty(n, 1, 1, **f)
+        fov_t = _c(fov, n) if torch.is_tensor(fov) else None
+        with torch.cuda.device(dev):
+            _abi.check(lib.c3d_camera_params(az.data_ptr(), el.data_ptr(), n, int(img_size),
+                                             None if fov_t is None else fov_t.data_ptr(),
+                                             0.0 if fov_t is not None else float(fov), float(dist_radius), pose.data_ptr(),
+                                             focal.data_ptr(), near.data_ptr(), far.data_ptr(), jac.data_ptr(), _stream()),
+                       "c3d_camera_params")
+        ctx.save_for_backward(jac)
+        ctx.shapes = (azim.shape, elev.shape)
+        ctx.mark_non_differentiable(focal, near, far)
+        return pose, focal, near, far
+
+    @staticmethod
+    def backward(ctx, g_pose, g_focal, g_near, g_far):
+        (jac,) = ctx.saved_tensors
+        g = torch.einsum("nk,nkj->nj", g_pose.reshape(-1, 12).to(torch.float32), jac)
+        return g[:, 0].reshape(ctx.shapes[0]), g[:, 1].reshape(ctx.shapes[1]), None, None, None
+
+
 class Camera:
     @staticmethod
     def generate_camera_params(img_size, device, batch=1, locations=None, sweep=False, uniform=False,
@@ -214,6 +245,12 @@ class Camera:
         if locations is not None:
             azim, elev = locations[:, 0:1], locations[:, 1:2]
             n = azim.shape[0]
+            if locations.device.type == "cuda" and up is None and not (torch.is_tensor(fov_ang) and fov_ang.requires_grad):
+                # one launch instead of ~35 (and ~60 more in its autograd): what keeps small inversion batches from being
+                # launch-bound; same values as the PyTorch glue below, which stays the path for CPU tensors / custom `up`
+                fov = fov_ang.to(locations.device).reshape(-1).expand(n) if torch.is_tensor(fov_ang) else fov_ang
+                pose, focal, near, far = _CameraFn.apply(azim, elev, img_size, fov, dist_radius)
+                return pose, focal, near, far, torch.cat([azim, elev], 1)
         elif sweep:
             (a0, a1), (e0, e1) = rng(azim_range), rng(elev_range)
             azim = (a0 + (a1 - a0) / 7 * torch.arange(8, device=device)).view(-1, 1).repeat(batch, 1)

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define C3D_ABI_VERSION 7
+#define C3D_ABI_VERSION 8
 #define C3D_MAX_LAYERS 16
 #define C3D_W 256
 
@@ -237,6 +237,33 @@ int c3d_composite_backward(const c3d_composite_params* p, c3d_stream_t stream);
 
 /* Inverse-CDF importance resampling; at least one output must be non-NULL.  One kernel launch. */
 int c3d_sample_pdf(const c3d_resample_params* p, c3d_stream_t stream);
+
+/* ---- flip-inversion driver helpers (projector_v9.py:998-1166): keep the optimisation step from being launch-bound ---- */
+
+/* Camera.generate_camera_params, `locations` mode (nerf_utils.py:369-378, 412-436): azim / elev (n) -> cam_poses (n,3,4),
+ * focal / near / far (n); fov_ang: device (n) degrees, or NULL to use fov_scalar.  jac (n,12,2) or NULL receives
+ * d cam_poses / d (azim, elev) (forward-mode), so the backward is a 12x2 contraction per camera.  One launch. */
+int c3d_camera_params(const float* azim, const float* elev, int32_t n, int32_t img_size, const float* fov_ang, float fov_scalar,
+                      float dist_radius, float* cam_poses, float* focal, float* near, float* far, float* jac,
+                      c3d_stream_t stream);
+
+/* torch.nn.utils.clip_grad_norm_ + torch.optim.Adam (defaults: no weight decay, no amsgrad) for up to 8 small fp32 tensors in
+ * two groups (group 0: latents, group 1: cameras; each with its own gradient-norm clipping and its own learning rate), one
+ * launch.  lr: two DEVICE scalars; step: DEVICE scalar counting the updates done so far (incremented by the call). */
+typedef struct c3d_adam_params {
+  int32_t n_tensors;                     /* 1..8 */
+  int32_t group[8];                      /* 0 or 1 */
+  int64_t numel[8];
+  float* param[8];
+  const float* grad[8];
+  float* exp_avg[8];
+  float* exp_avg_sq[8];
+  const float* lr[2];
+  float* step;
+  float beta1, beta2, eps, max_norm;     /* max_norm <= 0: no clipping */
+  float* grad_norm;                      /* optional (2): gradient norms of the groups before clipping, or NULL */
+} c3d_adam_params;
+int c3d_adam_clip_step(const c3d_adam_params* p, c3d_stream_t stream);
 
 /* Launch statistics of the most recent c3d_nerf_forward on this thread (kernel launches it made). */
 int c3d_last_launch_count(void);

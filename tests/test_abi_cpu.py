@@ -48,6 +48,7 @@ def test_struct_sizes_match_header(lib):
     assert ctypes.sizeof(a.ParamGrads) == ctypes.sizeof(a.RawParams) - 8
     assert ctypes.sizeof(a.RaygenParams) == 4 * 4 + 9 * 8
     assert ctypes.sizeof(a.CompositeParams) == 8 + 4 + 4 + 4 + 4 + 22 * 8
+    assert ctypes.sizeof(a.AdamParams) == 4 + 8 * 4 + 4 + 8 * 8 * 5 + 2 * 8 + 8 + 4 * 4 + 8   # int32[9] padded to 40, then 8-byte members
 
 
 def test_argument_validation_without_gpu(lib):
