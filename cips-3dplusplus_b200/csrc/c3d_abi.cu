@@ -128,7 +128,7 @@ static int launch_style_prep(const void* packed, int D, const float* styles, int
                              float* view, cudaStream_t st) {
   const PackedLayout L = packed_layout(D);
   dim3 grid(D + 1, (batch + SP_IMGS - 1) / SP_IMGS);
-  style_prep_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(packed), L, styles, batch,
+  style_prep_kernel<<<grid, SP_THREADS, 0, st>>>(reinterpret_cast<const uint8_t*>(packed), L, styles, batch,
                                           reinterpret_cast<float2*>(film), reinterpret_cast<float4*>(first),
                                           reinterpret_cast<float4*>(view));
   C3D_LAUNCH_CHECK();

@@ -130,14 +130,17 @@ __global__ void pack_matrix_kernel(c3d_raw_params raw, uint8_t* __restrict__ blo
 // grid (D+1, ceil(b/8)), block 256 (thread = output channel), 8 images per block share the weights.
 // ------------------------------------------------------------------------------------------
 constexpr int SP_IMGS = 8;
-__global__ void __launch_bounds__(256) style_prep_kernel(const uint8_t* __restrict__ blob, PackedLayout L,
-                                                          const float* __restrict__ styles, int batch,
-                                                          float2* __restrict__ film, float4* __restrict__ first,
-                                                          float4* __restrict__ view) {
+constexpr int SP_KSPLIT = 2;                     // the 256-long dot products are split over 2 thread groups: the kernel is
+constexpr int SP_THREADS = W * SP_KSPLIT;        // latency-bound (a 67 us fixed cost of every small-batch call otherwise)
+__global__ void __launch_bounds__(SP_THREADS) style_prep_kernel(const uint8_t* __restrict__ blob, PackedLayout L,
+                                                                 const float* __restrict__ styles, int batch,
+                                                                 float2* __restrict__ film, float4* __restrict__ first,
+                                                                 float4* __restrict__ view) {
   __shared__ float s[SP_IMGS][W];
-  const int l = blockIdx.x, D = L.D, c = threadIdx.x;
+  __shared__ float part[SP_KSPLIT - 1][SP_IMGS][2][W];
+  const int l = blockIdx.x, D = L.D, c = threadIdx.x & (W - 1), ks = threadIdx.x / W;
   const int b0 = blockIdx.y * SP_IMGS;
-  for (int i = 0; i < SP_IMGS; ++i) {
+  for (int i = ks; i < SP_IMGS; i += SP_KSPLIT) {
     const int b = b0 + i;
     s[i][c] = b < batch ? styles[((size_t)b * (D + 1) + l) * W + c] : 0.f;
   }
@@ -148,8 +151,10 @@ __global__ void __launch_bounds__(256) style_prep_kernel(const uint8_t* __restri
   float g[SP_IMGS], be[SP_IMGS];
 #pragma unroll
   for (int i = 0; i < SP_IMGS; ++i) g[i] = be[i] = 0.f;
-#pragma unroll 4
-  for (int k = 0; k < W; ++k) {
+  constexpr int KS = W / SP_KSPLIT;
+#pragma unroll 16
+  for (int kk = 0; kk < KS; ++kk) {
+    const int k = ks * KS + kk;
     const float gw = GwT[(size_t)k * W + c], bw = BwT[(size_t)k * W + c];
 #pragma unroll
     for (int i = 0; i < SP_IMGS; ++i) {
@@ -157,6 +162,16 @@ __global__ void __launch_bounds__(256) style_prep_kernel(const uint8_t* __restri
       be[i] = fmaf(s[i][k], bw, be[i]);
     }
   }
+  if (ks > 0) {
+#pragma unroll
+    for (int i = 0; i < SP_IMGS; ++i) { part[ks - 1][i][0][c] = g[i]; part[ks - 1][i][1][c] = be[i]; }
+  }
+  __syncthreads();
+  if (ks > 0) return;
+#pragma unroll
+  for (int q = 0; q < SP_KSPLIT - 1; ++q)
+#pragma unroll
+    for (int i = 0; i < SP_IMGS; ++i) { g[i] += part[q][i][0][c]; be[i] += part[q][i][1][c]; }
   const float gb = f[2 * W * W + c], bb = f[2 * W * W + W + c];
   const float bias = reinterpret_cast<const float*>(blob + L.bias)[l * W + c];
   const float4 w0 = reinterpret_cast<const float4*>(blob + L.w0)[c];
