@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -81,7 +82,8 @@ class FlipInversion:
         self.cam_cfg = dict(fov_ang=6, dist_radius=0.12) if cam_cfg is None else dict(cam_cfg)
         self.lr_latent, self.lr_cam, self.num_steps = lr_latent, lr_cam, num_steps
         self.loss_fn, self.clip, self.shared_latent, self.static_viewdirs = loss_fn, clip, shared_latent, static_viewdirs
-        self.fused_update = fused_update      # clipping + both Adam updates as one kernel (CUDA tensors); False: torch.optim
+        # clipping + both Adam updates as one kernel (CUDA tensors); False (or C3D_INV_FUSED=0, for A/B runs): torch.optim
+        self.fused_update = fused_update and os.environ.get("C3D_INV_FUSED", "1") != "0"
 
     def render_thumbs(self, w, azim, elev):
         """w (n, D+1, 256); azim, elev (n, 2, 1) -> thumbs (n*2, 3, S, S), differentiable."""
