@@ -375,15 +375,32 @@ __global__ void __launch_bounds__(256) gdot_kernel(const Args a, float* __restri
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   const uint4* f = reinterpret_cast<const uint4*>(a.save_feat + ((size_t)tile_g * 16 + pg) * W * 8);
-  for (int c = lane; c < W; c += 32) {
-    const uint4 fv = __ldcs(f + c);
-    const uint32_t fw[4] = {fv.x, fv.y, fv.z, fv.w};
+  const int ray_first = q0 / N, ray_last = min(q0 + 7, npts - 1) / N;
+  if (ray_first == ray_last) {
+    // the group's 8 points lie on one ray (always when N % 8 == 0): its cotangent row is read once per channel
+    const float* grow = a.g_feature_map + ((size_t)img * a.n_rays + r0 + ray_first) * W;
+    uint4 fv[W / 32];
+    float gv[W / 32];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int q = min(q0 + i, npts - 1);
-      const float g = a.g_feature_map[((size_t)img * a.n_rays + r0 + q / N) * W + c];
-      const float x = (i & 1) ? fusedbwd::bf16_hi(fw[i >> 1]) : fusedbwd::bf16_lo(fw[i >> 1]);
-      acc[i] = fmaf(g, x, acc[i]);
+    for (int j = 0; j < W / 32; ++j) { fv[j] = __ldcs(f + lane + 32 * j); gv[j] = grow[lane + 32 * j]; }
+#pragma unroll
+    for (int j = 0; j < W / 32; ++j) {
+      const uint32_t fw[4] = {fv[j].x, fv[j].y, fv[j].z, fv[j].w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        acc[i] = fmaf(gv[j], (i & 1) ? fusedbwd::bf16_hi(fw[i >> 1]) : fusedbwd::bf16_lo(fw[i >> 1]), acc[i]);
+    }
+  } else {
+    for (int c = lane; c < W; c += 32) {
+      const uint4 fv = __ldcs(f + c);
+      const uint32_t fw[4] = {fv.x, fv.y, fv.z, fv.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int q = min(q0 + i, npts - 1);
+        const float g = a.g_feature_map[((size_t)img * a.n_rays + r0 + q / N) * W + c];
+        const float x = (i & 1) ? fusedbwd::bf16_hi(fw[i >> 1]) : fusedbwd::bf16_lo(fw[i >> 1]);
+        acc[i] = fmaf(g, x, acc[i]);
+      }
     }
   }
 #pragma unroll
