@@ -284,8 +284,8 @@ static int forward_fp32(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
       rg.ray_offset = p->ray_offset ? p->ray_offset + (size_t)i0 * R : nullptr;
       rg.pts = reinterpret_cast<float*>(ck + w.c_pts); rg.rays_d = reinterpret_cast<float*>(ck + w.c_rd);
       rg.viewdirs = reinterpret_cast<float*>(ck + w.c_vd); rg.z_vals = reinterpret_cast<float*>(ck + w.c_z);
-      const long long n = (long long)ni * R;
-      raygen_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(rg);
+      const long long n = (long long)ni * R * p->n_samples;
+      raygen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rg);
       C3D_LAUNCH_CHECK();
       pts = rg.pts; rays_d = rg.rays_d; viewdirs = rg.viewdirs; z_vals = rg.z_vals;
       if (p->z_vals_out)
@@ -401,8 +401,9 @@ int c3d_nerf_forward(const c3d_fwd_params* p, c3d_stream_t stream) {
 int c3d_raygen(const c3d_raygen_params* p, c3d_stream_t stream) {
   C3D_CHECK_ARG(p && p->batch >= 1 && p->img_size >= 1 && p->n_samples >= 2, "bad raygen sizes");
   C3D_CHECK_ARG(p->cam_poses && p->focal && p->near && p->far, "cam_poses/focal/near/far must be non-NULL");
-  const long long n = (long long)p->batch * p->img_size * p->img_size;
-  raygen_kernel<<<(unsigned)((n + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*p);
+  const long long n = (long long)p->batch * p->img_size * p->img_size * p->n_samples;
+  C3D_CHECK_ARG(n < (1ll << 39), "too many sample points");
+  raygen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*p);
   C3D_LAUNCH_CHECK();
   return C3D_OK;
 }
@@ -762,8 +763,8 @@ static int backward_simt(const c3d_bwd_params* bp, cudaStream_t st) {
       rg.ray_offset = p->ray_offset ? p->ray_offset + (size_t)i0 * R : nullptr;
       rg.pts = reinterpret_cast<float*>(ck + w.c_pts); rg.rays_d = reinterpret_cast<float*>(ck + w.c_rd);
       rg.viewdirs = reinterpret_cast<float*>(ck + w.c_vd); rg.z_vals = reinterpret_cast<float*>(ck + w.c_z);
-      const long long n = (long long)ni * R;
-      raygen_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(rg);
+      const long long n = (long long)ni * R * p->n_samples;
+      raygen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rg);
       C3D_LAUNCH_CHECK();
       pts = rg.pts; rays_d = rg.rays_d; viewdirs = rg.viewdirs; z_vals = rg.z_vals;
     } else {
@@ -910,8 +911,8 @@ static int backward_tc(const c3d_bwd_params* bp, cudaStream_t st, int phases) {
       rg.pts = reinterpret_cast<float*>(ck + w.c_pts); rg.rays_d = reinterpret_cast<float*>(ck + w.c_rd);
       rg.viewdirs = reinterpret_cast<float*>(ck + w.c_vd); rg.z_vals = reinterpret_cast<float*>(ck + w.c_z);
       if (phases & 1) {
-        const long long n = (long long)ni * R;
-        raygen_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(rg);
+        const long long n = (long long)ni * R * p->n_samples;
+        raygen_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rg);
         C3D_LAUNCH_CHECK();
       }
       q.pts = rg.pts; q.rays_d = rg.rays_d; q.viewdirs = rg.viewdirs; q.z_vals = rg.z_vals;

@@ -123,26 +123,30 @@ __device__ __forceinline__ RayGeom make_ray(const float* __restrict__ pose /*3x4
   const float cy = -((float)iy + 0.5f - half) / focal;
   const float cz = -1.0f;
   RayGeom r;
-  r.dx = cx * pose[0] + cy * pose[1] + cz * pose[2];
-  r.dy = cx * pose[4] + cy * pose[5] + cz * pose[6];
-  r.dz = cx * pose[8] + cy * pose[9] + cz * pose[10];
+  // products and sums rounded separately, as (d_cam * R).sum(-1) rounds them (nerf_utils.py:49), and -- being explicit --
+  // identically in every kernel that inlines this function (no compiler-chosen FMA contraction)
+  r.dx = __fadd_rn(__fadd_rn(__fmul_rn(cx, pose[0]), __fmul_rn(cy, pose[1])), __fmul_rn(cz, pose[2]));
+  r.dy = __fadd_rn(__fadd_rn(__fmul_rn(cx, pose[4]), __fmul_rn(cy, pose[5])), __fmul_rn(cz, pose[6]));
+  r.dz = __fadd_rn(__fadd_rn(__fmul_rn(cx, pose[8]), __fmul_rn(cy, pose[9])), __fmul_rn(cz, pose[10]));
   r.ox = pose[3]; r.oy = pose[7]; r.oz = pose[11];
-  r.dnorm = sqrtf(r.dx * r.dx + r.dy * r.dy + r.dz * r.dz);
+  r.dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(r.dx, r.dx), __fmul_rn(r.dy, r.dy)), __fmul_rn(r.dz, r.dz)));
   float sx = static_viewdirs ? cx : r.dx, sy = static_viewdirs ? cy : r.dy, sz = static_viewdirs ? cz : r.dz;
-  float n = sqrtf(sx * sx + sy * sy + sz * sz);
+  float n = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(sx, sx), __fmul_rn(sy, sy)), __fmul_rn(sz, sz)));
   float inv = 1.0f / fmaxf(n, 1e-12f);
   r.vx = sx * inv; r.vy = sy * inv; r.vz = sz * inv;
   return r;
 }
 // sample depth k of N (nerf_utils.py:97-119, offset sampling): near*(1-t)+far*t (+ u*(far-near)/N)
 __device__ __forceinline__ float sample_depth(float near, float far, int k, int N, float u) {
-  const float t = (float)k * ((1.0f - 1.0f / (float)N) / (float)(N - 1 > 0 ? N - 1 : 1));
-  const float z = near * (1.0f - t) + far * t;
+  // explicit, separately rounded operations: the same depth in every kernel, rounded as the reference's tensor ops round it
+  const float step = (1.0f - 1.0f / (float)N) / (float)(N - 1 > 0 ? N - 1 : 1);
+  const float t = __fmul_rn((float)k, step);
+  const float z = __fadd_rn(__fmul_rn(near, 1.0f - t), __fmul_rn(far, t));
   if (u == 0.0f) return z;
   // perturb: lower + (upper-lower)*u with upper = z_{k+1} (far for the last sample)
-  const float t1 = (float)(k + 1) * ((1.0f - 1.0f / (float)N) / (float)(N - 1 > 0 ? N - 1 : 1));
-  const float zu = (k + 1 < N) ? near * (1.0f - t1) + far * t1 : far;
-  return z + (zu - z) * u;
+  const float t1 = __fmul_rn((float)(k + 1), step);
+  const float zu = (k + 1 < N) ? __fadd_rn(__fmul_rn(near, 1.0f - t1), __fmul_rn(far, t1)) : far;
+  return __fadd_rn(z, __fmul_rn(zu - z, u));
 }
 
 }  // namespace c3d

@@ -249,26 +249,28 @@ __global__ void __launch_bounds__(256) film_k16_kernel(const uint8_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------
-// raygen: Render.prepare_nerf_inputs (nerf_utils.py:172-218); thread per ray.
+// raygen: Render.prepare_nerf_inputs (nerf_utils.py:172-218); thread per sample point, so the (b,hw,N,3) / (b,hw,N)
+// writes of a warp are contiguous (a thread per ray would write 12 N-byte runs 12 N bytes apart).
 // ------------------------------------------------------------------------------------------
-__global__ void raygen_kernel(c3d_raygen_params p) {
-  const int hw = p.img_size * p.img_size;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (long long)p.batch * hw) return;
+__global__ void __launch_bounds__(256) raygen_kernel(c3d_raygen_params p) {
+  const int hw = p.img_size * p.img_size, N = p.n_samples;
+  const long long total = (long long)p.batch * hw * N;
+  const long long pid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pid >= total) return;
+  const long long gid = pid / N;                       // ray index over the batch
+  const int k = (int)(pid - gid * N);
   const int b = (int)(gid / hw), ray = (int)(gid - (long long)b * hw);
   const RayGeom r = make_ray(p.cam_poses + (size_t)b * 12, p.focal[b], p.img_size, ray, p.static_viewdirs != 0);
-  const float near = p.near[b], far = p.far[b];
   const float u = p.ray_offset ? p.ray_offset[gid] : 0.f;
-  if (p.rays_d) { float* o = p.rays_d + gid * 3; o[0] = r.dx; o[1] = r.dy; o[2] = r.dz; }
-  if (p.viewdirs) { float* o = p.viewdirs + gid * 3; o[0] = r.vx; o[1] = r.vy; o[2] = r.vz; }
-  const int N = p.n_samples;
-  for (int k = 0; k < N; ++k) {
-    const float z = sample_depth(near, far, k, N, u);
-    if (p.z_vals) p.z_vals[gid * N + k] = z;
-    if (p.pts) {
-      float* o = p.pts + (gid * N + k) * 3;
-      o[0] = fmaf(r.dx, z, r.ox); o[1] = fmaf(r.dy, z, r.oy); o[2] = fmaf(r.dz, z, r.oz);
-    }
+  if (k == 0) {
+    if (p.rays_d) { float* o = p.rays_d + gid * 3; o[0] = r.dx; o[1] = r.dy; o[2] = r.dz; }
+    if (p.viewdirs) { float* o = p.viewdirs + gid * 3; o[0] = r.vx; o[1] = r.vy; o[2] = r.vz; }
+  }
+  const float z = sample_depth(p.near[b], p.far[b], k, N, u);
+  if (p.z_vals) p.z_vals[pid] = z;
+  if (p.pts) {
+    float* o = p.pts + pid * 3;
+    o[0] = fmaf(r.dx, z, r.ox); o[1] = fmaf(r.dy, z, r.oy); o[2] = fmaf(r.dz, z, r.oz);
   }
 }
 
