@@ -155,8 +155,8 @@ def run_reference(args, cfg, rank, world):
 def run_inversion(args, cfg, rank, world, local_rank):
     """--config c5: one JSON line for the flip-inversion step (cips3dpp_b200.FlipInversion, stage 1 of projector_v9.py:
     862-1166).  value = rays/s through forward + backward + optimiser with targets resident (whole step replayed as a CUDA
-    graph, CUDA events around the replay loop); e2e = eager steps that copy the targets host -> device and read the loss
-    back every step; roofline = algorithmic 2 F FLOPs (forward + input-gradient GEMMs) of the step / its time."""
+    graph, CUDA events around the replay loop); e2e = the same loop with the targets copied pinned host -> device before and
+    the loss copied back to pinned host memory after every step; roofline = algorithmic 2 F FLOPs (forward + input-gradient GEMMs) of the step / its time."""
     import torch
     import torch.distributed as dist
     import cips3dpp_b200 as c3d
@@ -181,7 +181,7 @@ def run_inversion(args, cfg, rank, world, local_rank):
     th = inv.render_thumbs(wq, aq, aq.detach().clone().requires_grad_(True))
     launches = m.last_launch_count
     th.sum().backward()
-    launches += m.last_launch_count
+    launches += m.last_launch_count + 2                                    # + c3d_camera_params, c3d_adam_clip_step
     inv.num_steps = args.steps
 
     def sync():
@@ -196,7 +196,7 @@ def run_inversion(args, cfg, rank, world, local_rank):
     sampler.stop_flag = True
     sampler.join(timeout=2)
     ms_step = r["events"][0].elapsed_time(r["events"][1]) / args.steps
-    r2 = inv.run(tgt, w0, host_targets=host_t)
+    r2 = inv.run(tgt, w0, cuda_graph=True, host_targets=host_t)
     sync()
     ms_e2e = r2["events"][0].elapsed_time(r2["events"][1]) / args.steps
     if world > 1:

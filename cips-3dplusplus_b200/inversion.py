@@ -105,8 +105,9 @@ class FlipInversion:
         written from the host between replays.  It needs frozen renderer weights, a capturable `loss_fn`, and is
         refused together with a cross-rank shared latent (the all-reduce stays outside graphs).
 
-        `host_targets` (pinned host tensor shaped like `targets`, eager mode only) makes every step end to end: the step's
-        targets are copied host -> device and its loss is read back to the host (what bench.py's `e2e` times)."""
+        `host_targets` (pinned host tensor shaped like `targets`) makes every step end to end: the step's targets are
+        copied host -> device before it and its loss is copied back to (pinned) host memory after it -- asynchronously on
+        the same stream, so the loop still never waits for the host (what bench.py's `e2e` times)."""
         dev, n = targets.device, targets.shape[0]
         tgt = torch.stack([targets, targets.flip(-1)], 1).reshape(n * 2, *targets.shape[1:])
         nw = 1 if self.shared_latent else n
@@ -116,8 +117,6 @@ class FlipInversion:
         multi_rank = self.shared_latent and torch.distributed.is_available() and torch.distributed.is_initialized()
         if cuda_graph and multi_rank:
             raise ValueError("cuda_graph=True cannot be combined with a latent shared across ranks")
-        if host_targets is not None and cuda_graph:
-            raise ValueError("host_targets is an eager-mode option")
         fused = self.fused_update and dev.type == "cuda"
         device_lr = fused or cuda_graph                              # learning rates live on the device
         if fused:
@@ -169,6 +168,8 @@ class FlipInversion:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 loss_static = one_step()
+        if host_targets is not None:
+            losses_host = torch.empty(self.num_steps, dtype=torch.float32).pin_memory()
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
         for step in range(self.num_steps):
@@ -186,8 +187,8 @@ class FlipInversion:
                 losses.append(loss_static.clone())
             else:
                 losses.append(one_step())
-            if host_targets is not None:
-                losses[-1].item()                                    # device -> host read of the step's result
+            if host_targets is not None:                             # device -> host read of the step's result
+                losses_host[step:step + 1].copy_(losses[-1].reshape(1), non_blocking=True)
             if callback is not None:
                 callback(step, losses[-1])
         ev[1].record()
