@@ -59,9 +59,12 @@ class RaygenParams(C.Structure):
         [(n, _fp) for n in ("cam_poses", "focal", "near", "far", "ray_offset", "pts", "rays_d", "viewdirs", "z_vals")]
 
 
+COMPOSITE_RAW_DENSITY, COMPOSITE_FORCE_BACKGROUND = 1, 2
+
+
 class CompositeParams(C.Structure):
     _fields_ = [("n_rays", C.c_int64), ("n_samples", C.c_int32), ("n_feat", C.c_int32),
-                ("sigmoid_beta", C.c_float), ("_pad", C.c_int32)] + \
+                ("sigmoid_beta", C.c_float), ("flags", C.c_int32)] + \
         [(n, _fp) for n in ("sigmoid_beta_ptr", "rgb", "sdf", "features", "z_vals", "rays_d", "pts",
                             "rgb_map", "feature_map", "xyz", "mask", "weights",
                             "g_rgb_map", "g_feature_map", "g_xyz", "g_mask",

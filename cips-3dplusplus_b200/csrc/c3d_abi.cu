@@ -416,7 +416,8 @@ int c3d_composite_forward(const c3d_composite_params* p, c3d_stream_t stream) {
   C3D_CHECK_ARG(p->rgb_map && p->xyz && p->mask, "rgb_map/xyz/mask outputs must be non-NULL");
   C3D_CHECK_ARG(!p->features || p->feature_map, "feature_map output missing");
   C3D_CHECK_ARG(aligned16(p->features) && aligned16(p->feature_map), "features must be 16-byte aligned");
-  C3D_CHECK_ARG(p->sigmoid_beta_ptr || p->sigmoid_beta > 0.f, "sigmoid_beta must be > 0");
+  C3D_CHECK_ARG((p->flags & ~3) == 0, "unknown composite flags 0x%x", p->flags);
+  C3D_CHECK_ARG((p->flags & C3D_COMPOSITE_RAW_DENSITY) || p->sigmoid_beta_ptr || p->sigmoid_beta > 0.f, "sigmoid_beta must be > 0");
   composite_fwd_kernel<<<(unsigned)((p->n_rays + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*p);
   C3D_LAUNCH_CHECK();
   return C3D_OK;
@@ -1172,6 +1173,7 @@ int c3d_composite_backward(const c3d_composite_params* p, c3d_stream_t stream) {
   C3D_CHECK_ARG(p->n_samples >= 1 && p->n_samples <= CMP_MAX_N, "n_samples=%d outside [1,%d]", p->n_samples, CMP_MAX_N);
   C3D_CHECK_ARG(p->n_feat >= 0 && p->n_feat % 4 == 0, "n_feat=%d must be a multiple of 4", p->n_feat);
   C3D_CHECK_ARG(p->rgb && p->sdf && p->z_vals && p->rays_d && p->pts, "rgb/sdf/z_vals/rays_d/pts must be non-NULL");
+  C3D_CHECK_ARG(p->flags == 0, "composite backward covers the with_sdf=True branch only (flags must be 0)");
   C3D_CHECK_ARG(p->sigmoid_beta_ptr, "composite backward needs sigmoid_beta_ptr (device scalar)");
   C3D_CHECK_ARG(p->weights && p->g_rgb && p->g_sdf && p->g_pts && p->g_rays_d, "weights/g_rgb/g_sdf/g_pts/g_rays_d outputs are required");
   C3D_CHECK_ARG(!p->features || !p->g_feature_map || p->g_features, "g_features output missing");

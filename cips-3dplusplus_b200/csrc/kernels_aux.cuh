@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(c3d_composite_params
   const long long ray = (long long)blockIdx.x * 8 + warp;
   if (ray >= p.n_rays) return;
   const int N = p.n_samples;
+  const bool raw_density = (p.flags & C3D_COMPOSITE_RAW_DENSITY) != 0;     // with_sdf=False branch (nerf_utils.py:288-296)
   const float beta = p.sigmoid_beta_ptr ? *p.sigmoid_beta_ptr : p.sigmoid_beta;
   const float inv_beta = 1.0f / beta;
   const float* rd = p.rays_d + ray * 3;
@@ -315,30 +316,48 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(c3d_composite_params
   const float* z = p.z_vals + ray * N;
   const float* sdf = p.sdf + ray * N;
   float carry = 1.0f;
-  float a_rgb0 = 0.f, a_rgb1 = 0.f, a_rgb2 = 0.f, a_x = 0.f, a_y = 0.f, a_z = 0.f, w_last = 0.f;
+  // ---- pass 1: weights w_k = alpha_k T_k into shared memory
+  float wsum_head = 0.f;                                                    // sum of w_0 .. w_{N-2} (force_background)
   for (int k0 = 0; k0 < N; k0 += 32) {
     const int k = k0 + lane;
-    float one_minus = 1.0f, w = 0.f, alpha = 0.f;
+    float one_minus = 1.0f, alpha = 0.f;
     if (k < N) {
       const float dist = (k + 1 < N ? z[k + 1] - z[k] : 1e10f) * dnorm;
-      alpha = alpha_from_sdf<true>(sdf[k], inv_beta, dist);
+      if (raw_density) {
+        const float x = sdf[k];                                             // raw sigma (+ noise, added by the caller)
+        const float sp = x > 20.0f ? x : log1pf(expf(x));                   // F.softplus (threshold 20)
+        alpha = 1.0f - expf(-sp * dist);
+      } else {
+        alpha = alpha_from_sdf<true>(sdf[k], inv_beta, dist);
+      }
       one_minus = 1.0f - alpha + 1e-10f;
     }
     float total;
     const float T = carry * warp_excl_prod(one_minus, lane, total);
     carry *= total;
     if (k < N) {
-      w = alpha * T;
+      const float w = alpha * T;
       s_w[warp][k] = w;
-      if (p.weights) p.weights[ray * N + k] = w;
-      const float* c = p.rgb + (ray * N + k) * 3;
-      a_rgb0 = fmaf(w, sigmoid_precise(c[0]), a_rgb0);
-      a_rgb1 = fmaf(w, sigmoid_precise(c[1]), a_rgb1);
-      a_rgb2 = fmaf(w, sigmoid_precise(c[2]), a_rgb2);
-      const float* q = p.pts + (ray * N + k) * 3;
-      a_x = fmaf(w, q[0], a_x); a_y = fmaf(w, q[1], a_y); a_z = fmaf(w, q[2], a_z);
-      if (k == N - 1) w_last = w;
+      if (k < N - 1) wsum_head += w;
     }
+  }
+  if (p.flags & C3D_COMPOSITE_FORCE_BACKGROUND) {                           // weights[..., -1] = 1 - sum(weights[..., :-1])
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wsum_head += __shfl_xor_sync(0xffffffffu, wsum_head, o);
+    if (lane == 0) s_w[warp][N - 1] = 1.0f - wsum_head;
+  }
+  __syncwarp();
+  // ---- pass 2: weighted sums of sigmoid(rgb) and of the points
+  float a_rgb0 = 0.f, a_rgb1 = 0.f, a_rgb2 = 0.f, a_x = 0.f, a_y = 0.f, a_z = 0.f;
+  for (int k = lane; k < N; k += 32) {
+    const float w = s_w[warp][k];
+    if (p.weights) p.weights[ray * N + k] = w;
+    const float* c = p.rgb + (ray * N + k) * 3;
+    a_rgb0 = fmaf(w, sigmoid_precise(c[0]), a_rgb0);
+    a_rgb1 = fmaf(w, sigmoid_precise(c[1]), a_rgb1);
+    a_rgb2 = fmaf(w, sigmoid_precise(c[2]), a_rgb2);
+    const float* q = p.pts + (ray * N + k) * 3;
+    a_x = fmaf(w, q[0], a_x); a_y = fmaf(w, q[1], a_y); a_z = fmaf(w, q[2], a_z);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -348,14 +367,13 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(c3d_composite_params
     a_x += __shfl_xor_sync(0xffffffffu, a_x, o);
     a_y += __shfl_xor_sync(0xffffffffu, a_y, o);
     a_z += __shfl_xor_sync(0xffffffffu, a_z, o);
-    w_last += __shfl_xor_sync(0xffffffffu, w_last, o);
   }
   if (lane == 0) {
     float* o = p.rgb_map + ray * 3;
     o[0] = -1.0f + 2.0f * a_rgb0; o[1] = -1.0f + 2.0f * a_rgb1; o[2] = -1.0f + 2.0f * a_rgb2;
     float* x = p.xyz + ray * 3;
     x[0] = a_x; x[1] = a_y; x[2] = a_z;
-    p.mask[ray * 2 + 0] = w_last;
+    p.mask[ray * 2 + 0] = s_w[warp][N - 1];
     p.mask[ray * 2 + 1] = -sqrtf(a_x * a_x + a_y * a_y + a_z * a_z);
   }
   __syncwarp();

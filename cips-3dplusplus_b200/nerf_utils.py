@@ -99,9 +99,12 @@ class Render:
     @staticmethod
     def volume_integration(rgb, sdf, features, z_vals, rays_d, pts, with_sdf=True, sigmoid_beta=None,
                            return_eikonal=False, raw_noise_std=0.0, force_background=False):
-        """nerf_utils.py:230-338 -> rgb_map, feature_map, xyz, mask, eikonal_term(None)."""
-        if not with_sdf or return_eikonal or raw_noise_std > 0 or force_background:
-            raise NotImplementedError("only the with_sdf=True inference branch used by the v10 configs is provided")
+        """nerf_utils.py:230-338 -> rgb_map, feature_map, xyz, mask, eikonal_term(None).  Forward only (no autograd).
+        `with_sdf=False` takes `sdf` as the raw density (softplus, plus N(0, raw_noise_std) noise when asked);
+        `force_background` puts the remaining weight on the last sample.  For the eikonal term use
+        `NerfBranch.forward(return_eikonal=True)` (or `Render.get_eikonal_term`)."""
+        if return_eikonal:
+            raise NotImplementedError("use NerfBranch.forward(return_eikonal=True) or Render.get_eikonal_term")
         if rgb.device.type != "cuda":
             raise RuntimeError("Render.volume_integration needs CUDA tensors (no CPU fallback)")
         lib = _abi.load()
@@ -115,6 +118,11 @@ class Render:
         feature_map = None if features is None else torch.empty(R, C, **f)
         P = _abi.CompositeParams()
         P.n_rays, P.n_samples, P.n_feat = R, N, C
+        P.flags = (0 if with_sdf else _abi.COMPOSITE_RAW_DENSITY) | (_abi.COMPOSITE_FORCE_BACKGROUND if force_background else 0)
+        if not with_sdf:
+            if raw_noise_std > 0:
+                keep[1] = keep[1] + torch.randn_like(keep[1]) * raw_noise_std        # nerf_utils.py:292-294
+            sigmoid_beta = 1.0 if sigmoid_beta is None else sigmoid_beta            # unused by this branch
         if torch.is_tensor(sigmoid_beta):
             sb = _c(sigmoid_beta, 1)
             keep.append(sb)

@@ -162,15 +162,18 @@ typedef struct c3d_raygen_params {
   float* z_vals;             /* (batch,hw,N) */
 } c3d_raygen_params;
 
+/* the two branches of Render.volume_integration that the v10 configs leave unused (nerf_utils.py:288-296, 309-310) */
+enum { C3D_COMPOSITE_RAW_DENSITY = 1,      /* with_sdf=False: alpha = 1 - exp(-softplus(sigma) * dist) */
+       C3D_COMPOSITE_FORCE_BACKGROUND = 2  /* weights[..., -1] = 1 - sum(weights[..., :-1]) */ };
 typedef struct c3d_composite_params {
   int64_t n_rays;            /* total rays (batch*hw) */
   int32_t n_samples;
   int32_t n_feat;            /* feature channels, multiple of 4, <= 256 (0: no features) */
   float sigmoid_beta;        /* used when sigmoid_beta_ptr == NULL */
-  int32_t _pad;
+  int32_t flags;             /* C3D_COMPOSITE_* (forward only); 0 = the with_sdf=True branch the v10 configs use */
   const float* sigmoid_beta_ptr; /* device scalar or NULL */
   const float* rgb;          /* (n_rays,N,3) raw rgb head output */
-  const float* sdf;          /* (n_rays,N) */
+  const float* sdf;          /* (n_rays,N): sdf, or the raw density (+ noise) with C3D_COMPOSITE_RAW_DENSITY */
   const float* features;     /* (n_rays,N,n_feat) or NULL */
   const float* z_vals;       /* (n_rays,N) */
   const float* rays_d;       /* (n_rays,3) */

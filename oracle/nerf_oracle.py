@@ -195,18 +195,25 @@ def points_forward(params, pts_n, viewdirs_pt, styles):
 # --------------------------------------------------------------------------------------
 # Volume integration  (nerf_utils.py:230-338, with_sdf=True branch)
 # --------------------------------------------------------------------------------------
-def volume_integration(rgb, sdf, features, z_vals, rays_d, pts, sigmoid_beta):
-    """nerf_utils.py:230-338. Shapes (..., n, c) / (..., n) / (..., 3)."""
+def volume_integration(rgb, sdf, features, z_vals, rays_d, pts, sigmoid_beta, with_sdf=True, force_background=False):
+    """nerf_utils.py:230-338. Shapes (..., n, c) / (..., n) / (..., 3).  `with_sdf=False`: `sdf` holds the raw density
+    (softplus branch, :288-296, noise-free); `force_background`: :309-310."""
     rgb, sdf, z_vals, rays_d, pts = map(_f32, (rgb, sdf, z_vals, rays_d, pts))
-    beta = F32(np.asarray(sigmoid_beta, F32).reshape(-1)[0])
     dists = z_vals[..., 1:] - z_vals[..., :-1]
     d_norm = np.sqrt(np.sum(rays_d * rays_d, axis=-1, keepdims=True, dtype=F32), dtype=F32)
     dists = np.concatenate([dists, np.broadcast_to(F32(1e10), d_norm.shape)], -1) * d_norm
-    sigma = sigmoid(-sdf / beta) / beta
+    if with_sdf:
+        beta = F32(np.asarray(sigmoid_beta, F32).reshape(-1)[0])
+        sigma = sigmoid(-sdf / beta) / beta
+    else:
+        sigma = np.where(sdf > F32(20), sdf, np.log1p(np.exp(np.minimum(sdf, F32(20)), dtype=F32), dtype=F32)).astype(F32)
     alpha = (F32(1) - np.exp(-sigma * dists[..., None], dtype=F32)).astype(F32)
     ones = np.ones_like(alpha[..., :1, :])
     vis = np.cumprod(np.concatenate([ones, F32(1) - alpha + F32(1e-10)], axis=-2), axis=-2, dtype=F32)[..., :-1, :]
     weights = (alpha * vis).astype(F32)
+    if force_background:
+        weights = weights.copy()
+        weights[..., -1, :] = F32(1) - np.sum(weights[..., :-1, :], axis=-2, dtype=F32)
     rgb_map = (F32(-1) + F32(2) * np.sum(weights * sigmoid(rgb), axis=-2, dtype=F32)).astype(F32)
     feature_map = None if features is None else np.sum(weights * _f32(features), axis=-2, dtype=F32)
     xyz = np.sum(weights * pts, axis=-2, dtype=F32)

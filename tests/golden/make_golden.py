@@ -15,6 +15,7 @@ Outputs (committed):
   case_*.npz          inputs (256-ray subsets of a 64x64 image) and reference outputs
   camera.npz          Camera.generate_camera_params + prepare_nerf_inputs checks
   camera_v1.npz       `--camera-v1`: Camera.generate_camera_params_v1 with caller-given up vectors
+  volint_modes.npz    `--volint`: Render.volume_integration with with_sdf=False / force_background
   pgrads_*.npz        `--param-grads`: gradients w.r.t. every renderer parameter for the two *_grads cases, computed
                       by the reference's autograd on the committed case inputs / cotangents (fp32; at D=8 the
                       256x256 matrices are kept for layers 1 and 7 only, to bound the fixture size)
@@ -182,6 +183,28 @@ def main():
     camera_v1(nu)
 
 
+def volint_modes(nu=None):
+    """Render.volume_integration in the branches the v10 configs leave unused (with_sdf=False, force_background) ->
+    volint_modes.npz (random inputs, noise-free)."""
+    if nu is None:
+        nu, _ = import_reference()
+    g = torch.Generator().manual_seed(11)
+    R, N, C = 40, 24, 16
+    rgb = torch.randn(R, N, 3, generator=g)
+    raw = torch.randn(R, N, 1, generator=g) * 3.0
+    feat = torch.randn(R, N, C, generator=g)
+    z = torch.sort(0.7 + 0.6 * torch.rand(R, N, generator=g), dim=-1).values
+    rd = torch.randn(R, 3, generator=g)
+    pts = torch.randn(R, N, 3, generator=g)
+    out = {"rgb": rgb, "raw": raw, "features": feat, "z_vals": z, "rays_d": rd, "pts": pts}
+    for tag, kw in (("raw", dict(with_sdf=False)), ("raw_bg", dict(with_sdf=False, force_background=True)),
+                    ("sdf_bg", dict(with_sdf=True, sigmoid_beta=torch.tensor([0.1]), force_background=True))):
+        sdf_in = raw if not kw["with_sdf"] else raw * 0.05
+        r = nu.Render.volume_integration(rgb=rgb, sdf=sdf_in, features=feat, z_vals=z, rays_d=rd, pts=pts, **kw)
+        out.update({f"{tag}_rgb_map": r[0], f"{tag}_feature_map": r[1], f"{tag}_xyz": r[2], f"{tag}_mask": r[3]})
+    np.savez_compressed(os.path.join(HERE, "volint_modes.npz"), **{k: v.numpy() for k, v in out.items()})
+
+
 def camera_v1(nu=None):
     """Camera.generate_camera_params_v1 (caller-given up vector, nerf_utils.py:466-560) -> camera_v1.npz."""
     if nu is None:
@@ -271,5 +294,7 @@ if __name__ == "__main__":
         mlp_init_case()
     elif "--camera-v1" in sys.argv:
         camera_v1()
+    elif "--volint" in sys.argv:
+        volint_modes()
     else:
         main()

@@ -326,3 +326,22 @@ def test_forward_edge_shapes_match_oracle(D, N, R, b, mode, monkeypatch):
         else:
             lim = tol if name != "sdf" or precision == "fp32" else max(tol, 5e-2) * (1 if D <= 8 else 2)
             assert rel_l2(got, want) < lim, (name, rel_l2(got, want))
+
+
+@pytest.mark.parametrize("tag,with_sdf,bg,scale", [("raw", False, False, 1.0), ("raw_bg", False, True, 1.0), ("sdf_bg", True, True, 0.05)])
+def test_composite_unused_branches_match_reference_golden(tag, with_sdf, bg, scale):
+    """Render.volume_integration with with_sdf=False (softplus density) / force_background through c3d_composite_forward vs the
+    reference's own output (tests/golden/volint_modes.npz)."""
+    import cips3dpp_b200 as c3d
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "volint_modes.npz"))
+    out = c3d.Render.volume_integration(_t(g["rgb"]), _t(g["raw"] * np.float32(scale)), _t(g["features"]), _t(g["z_vals"]),
+                                        _t(g["rays_d"]), _t(g["pts"]), with_sdf=with_sdf,
+                                        sigmoid_beta=torch.tensor([0.1], device=_dev()) if with_sdf else None,
+                                        force_background=bg)
+    for a, k in zip(out[:4], ("rgb_map", "feature_map", "xyz", "mask")):
+        np.testing.assert_allclose(a.cpu().numpy(), g[f"{tag}_{k}"], atol=5e-6, rtol=5e-5)
+    torch.manual_seed(0)
+    noisy = c3d.Render.volume_integration(_t(g["rgb"]), _t(g["raw"]), None, _t(g["z_vals"]), _t(g["rays_d"]), _t(g["pts"]),
+                                          with_sdf=False, raw_noise_std=0.5)
+    assert noisy[1] is None and torch.isfinite(noisy[0]).all()

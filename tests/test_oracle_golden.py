@@ -80,3 +80,16 @@ def test_perturbed_z_vals():
     assert np.abs(t - t[..., :1]).max() < 1e-3          # one shared offset per ray (nerf_utils.py:110)
     z2 = O.get_z_vals(near, far, 2, 1, 256, 24, t_rand=t[..., :1])
     assert np.abs(z2 - c["z_vals"].reshape(2, 1, 256, 24)).max() < 1e-6
+
+
+def test_volume_integration_unused_branches_match_reference():
+    """with_sdf=False (softplus density) and force_background (nerf_utils.py:288-296, 309-310) vs the reference's own output
+    (tests/golden/volint_modes.npz, written by make_golden.py --volint)."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "volint_modes.npz"))
+    for tag, with_sdf, bg, scale in (("raw", False, False, 1.0), ("raw_bg", False, True, 1.0), ("sdf_bg", True, True, 0.05)):
+        out = O.volume_integration(g["rgb"], g["raw"] * np.float32(scale), g["features"], g["z_vals"], g["rays_d"], g["pts"],
+                                   np.float32(0.1), with_sdf=with_sdf, force_background=bg)
+        for a, k in zip(out[:4], ("rgb_map", "feature_map", "xyz", "mask")):
+            np.testing.assert_allclose(a, g[f"{tag}_{k}"], atol=3e-6, rtol=2e-5)
