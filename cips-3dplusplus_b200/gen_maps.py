@@ -25,13 +25,14 @@ def image_index(idx_b, idx_i, batch_gpu, world_size, rank):
 
 
 def gen_maps(renderer, style_fn, cam_cfg, num_imgs, batch_gpu, out_dir=None, decoder=None, rank=0, world_size=1,
-             img_size=64, N_samples=24, static_viewdirs=False, seed=0, device=None, keep=False):
+             img_size=64, N_samples=24, static_viewdirs=False, seed=0, device=None, keep=False, N_importance=0):
     """Render `num_imgs` images in total over `world_size` ranks.
 
     style_fn(batch, generator) -> styles (batch, D+1, 256) for the NeRF branch (the reference maps z through
     `Generator.style`, model_v3.py:1420-1433; any callable works).  cam_cfg: keyword arguments of
     `Camera.generate_camera_params` (fov_ang, dist_radius, azim_range, elev_range, uniform, ...).
-    Returns the list of (index, path or arrays) this rank produced."""
+    `N_importance > 0` renders with the optional coarse + fine pass (`NerfBranch.render_hierarchical`, an extension: the
+    reference renders in one pass).  Returns the list of (index, path or arrays) this rank produced."""
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     g = torch.Generator(device=device).manual_seed(seed * 1000003 + rank)
     if out_dir is not None and rank == 0:
@@ -45,8 +46,11 @@ def gen_maps(renderer, style_fn, cam_cfg, num_imgs, batch_gpu, out_dir=None, dec
             styles = style_fn(batch_gpu, g)
             torch.manual_seed(seed * 7919 + idx_b * world_size + rank)          # camera draws (torch.randn / rand inside)
             pose, focal, near, far, _ = Camera.generate_camera_params(img_size, device, batch=batch_gpu, **cam_cfg)
-            maps = renderer.render(pose, focal, near, far, styles, img_size=img_size, N_samples=N_samples,
-                                   static_viewdirs=static_viewdirs, features_nchw=decoder is not None)
+            kw = dict(img_size=img_size, N_samples=N_samples, static_viewdirs=static_viewdirs, features_nchw=decoder is not None)
+            if N_importance > 0:
+                maps = renderer.render_hierarchical(pose, focal, near, far, styles, N_importance=N_importance, **kw)
+            else:
+                maps = renderer.render(pose, focal, near, far, styles, **kw)
             images = None
             if decoder is not None:
                 images = decoder(maps["feature_map"].view(batch_gpu, -1, img_size, img_size), maps)
@@ -89,6 +93,7 @@ def main():
     ap.add_argument("--batch-gpu", type=int, default=64)
     ap.add_argument("--out", required=True)
     ap.add_argument("--n-samples", type=int, default=24)
+    ap.add_argument("--n-importance", type=int, default=0, help="> 0: coarse + fine render (extension, off by default)")
     ap.add_argument("--fov", type=float, default=6.0)
     ap.add_argument("--dist-radius", type=float, default=0.12)
     ap.add_argument("--azim-range", type=float, default=0.3)
@@ -105,7 +110,7 @@ def main():
     m = m.cuda().eval().requires_grad_(False)
     cam = dict(fov_ang=a.fov, dist_radius=a.dist_radius, azim_range=a.azim_range, elev_range=a.elev_range, uniform=a.uniform)
     out = gen_maps(m, gaussian_styles(a.layers), cam, a.num_imgs, a.batch_gpu, out_dir=a.out, rank=rank, world_size=world,
-                   N_samples=a.n_samples, seed=a.seed)
+                   N_samples=a.n_samples, seed=a.seed, N_importance=a.n_importance)
     if rank == 0:
         print(f"rank 0 wrote {len(out)} of {a.num_imgs} images to {a.out}")
     if world > 1:
