@@ -5,15 +5,19 @@
 // (oracle/nerf_oracle.py::importance_depths) for the SDF compositing weights of Render.volume_integration
 // (nerf_utils.py:267-307).
 //
-// Bound: HBM.  Per ray the kernel reads z (4N) + weights or sdf (4N) [+ rays 24 B, + u 4K] and writes z_fine (4K),
-// z_merged 4(N+K) and the fine-pass points 12(N+K).  Data path: a block owns chunks of RB consecutive rays; every
-// input/output array of a chunk is one contiguous span, moved by the TMA engine as 1-D bulk copies
-// (cp.async.bulk global->shared with mbarrier complete_tx; shared->global bulk groups), so global traffic is issued as
-// a few large transactions per chunk instead of 96-byte rows per warp.  Compute: one warp per ray --
-//   lanes = samples: density -> alpha -> transmittance (shuffle prefix product), interior weights + 1e-5 -> sum
-//   (butterfly) -> CDF (shuffle prefix sum with carry for N > 32);
-//   lanes = new samples: per-lane binary search of u in the CDF (upper bound), linear interpolation in the bin;
-//   merge: rank of every coarse / new depth in the union by binary search in the other (sorted) list.
+// Bound: HBM.  Per ray the kernels read z (4N) + weights or sdf (4N) [+ rays 24 B, + u 4K] and write z_fine (4K),
+// z_merged 4(N+K) and the fine-pass points 12(N+K).  Two kernels behind c3d_sample_pdf:
+//
+//  * sample_pdf_lane_kernel (below, second half; the default whenever the rows of >= 64 rays fit shared memory):
+//    lanes = rays.
+//  * sample_pdf_kernel (first half; larger N / K, or C3D_RESAMPLE=warp): lanes = samples.  A block owns chunks of RB
+//    consecutive rays; every input / output array of a chunk is one contiguous span, moved by the TMA engine as 1-D bulk
+//    copies (cp.async.bulk global->shared with mbarrier complete_tx; shared->global bulk groups; the next chunk's loads
+//    are issued while the stores drain).  Compute, one warp per ray --
+//      lanes = samples: density -> alpha -> transmittance (shuffle prefix product), interior weights + 1e-5 -> sum
+//      (butterfly) -> CDF (shuffle prefix sum with carry for N > 32);
+//      lanes = new samples: per-lane binary search of u in the CDF (upper bound), linear interpolation in the bin;
+//      merge: rank of every coarse / new depth in the union by binary search in the other (sorted) list.
 #pragma once
 #include "c3d_common.cuh"
 #include "sm100_ptx.cuh"
@@ -258,8 +262,8 @@ __global__ void __launch_bounds__(THREADS) sample_pdf_kernel(c3d_resample_params
 // ------------------------------------------------------------------------------------------
 // Lane-per-ray variant (default when a ray's working set is small, e.g. the N = K = 24 configuration): with 24 samples
 // a warp-per-ray scan leaves lanes idle and pays the shuffle / control overhead once per ray; here a thread owns a ray
-// and runs the prefix product, the CDF, a fixed-length binary search and an in-place backward merge serially in shared memory (~4x fewer issued
-// instructions per ray).  Rows are staged in shared memory with an ODD stride, so the 32 rays of a warp hit 32
+// and runs the prefix product, the CDF, a fixed-length binary search and an in-place backward merge serially in shared
+// memory (~2.5x fewer issued instructions per ray).  Rows are staged in shared memory with an ODD stride, so the 32 rays of a warp hit 32
 // different banks; global traffic stays fully coalesced: the block's input / output spans are contiguous and are moved
 // by flat 16-byte / 4-byte accesses, with (row, column) recovered by a multiply-high division.
 // Summation order here is the reference's own (sequential cumprod / cumsum).
