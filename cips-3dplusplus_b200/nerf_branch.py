@@ -283,6 +283,10 @@ class NerfBranch(nn.Module):
         nws = lib.c3d_backward_workspace_bytes(B)
         if nws == 0 or nws > budget:
             return None
+        try:                                                         # memory is tight: plain forward + chunked recomputation
+            ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        except torch.cuda.OutOfMemoryError:
+            return None
         f = dict(dtype=torch.float32, device=dev)
         rgb_map = torch.empty(b, n_rays, 3, **f)
         feat = torch.empty((b, W, n_rays) if nchw else (b, n_rays, W), **f)
@@ -293,7 +297,6 @@ class NerfBranch(nn.Module):
         P = B.fwd
         P.rgb_map, P.feature_map, P.sdf, P.mask, P.xyz = (t.data_ptr() for t in (rgb_map, feat, sdf, mask, xyz))
         P.z_vals_out = z_out.data_ptr() if z_out is not None else None
-        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
         P.workspace, P.workspace_bytes = ws.data_ptr(), nws
         with torch.cuda.device(dev):
             _abi.check(lib.c3d_nerf_forward_save(B, torch.cuda.current_stream().cuda_stream), "c3d_nerf_forward_save")
