@@ -202,6 +202,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_backward_kernel(const Args 
     const int c7 = t & 7;
     uint32_t jobcnt = 0;
     const int total_units = a.batch * a.units_per_img;
+    // cycle counters of one epilogue thread (build with -DC3D_KERNEL_PROF, run with C3D_DEBUG=2), as in the forward kernel
+#ifdef C3D_KERNEL_PROF
+    const bool eprof = (a.debug & 2) != 0 && blockIdx.x == 0 && t == 0;
+    long long e_setup = 0, e_wait = 0, e_epi = 0, e_other = 0, e_mark = clock64(), e_begin = e_mark;
+    int e_tiles = 0;
+#define C3D_BPROF(acc) do { if (eprof) { const long long now_ = clock64(); acc += now_ - e_mark; e_mark = now_; } } while (0)
+#else
+#define C3D_BPROF(acc) do { } while (0)
+#endif
 
     for (int u = slot; u < total_units; u += nslots) {
       const int img = u / a.units_per_img;
@@ -266,10 +275,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_backward_kernel(const Args 
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&misc->a_ready[s]);
+        C3D_BPROF(e_setup);
 
         // ---- layers D .. 0: cotangent through sin/FiLM, column sums, G^T tile for the next MMA job
         for (int l = D; l >= 0; --l) {
+          C3D_BPROF(e_other);
           mbar_wait(&misc->acc_full[s], jobcnt & 1u);
+          C3D_BPROF(e_wait);
           jobcnt++;
           tc_fence_after();
 #pragma unroll 1
@@ -313,6 +325,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_backward_kernel(const Args 
           tc_fence_before();
           fence_proxy_async_smem();
           mbar_arrive(&misc->a_ready[s]);
+          C3D_BPROF(e_epi);
           if (l == D) {
             // ---- d viewdirs of my point (job 1: heads rows 4..6 = Wview[:, 256..258])
             mbar_wait(&misc->acc_full[s], jobcnt & 1u);
@@ -344,8 +357,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_backward_kernel(const Args 
             for (int jx = 0; jx < 3; ++jx) gp[jx] += nscale * __uint_as_float(v4[jx]);
           }
         }
+#ifdef C3D_KERNEL_PROF
+        if (eprof) ++e_tiles;
+#endif
+        C3D_BPROF(e_other);
       }
     }
+#ifdef C3D_KERNEL_PROF
+    if (eprof)
+      printf("c3d prof bwd eg(slot %d): total %lld tiles %d  setup %lld  wait_acc_full %lld  layer epilogues %lld  other(narrow waits, d pts) %lld\n",
+             s, clock64() - e_begin, e_tiles, e_setup, e_wait, e_epi, e_other);
+#endif
   }
 
   tc_fence_before();
