@@ -90,30 +90,31 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], float scale,
   }
 }
 
-// Same, additionally keeping what the backward needs: bf16(acc) and bf16(cos(arg)) (and the output itself for the view
-// layer) in global memory, layout [point group][channel][8 points] so a warp writes 512 contiguous bytes per group.
+// Same, additionally keeping what the backward needs: the pre-FiLM accumulator as fp16 (and the output itself for the view
+// layer) in global memory, layout [point group][channel][8 points] so a warp writes 512 contiguous bytes per group.  The
+// backward recomputes cos(scale * acc + shift) from it: |acc| < 2, so fp16's 11 significant bits put the ~30 rad argument within
+// 0.007 rad -- the accuracy a stored bf16 cosine has -- at half the bytes of storing both.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ void epilogue16_save(const uint32_t (&v)[16], float scale, float shift, uint32_t row_addr,
-                                                int u0, int c7, __nv_bfloat16* sacc, __nv_bfloat16* scos,
+                                                int u0, int c7, __nv_bfloat16* sacc,
                                                 __nv_bfloat16* sfeat /* NULL unless view layer */) {
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
-    float o[8], cs[8];
+    float o[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float arg = fmaf(__uint_as_float(v[g * 8 + i]), scale, shift);
-      o[i] = __sinf(arg);
-      cs[i] = __cosf(arg);
-    }
+    for (int i = 0; i < 8; ++i) o[i] = __sinf(fmaf(__uint_as_float(v[g * 8 + i]), scale, shift));
     const uint4 po = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
     st_v4(row_addr + (uint32_t)(((u0 + g) ^ c7) << 4), po.x, po.y, po.z, po.w);
     const size_t goff = (size_t)g * (W * 8);
     *reinterpret_cast<uint4*>(sacc + goff) =
-        make_uint4(pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1])),
-                   pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
-                   pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
-                   pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
-    *reinterpret_cast<uint4*>(scos + goff) =
-        make_uint4(pack_bf16x2(cs[0], cs[1]), pack_bf16x2(cs[2], cs[3]), pack_bf16x2(cs[4], cs[5]), pack_bf16x2(cs[6], cs[7]));
+        make_uint4(pack_f16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1])),
+                   pack_f16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
+                   pack_f16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
+                   pack_f16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
     if (sfeat) *reinterpret_cast<uint4*>(sfeat + goff) = po;
   }
 }
@@ -458,12 +459,11 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
                 const size_t so = ((((size_t)l * a.n_tiles_g + tile_g) * 16 + cp * 4) * W + (t + TILE * h)) * 8;
                 const size_t fo = (((size_t)tile_g * 16 + cp * 4) * W + (t + TILE * h)) * 8;
                 epilogue16_save(v0, hh ? fb.x : fa.x, hh ? fb.y : fa.y, row, (cp & 1) * 4, c7, a.save_acc + so,
-                                a.save_cos + so, l == D ? a.save_feat + fo : nullptr);
+                                l == D ? a.save_feat + fo : nullptr);
                 tmem_ld_wait();
                 if (cp < 3) tmem_ld_32x16(tcol + (cp + 1) * 32, v0);
                 epilogue16_save(v1, hh ? fb.x : fa.x, hh ? fb.y : fa.y, row, (cp & 1) * 4 + 2, c7,
-                                a.save_acc + so + 2 * W * 8, a.save_cos + so + 2 * W * 8,
-                                l == D ? a.save_feat + fo + 2 * W * 8 : nullptr);
+                                a.save_acc + so + 2 * W * 8, l == D ? a.save_feat + fo + 2 * W * 8 : nullptr);
               } else {
                 epilogue16(v0, hh ? fb.x : fa.x, hh ? fb.y : fa.y, row, (cp & 1) * 4, c7);
                 tmem_ld_wait();

@@ -1,7 +1,7 @@
 // Fused backward of the point MLP on tcgen05 (bf16 operands, fp32 accumulation) -- the tensor-core counterpart of
 // mlp_bwd_kernel (backward.cuh), same persistent two-slot structure as the forward kernel.
 //
-// Inputs per tile come from the forward kernel's save mode (bf16 acc / cos(arg) tiles per layer), from the
+// Inputs per tile come from the forward kernel's save mode (fp16 acc tiles per layer; cos(arg) is recomputed here), from the
 // compositing backward (per-point weights, d rgb, d sdf) and from the caller (d feature_map).  Orientation as in the
 // forward: TMEM lanes = channels, columns = points, so for every layer the epilogue thread of channel c computes
 //     g_a = g_h * cos(arg)          (cotangent of the SIREN argument)
@@ -16,6 +16,7 @@
 //   2..D+1 layers D..1           g_h^T = W^T g_acc  (+ sigma-head rank-1 term for the first of them)
 //   D+2    d points              D[p][j] = sum_c g_acc_0[c][p] W0[c][j]
 #pragma once
+#include <cuda_fp16.h>
 #include "c3d_common.cuh"
 #include "sm100_ptx.cuh"
 #include "fused_common.cuh"
@@ -287,31 +288,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_backward_kernel(const Args 
 #pragma unroll 1
           for (int h = 0; h < 2; ++h) {
             const int ch = t + TILE * h;
-            const float scale = film_img[l * W + ch].x;
+            const float scale = film_img[l * W + ch].x, shift = film_img[l * W + ch].y;
             const uint32_t tcol = tacc + (uint32_t)h * 128u;
             const uint32_t row_u32 = act_u32 + (uint32_t)ch * 128u;
             const size_t so = (((size_t)l * a.n_tiles_g + tile_g) * 16 * W + ch) * 8;
             const uint4* pacc = reinterpret_cast<const uint4*>(a.save_acc + so);
-            const uint4* pcos = reinterpret_cast<const uint4*>(a.save_cos + so);
             float G1 = 0.f, G2 = 0.f;
             uint32_t v[16];
 #pragma unroll 2
             for (int cp = 0; cp < 8; ++cp) {               // 16 points per iteration = 2 point groups
               tmem_ld_32x16(tcol + cp * 16, v);
-              uint4 ac[2], co[2];
+              uint4 ac[2];
 #pragma unroll
-              for (int g = 0; g < 2; ++g) { ac[g] = __ldcs(pacc + (size_t)(cp * 2 + g) * W); co[g] = __ldcs(pcos + (size_t)(cp * 2 + g) * W); }
+              for (int g = 0; g < 2; ++g) ac[g] = __ldcs(pacc + (size_t)(cp * 2 + g) * W);
               tmem_ld_wait();
 #pragma unroll
               for (int g = 0; g < 2; ++g) {
-                const uint32_t aw[4] = {ac[g].x, ac[g].y, ac[g].z, ac[g].w}, cw[4] = {co[g].x, co[g].y, co[g].z, co[g].w};
+                const uint32_t aw[4] = {ac[g].x, ac[g].y, ac[g].z, ac[g].w};
                 float o[8];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  const float ga0 = __uint_as_float(v[g * 8 + 2 * i]) * bf16_lo(cw[i]);
-                  const float ga1 = __uint_as_float(v[g * 8 + 2 * i + 1]) * bf16_hi(cw[i]);
+                  const float2 acc2 = __half22float2(*reinterpret_cast<const __half2*>(&aw[i]));     // saved fp16 accumulators
+                  const float ga0 = __uint_as_float(v[g * 8 + 2 * i]) * __cosf(fmaf(acc2.x, scale, shift));
+                  const float ga1 = __uint_as_float(v[g * 8 + 2 * i + 1]) * __cosf(fmaf(acc2.y, scale, shift));
                   G2 += ga0 + ga1;
-                  G1 = fmaf(ga0, bf16_lo(aw[i]), fmaf(ga1, bf16_hi(aw[i]), G1));
+                  G1 = fmaf(ga0, acc2.x, fmaf(ga1, acc2.y, G1));
                   o[2 * i] = ga0 * scale; o[2 * i + 1] = ga1 * scale;
                 }
                 const int unit = (cp & 3) * 2 + g;            // 16-byte unit inside the 64-point block

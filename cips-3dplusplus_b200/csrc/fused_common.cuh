@@ -28,8 +28,8 @@ struct Args {
   const uint8_t* wimg; const uint8_t* kimg;   // CTA-pair kernel: per-image FiLM-folded weight images (film_weights_kernel)
   // ---- backward support (NULL in plain forward launches) ----
   // bf16 tiles [layer][tile_g][point group 16][channel 256][8 points]; tile_g = unit * tiles_per_unit + tile
-  __nv_bfloat16* save_acc;    // pre-FiLM accumulators, layers 0..D
-  __nv_bfloat16* save_cos;    // cos of the SIREN argument, layers 0..D
+  __nv_bfloat16* save_acc;    // pre-FiLM accumulators, layers 0..D, stored as fp16 bit patterns (the backward recomputes
+                              // cos(scale * acc + shift) from them)
   __nv_bfloat16* save_feat;   // view-layer output (one layer)
   float* rgb_pt;              // (b, n_rays, N, 3) raw rgb head output
   float* w_pt;                // (b, n_rays, N) compositing weights
