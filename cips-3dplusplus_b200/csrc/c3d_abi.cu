@@ -645,7 +645,7 @@ static BwdTcWs bwd_tc_ws(const c3d_bwd_params* bp) {
   w.g_film = o; o += align_up(b * (D + 1) * W * sizeof(float2), 256);
   w.chunk = o;
   const bool poses = p->input_kind == C3D_INPUT_POSES;
-  const size_t per_img = tiles_img * 65536 * ((D + 1) + 1) + P * (12 + 4 + 4 + 4 + 12 + 4 + 4 + 12) + R * (12 + 1024 + 8 + 12 + 24) +
+  const size_t per_img = tiles_img * 65536 * (D + 1) + P * (12 + 4 + 4 + 4 + 12 + 4 + 4 + 12) + R * (12 + 1024 + 8 + 12 + 24) +
                          (poses ? P * 16 + R * 24 : 0) + 8192;
   size_t ci = ((size_t)4 << 30) / per_img;
   if (ci < 1) ci = 1;
@@ -655,7 +655,7 @@ static BwdTcWs bwd_tc_ws(const c3d_bwd_params* bp) {
   auto take = [&](size_t bytes) { const size_t at = c; c += align_up(bytes, 256); return at; };
   w.c_acc = take(ci * tiles_img * 65536 * (D + 1));
   w.c_cos = 0;                                    // cos(arg) is recomputed from the fp16 accumulators in the backward
-  w.c_feat = take(ci * tiles_img * 65536);
+  w.c_feat = 0;                                   // the view layer's output is recomputed from its accumulators (gdot_kernel)
   w.c_rgbpt = take(ci * P * 12); w.c_wpt = take(ci * P * 4); w.c_sdfpt = take(ci * P * 4); w.c_gdot = take(ci * P * 4);
   w.c_grgb = take(ci * P * 12); w.c_gsdf = take(ci * P * 4); w.c_wts = take(ci * P * 4);
   w.c_orgb = take(ci * R * 12); w.c_ofeat = take(ci * R * W * 4); w.c_omask = take(ci * R * 8); w.c_oxyz = take(ci * R * 12);
@@ -935,7 +935,6 @@ static int backward_tc(const c3d_bwd_params* bp, cudaStream_t st, int phases) {
     fused::Args a;
     fused_fill_args(a, &q, film + (size_t)i0 * (D + 1) * W, first + (size_t)i0 * W, view + (size_t)i0 * W);
     a.save_acc = reinterpret_cast<__nv_bfloat16*>(ck + w.c_acc);
-    a.save_feat = reinterpret_cast<__nv_bfloat16*>(ck + w.c_feat);
     a.rgb_pt = reinterpret_cast<float*>(ck + w.c_rgbpt); a.w_pt = reinterpret_cast<float*>(ck + w.c_wpt);
     a.g_feature_map = gF;
     if (phases & 1) {

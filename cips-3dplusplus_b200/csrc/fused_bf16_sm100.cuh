@@ -90,18 +90,18 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], float scale,
   }
 }
 
-// Same, additionally keeping what the backward needs: the pre-FiLM accumulator as fp16 (and the output itself for the view
-// layer) in global memory, layout [point group][channel][8 points] so a warp writes 512 contiguous bytes per group.  The
-// backward recomputes cos(scale * acc + shift) from it: |acc| < 2, so fp16's 11 significant bits put the ~30 rad argument within
-// 0.007 rad -- the accuracy a stored bf16 cosine has -- at half the bytes of storing both.
+// Same, additionally keeping what the backward needs: the pre-FiLM accumulator as fp16 in global memory, layout
+// [point group][channel][8 points] so a warp writes 512 contiguous bytes per group.  The backward recomputes
+// cos(scale * acc + shift) (and, for the view layer, the output sin(...) itself) from it: |acc| < 2, so fp16's 11 significant
+// bits put the ~30 rad argument within 0.007 rad -- the accuracy a stored bf16 cosine has -- at a third of the bytes of storing
+// accumulator, cosine and output.
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 __device__ __forceinline__ void epilogue16_save(const uint32_t (&v)[16], float scale, float shift, uint32_t row_addr,
-                                                int u0, int c7, __nv_bfloat16* sacc,
-                                                __nv_bfloat16* sfeat /* NULL unless view layer */) {
+                                                int u0, int c7, __nv_bfloat16* sacc) {
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     float o[8];
@@ -115,7 +115,6 @@ __device__ __forceinline__ void epilogue16_save(const uint32_t (&v)[16], float s
                    pack_f16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3])),
                    pack_f16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5])),
                    pack_f16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7])));
-    if (sfeat) *reinterpret_cast<uint4*>(sfeat + goff) = po;
   }
 }
 
@@ -457,13 +456,11 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
               if (kSave) {
                 // element offset of (layer l, this tile, point group 4*cp, my channel)
                 const size_t so = ((((size_t)l * a.n_tiles_g + tile_g) * 16 + cp * 4) * W + (t + TILE * h)) * 8;
-                const size_t fo = (((size_t)tile_g * 16 + cp * 4) * W + (t + TILE * h)) * 8;
-                epilogue16_save(v0, hh ? fb.x : fa.x, hh ? fb.y : fa.y, row, (cp & 1) * 4, c7, a.save_acc + so,
-                                l == D ? a.save_feat + fo : nullptr);
+                epilogue16_save(v0, hh ? fb.x : fa.x, hh ? fb.y : fa.y, row, (cp & 1) * 4, c7, a.save_acc + so);
                 tmem_ld_wait();
                 if (cp < 3) tmem_ld_32x16(tcol + (cp + 1) * 32, v0);
                 epilogue16_save(v1, hh ? fb.x : fa.x, hh ? fb.y : fa.y, row, (cp & 1) * 4 + 2, c7,
-                                a.save_acc + so + 2 * W * 8, l == D ? a.save_feat + fo + 2 * W * 8 : nullptr);
+                                a.save_acc + so + 2 * W * 8);
               } else {
                 epilogue16(v0, hh ? fb.x : fa.x, hh ? fb.y : fa.y, row, (cp & 1) * 4, c7);
                 tmem_ld_wait();

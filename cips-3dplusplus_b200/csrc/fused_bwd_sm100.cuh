@@ -377,8 +377,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_backward_kernel(const Args 
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-// gdot[point] = sum_c g_feature_map[ray][c] * feat[c][point] from the saved bf16 view-layer tiles; one warp per
-// (tile, point group of 8), lanes over channels.
+// gdot[point] = sum_c g_feature_map[ray][c] * feat[c][point]; feat = sin(scale * acc + shift) of the view layer, recomputed
+// from its saved fp16 accumulator tiles; one warp per (tile, point group of 8), lanes over channels.
 __global__ void __launch_bounds__(256) gdot_kernel(const Args a, float* __restrict__ gdot) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long wid = (long long)blockIdx.x * 8 + warp;
@@ -397,7 +397,12 @@ __global__ void __launch_bounds__(256) gdot_kernel(const Args a, float* __restri
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  const uint4* f = reinterpret_cast<const uint4*>(a.save_feat + ((size_t)tile_g * 16 + pg) * W * 8);
+  const uint4* f = reinterpret_cast<const uint4*>(a.save_acc + (((size_t)a.D * a.n_tiles_g + tile_g) * 16 + pg) * W * 8);
+  const float2* film = a.film + ((size_t)img * (a.D + 1) + a.D) * W;                 // view layer's (scale, shift)
+  auto feat2 = [&](uint32_t w, float2 fs) {                                          // two saved accumulators -> outputs
+    const float2 acc = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    return make_float2(__sinf(fmaf(acc.x, fs.x, fs.y)), __sinf(fmaf(acc.y, fs.x, fs.y)));
+  };
   const int ray_first = q0 / N, ray_last = min(q0 + 7, npts - 1) / N;
   if (ray_first == ray_last) {
     // the group's 8 points lie on one ray (always when N % 8 == 0): its cotangent row is read once per channel
@@ -409,20 +414,25 @@ __global__ void __launch_bounds__(256) gdot_kernel(const Args a, float* __restri
 #pragma unroll
     for (int j = 0; j < W / 32; ++j) {
       const uint32_t fw[4] = {fv[j].x, fv[j].y, fv[j].z, fv[j].w};
+      const float2 fs = film[lane + 32 * j];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        acc[i] = fmaf(gv[j], (i & 1) ? fusedbwd::bf16_hi(fw[i >> 1]) : fusedbwd::bf16_lo(fw[i >> 1]), acc[i]);
+      for (int i = 0; i < 4; ++i) {
+        const float2 x = feat2(fw[i], fs);
+        acc[2 * i] = fmaf(gv[j], x.x, acc[2 * i]);
+        acc[2 * i + 1] = fmaf(gv[j], x.y, acc[2 * i + 1]);
+      }
     }
   } else {
     for (int c = lane; c < W; c += 32) {
       const uint4 fv = __ldcs(f + c);
       const uint32_t fw[4] = {fv.x, fv.y, fv.z, fv.w};
+      const float2 fs = film[c];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int q = min(q0 + i, npts - 1);
         const float g = a.g_feature_map[((size_t)img * a.n_rays + r0 + q / N) * W + c];
-        const float x = (i & 1) ? fusedbwd::bf16_hi(fw[i >> 1]) : fusedbwd::bf16_lo(fw[i >> 1]);
-        acc[i] = fmaf(g, x, acc[i]);
+        const float2 x2 = feat2(fw[i >> 1], fs);
+        acc[i] = fmaf(g, (i & 1) ? x2.y : x2.x, acc[i]);
       }
     }
   }

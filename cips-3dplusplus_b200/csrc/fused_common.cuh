@@ -30,7 +30,6 @@ struct Args {
   // bf16 tiles [layer][tile_g][point group 16][channel 256][8 points]; tile_g = unit * tiles_per_unit + tile
   __nv_bfloat16* save_acc;    // pre-FiLM accumulators, layers 0..D, stored as fp16 bit patterns (the backward recomputes
                               // cos(scale * acc + shift) from them)
-  __nv_bfloat16* save_feat;   // view-layer output (one layer)
   float* rgb_pt;              // (b, n_rays, N, 3) raw rgb head output
   float* w_pt;                // (b, n_rays, N) compositing weights
   int tiles_per_unit; long long n_tiles_g;
