@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("C3D_LIB") or os.path.join(HERE, "libc3dpp.so")   # C3
 SRC = os.path.join(HERE, "csrc", "c3d_abi.cu")
 ABI_VERSION = 8
 MAX_LAYERS = 16
+MIN_SAMPLES_BF16 = 8     # fused::MIN_SAMPLES (csrc/fused_common.cuh)
 MODE_FP32, MODE_BF16 = 0, 1
 INPUT_POSES, INPUT_POINTS = 0, 1
 FEAT_NHWC, FEAT_NCHW = 0, 1

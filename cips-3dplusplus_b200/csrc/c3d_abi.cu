@@ -231,7 +231,6 @@ static int forward_pair(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
   a.unit_rays = ur;
   a.units_per_img = (p->n_rays + 2 * ur - 1) / (2 * ur);
   a.wimg = ws + w.wimg; a.kimg = ws + w.kimg;
-  { const char* e = getenv("C3D_STAGGER"); a.stagger = e ? atoi(e) : 0; }
   film_weights_kernel<<<dim3(8, p->D, p->batch), 256, 0, st>>>(a.blob, a.L, a.film, ws + w.wimg);
   C3D_LAUNCH_CHECK();
   film_k16_kernel<<<dim3(p->D + 1, p->batch), 256, 0, st>>>(a.blob, a.L, a.film, ws + w.kimg);
@@ -243,14 +242,12 @@ static int forward_pair(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
   if (genv && atoi(genv) > 0) grid = (atoi(genv) + 1) & ~1;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  const char* eenv = getenv("C3D_EGW");
-  const int egw = (eenv && atoi(eenv) == 4) ? 4 : 8;            // epilogue warps per slot
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(pairk::nthreads(egw)); cfg.dynamicSmemBytes = pairk::SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(pairk::NTHREADS); cfg.dynamicSmemBytes = pairk::SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  void (*kern)(const fused::Args) = egw == 8 ? pairk::fused_forward_pair_kernel<8> : pairk::fused_forward_pair_kernel<4>;
+  void (*kern)(const fused::Args) = pairk::fused_forward_pair_kernel;
   C3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pairk::SMEM_BYTES));
   C3D_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   C3D_LAUNCH_CHECK();

@@ -1,30 +1,36 @@
-// Fused NeRF-branch forward for sm_100a, CTA-pair version (fourth structure of the round; profiles/r01_fused.md).
+// Fused NeRF-branch forward for sm_100a, CTA-pair kernel (the default bf16 forward since round 2).
 //
 // Reference semantics: exp/cips3d/volume_renderer.py:133-160,192-283, exp/cips3d/nerf_utils.py:17-218,230-338.
 //
-// What changed against fused_bf16_sm100.cuh and why
+// Structure (profiles/r02_fused.md has the measurements behind each choice)
 //   * FiLM is folded into the GEMM.  film_weights_kernel (kernels_aux.cuh) writes, per image, bf16(gamma_c * W_l[c][k]) in
 //     the stage layout plus a K = 16 side image holding the shift (gamma b + beta, hi/lo split, multiplied by two "ones"
 //     slots of the point tile), the layer-0 weights and the view-direction columns.  The accumulator is the SIREN argument
 //     itself, so the epilogue is sin -> bf16 -> store with no per-channel constants.
-//   * That frees the orientation: D[point][channel] = H * W'^T, TMEM lanes are points.  A thread owns one point of its
-//     tile in every stage (geometry, layer epilogues, sdf / transmittance, rgb) and writes its own 512-byte row of the
-//     K-major activation tile.
-//   * Two CTAs of a cluster form a pair and issue ONE tcgen05.mma.cta_group::2 (M = 256 points = 128 per CTA, N = 256
-//     channels): every CTA stages only its 128 weight rows (half of B), reads its activation tile once per layer, and
-//     never exchanges activations.  Per 128 points and layer the SM moves 256 KB through shared memory instead of 448 KB
-//     and the 4 x 16 KB ring holds a whole layer of its weight half.
+//   * Orientation D[point][channel] = H * W'^T: TMEM lanes are points.  A thread owns one point of its tile in every
+//     stage (geometry, layer epilogues, sdf / transmittance, rgb) and writes its own rows of the K-major activation tile.
+//   * Two CTAs of a cluster form a pair and issue tcgen05.mma.cta_group::2 (M = 256 points = 128 per CTA): every CTA
+//     stages only its half of the weight rows and never exchanges activations, so a 64 KB ring holds a WHOLE layer.
+//     Both slots of a pair run the same layer back to back from the same ring stages (slot 1 trails slot 0 by one job),
+//     which streams every layer once per two tiles and leaves the refill a full job of slack.
+//   * The per-SM bound of this kernel is the SFU, not the tensor pipe: a 128-point tile-layer needs 2048 tensor cycles
+//     and 32768 MUFU.SIN = 2076 SFU cycles (sm_probe M1), and 9 sine layers face 8 K = 256 layers at D = 8.  The job
+//     structure therefore exists to keep the epilogue warps fed: a K = 256 layer is issued as two channel halves
+//     (N = 128 each, accumulator columns 0..127 / 128..255 of the slot); half 0 is committed on its own, so its sines
+//     run under half 1's MMAs.  The activation tile is updated in place: half 0's outputs overwrite K-chunks 0, 1, which
+//     half 1's MMAs still read -- half 1 consumes those chunks first and a third commit (act_free) releases them.
 //
-// Roles per CTA (384 threads): warp 0 weight producer (bulk copies of its half), warp 1 MMA issuer (leader CTA) or
-// barrier relay (peer CTA: forwards "my stage landed" to the leader), warp 2 TMEM allocator, warps 4-7 / 8-11 epilogue
-// group of slot 0 / 1.  Barriers the leader waits on (full, kfull, a_ready) collect arrivals from both CTAs; barriers
-// signalled by tcgen05.commit (empty, kempty, acc_full) are multicast to both.
+// Roles per CTA (640 threads): warp 0 weight producer (bulk copies of its halves), warp 1 MMA issuer (leader CTA) or
+// barrier relay (peer CTA: forwards "my stage landed" to the leader), warp 2 TMEM allocator, warps 4-11 / 12-19 epilogue
+// group of slot 0 / 1 (8 warps: two per sub-partition, what the SFU needs to stay saturated while one waits on TMEM).
+// Barriers the leader waits on (full, kfull, a_ready) collect arrivals from both CTAs; barriers signalled by
+// tcgen05.commit (empty, kempty, acc_full, act_free) are multicast to both.
 //
-// Per pair-tile (128 points per CTA) the issuer runs D+3 jobs, as before:
-//   job 0       layer 0    : K = 16 product of the point tile (hi, mid, hi, lo per coordinate, ones) with the K16 image
-//   job 1..D-1  hidden l   : K16 product (shift) + 16 x (256x256x16), A = activation tile, B = weight ring
+// Per pair-tile (128 points per CTA) the issuer runs D+3 jobs:
+//   job 0       layer 0    : per half a K = 16 product of the point tile (hi, mid, hi, lo per coordinate, ones) with the K16 image
+//   job 1..D-1  hidden l   : per half K16 product (shift) + 16 x (256x128x16), A = activation tile, B = weight ring
 //   job D       sdf head   : 16 x (256x16x16), B = heads16 (8 rows per CTA)
-//   job D+1     view layer : K16 product (view direction, shift) + 16 x (256x256x16)
+//   job D+1     view layer : per half K16 product (view direction, shift) + 16 x (256x128x16)
 //   job D+2     post       : compositing MMAs (A = feat^T as MN-major view, B = Wgt; N = 32, each CTA reads its own 16
 //                            columns) + rgb head
 #pragma once
@@ -40,18 +46,17 @@ using fused::TILE;
 using fused::ACT_BYTES;
 using fused::ACT_CHUNK;
 
-// epilogue warps per slot (template parameter kEgw): 4 -> a thread owns all 256 channels of its point; 8 -> warps 0-3 of the
-// slot own channels 0..127 and run the per-point stages, warps 4-7 own channels 128..255 (a warp pays 8 issue cycles per
-// MUFU.SIN, so one warp per sub-partition and slot cannot saturate the SFU while it also packs and stores)
-__host__ __device__ constexpr int nthreads(int egw) { return 128 + 2 * egw * 32; }
-constexpr int STAGE_BYTES = 128 * 128;         // [128 weight rows][64 k] bf16, K-major SWIZZLE_128B
-constexpr int NSTAGE = 4;
+constexpr int EGW = 8;                         // epilogue warps per slot: warp (quad, grp) owns lanes 32 quad.. and columns 64 grp..
+                                               // of each accumulator half; grp 0 threads also run the per-point stages
+constexpr int NTHREADS = 128 + 2 * EGW * 32;   // 640
+constexpr int STAGE_BYTES = 64 * 128;          // [64 weight rows][64 k] bf16, K-major SWIZZLE_128B: this CTA's part of (half, K-chunk)
+constexpr int NSTAGE = 8;                      // one layer: 2 channel halves x 4 K-chunks
 constexpr int RAYS = 16;                       // rays touching one tile (n_samples >= 8)
 constexpr int AUX_BYTES = 4096;                // per slot: point / view tile ([128][16] k16) or Wgt ([16][128] sw128)
-constexpr int K16_BYTES = 4096;                // per slot: this CTA's half of the layer's K16 image ([128 rows][16])
+constexpr int K16_BYTES = 4096;                // per slot: this CTA's part of the layer's K16 image ([half 2][64 rows][16])
 constexpr int HEADS_BYTES = 4096;              // 4 K-chunks x [8 rows][64 k]: this CTA's half of heads16
-constexpr size_t WIMG_LAYER_BYTES = (size_t)W * W * 2;   // per image and K=256 layer: [kc 4][half 2][16 KB]
-constexpr size_t KIMG_LAYER_BYTES = (size_t)W * 16 * 2;  // per image and layer 0..D: [half 2][4 KB]
+constexpr size_t WIMG_LAYER_BYTES = (size_t)W * W * 2;   // per image and K=256 layer: [half 2][kc 4][rank 2][8 KB]
+constexpr size_t KIMG_LAYER_BYTES = (size_t)W * 16 * 2;  // per image and layer 0..D: [rank 2][half 2][2 KB]
 
 constexpr int SM_ACT = 0;
 constexpr int SM_STAGE = SM_ACT + 2 * ACT_BYTES;                 // 131072
@@ -65,19 +70,12 @@ constexpr int SM_TOTAL = SM_MISC + 256;
 constexpr int SMEM_BYTES = SM_TOTAL + 1024;
 
 struct Misc {
-  uint64_t full[NSTAGE], empty[NSTAGE], kfull[2], kempty[2], a_ready[2], acc_full[2];
+  uint64_t full[NSTAGE], empty[NSTAGE], kfull[2], kempty[2], a_ready[2];
+  uint64_t acc_full[2][2];   // [slot][half]; the narrow jobs (sdf head, post) signal half 0 only
+  uint64_t act_free[2];      // [slot]: the job's MMAs no longer read K-chunks 0, 1 of the activation tile (nor the aux tile)
   uint32_t tmem_base;
   float carry[2];
-#ifdef C3D_KERNEL_PROF
-  long long tl[8];           // timeline of one layer job of slot 0: see C3D_TL
-  int tl_job;
-#endif
 };
-#ifdef C3D_KERNEL_PROF
-#define C3D_TL(i) do { misc->tl[i] = clock64(); } while (0)
-#else
-#define C3D_TL(i) do { } while (0)
-#endif
 
 // ---- static schedule: pair-slot ps handles pair-units ps, ps + n_pairslots, ...; a pair-unit is 2 * unit_rays rays of one
 // image (the leader takes the first unit_rays); Args::units_per_img counts pair-units.
@@ -127,56 +125,28 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
 // descriptor of the same layout `bytes` further (start-address field, 16-byte units; no carry out of the field here)
 __device__ __forceinline__ uint64_t desc_at(uint64_t base, uint32_t bytes) { return base + (uint64_t)(bytes >> 4); }
 
-// Tuning knob, off by default: bit i of C3D_POLY_MASK moves element i of every group of 8 from the SFU (MUFU.SIN) to the
-// FMA pipe (Cody-Waite reduction to [-pi, pi], odd degree-7 minimax polynomial, max abs error 2.5e-4).  Measured on
-// B200 (profiles/r01_fused.md): every non-zero mask is slower (0x88 +1.7 %, 0x92 +3.5 %, 0xAA +8 %), with 4 or 8
-// epilogue warps per slot -- the epilogue is not SFU-throughput bound.
-#ifndef C3D_POLY_MASK
-#define C3D_POLY_MASK 0x00
-#endif
-__device__ __forceinline__ float sin_fma_pipe(float x) {
-  const float t = fmaf(x, 0.15915494309189535f, 12582912.0f);      // round(x / 2pi) in the low mantissa bits
-  const float k = t - 12582912.0f;
-  const float r = fmaf(k, -6.283185307179586f, x);
-  const float r2 = r * r;
-  float p = fmaf(-0.00014507691616902975f, r2, 0.007958060561828354f);
-  p = fmaf(p, r2, -0.16566697968747116f);
-  p = fmaf(p, r2, 0.9992758634237795f);
-  return r * p;
-}
-template <int i>
-__device__ __forceinline__ float siren_sin(float x) {
-  return ((C3D_POLY_MASK >> (i & 7)) & 1) ? sin_fma_pipe(x) : __sinf(x);
-}
-
 // sin of 16 consecutive channels of one point -> bf16 -> two 16-byte stores into the point's row (units u0, u0 + 1)
-__device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], uint32_t row_addr, int u0, int r7, int dbg = 0) {
+__device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], uint32_t row_addr, int u0, int r7) {
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     float o[8];
-#ifdef C3D_KERNEL_PROF
-    if (dbg & 4) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v[g * 8 + i]) * 0.5f;
-    } else
-#endif
-    {
-#define C3D_SIN_AT(i) o[i] = siren_sin<i>(__uint_as_float(v[g * 8 + i]))
-      C3D_SIN_AT(0); C3D_SIN_AT(1); C3D_SIN_AT(2); C3D_SIN_AT(3); C3D_SIN_AT(4); C3D_SIN_AT(5); C3D_SIN_AT(6); C3D_SIN_AT(7);
-#undef C3D_SIN_AT
-    }
-#ifdef C3D_KERNEL_PROF
-    if (dbg & 8) continue;
-#endif
+    for (int i = 0; i < 8; ++i) o[i] = __sinf(__uint_as_float(v[g * 8 + i]));
     st_v4(row_addr + (uint32_t)(((u0 + g) ^ r7) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
           pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
   }
 }
 
-template <int kEgw>
-__global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_pair_kernel(const Args a) {
-  constexpr int NTHREADS = nthreads(kEgw);
-  constexpr int CPT = 32 / kEgw;                   // 32-channel groups per epilogue thread: 8 or 4
+// In-kernel cycle counters of the issuing thread and of one epilogue thread (development builds only: -DC3D_KERNEL_PROF).
+#ifdef C3D_KERNEL_PROF
+#define C3D_PROF_DECL(n) long long prof_t[n] = {}; long long prof_mark = clock64(); const long long prof_begin = prof_mark
+#define C3D_PROF(i) do { const long long now_ = clock64(); prof_t[i] += now_ - prof_mark; prof_mark = now_; } while (0)
+#else
+#define C3D_PROF_DECL(n) do { } while (0)
+#define C3D_PROF(i) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   Misc* misc = reinterpret_cast<Misc*>(smem + SM_MISC);
@@ -194,8 +164,10 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_pair_kernel(c
     for (int i = 0; i < 2; ++i) {
       mbar_init(&misc->kfull[i], leader ? 2 : 1);
       mbar_init(&misc->kempty[i], 1);
-      mbar_init(&misc->a_ready[i], 2 * kEgw);      // one arrival per epilogue warp of both CTAs (leader's copy is used)
-      mbar_init(&misc->acc_full[i], 1);
+      mbar_init(&misc->a_ready[i], 2 * EGW);       // one arrival per epilogue warp of both CTAs (leader's copy is used)
+      mbar_init(&misc->acc_full[i][0], 1);
+      mbar_init(&misc->acc_full[i][1], 1);
+      mbar_init(&misc->act_free[i], 1);
     }
     misc->carry[0] = misc->carry[1] = 1.0f;
     fence_mbar_init();
@@ -217,11 +189,11 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_pair_kernel(c
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = misc->tmem_base;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, misc->tmem_base, 0);     // provably warp-uniform
 
   if (warp == 0) {
    if (elect_one()) {
-    // ============================================================ weight producer (this CTA's halves)
+    // ============================================================ weight producer (this CTA's parts)
     Cursor c[2];
     c[0].init(a, ps0, n_pairslots); c[1].init(a, ps0 + 1, n_pairslots);
     int jb[2] = {0, 0};
@@ -240,11 +212,12 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_pair_kernel(c
                    a.kimg + (img * (D + 1) + job_film_layer(j, D)) * KIMG_LAYER_BYTES + rank * K16_BYTES, K16_BYTES, &misc->kfull[s]);
           if (kind == 1 && !(shared && s == 1)) {
             const uint8_t* wl = a.wimg + (img * D + job_w_layer(j, D)) * WIMG_LAYER_BYTES + rank * STAGE_BYTES;
-            for (int kc = 0; kc < NCHUNK; ++kc, ++n) {
+#pragma unroll 1
+            for (int pc = 0; pc < NSTAGE; ++pc, ++n) {             // piece pc = half * 4 + K-chunk, in the order the issuer consumes
               const uint32_t st = n % NSTAGE, ph = (n / NSTAGE) & 1u;
               mbar_wait(&misc->empty[st], ph ^ 1u);
               mbar_arrive_expect_tx(&misc->full[st], STAGE_BYTES);
-              bulk_g2s(smem + SM_STAGE + st * STAGE_BYTES, wl + (size_t)kc * 2 * STAGE_BYTES, STAGE_BYTES, &misc->full[st]);
+              bulk_g2s(smem + SM_STAGE + st * STAGE_BYTES, wl + (size_t)pc * 2 * STAGE_BYTES, STAGE_BYTES, &misc->full[st]);
             }
           }
         }
@@ -254,7 +227,7 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_pair_kernel(c
    }
   } else if (warp == 1 && !leader) {
    if (elect_one()) {
-    // ============================================================ relay: "my half landed" -> leader's full / kfull
+    // ============================================================ relay: "my part landed" -> leader's full / kfull
     Cursor c[2];
     c[0].init(a, ps0, n_pairslots); c[1].init(a, ps0 + 1, n_pairslots);
     int jb[2] = {0, 0};
@@ -270,7 +243,8 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_pair_kernel(c
           kcnt[s]++;
           mbar_arrive_remote(r_kfull + (uint32_t)s * 8u);
           if (kind == 1 && !(shared && s == 1)) {
-            for (int kc = 0; kc < NCHUNK; ++kc, ++n) {
+#pragma unroll 1
+            for (int pc = 0; pc < NSTAGE; ++pc, ++n) {
               const uint32_t st = n % NSTAGE, ph = (n / NSTAGE) & 1u;
               mbar_wait(&misc->full[st], ph);
               mbar_arrive_remote(r_full + st * 8u);
@@ -282,95 +256,88 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_pair_kernel(c
     }
    }
   } else if (warp == 1) {
-   if (elect_one()) {
+   {
     // ============================================================ MMA issuer (leader CTA, issues for the pair)
-    const uint32_t idesc_l = umma_idesc_bf16(256, 256, 0, 0);      // layers and K16 side products: both K-major
+    // The whole warp runs the (warp-uniform) control flow and one elected lane executes the tcgen05 instructions: every
+    // operand is then uniform by data flow and lives in uniform registers.  (With the loop inside `if (elect_one())`
+    // ptxas wrapped each UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall -- ~170 cycles per MMA.)
+    const bool issue = elect_one();
+    const uint32_t idesc_l = umma_idesc_bf16(256, 128, 0, 0);      // one channel half of a layer / K16 side product: both K-major
     const uint32_t idesc_h = umma_idesc_bf16(256, 16, 0, 0);       // heads: B = 8 rows of heads16 per CTA
     const uint32_t idesc_c = umma_idesc_bf16(256, 32, 1, 0);       // compositing: A = feat^T (MN-major view), B = Wgt
-    const uint32_t act_addr[2] = {smem_u32(smem + SM_ACT), smem_u32(smem + SM_ACT + ACT_BYTES)};
+    const uint32_t act_base = smem_u32(smem + SM_ACT);
     const uint32_t stage_base = smem_u32(smem + SM_STAGE);
-    const uint32_t aux_addr[2] = {smem_u32(smem + SM_AUX), smem_u32(smem + SM_AUX + AUX_BYTES)};
-    const uint32_t k16_addr[2] = {smem_u32(smem + SM_K16), smem_u32(smem + SM_K16 + K16_BYTES)};
+    const uint32_t aux_base = smem_u32(smem + SM_AUX);
+    const uint32_t k16_base = smem_u32(smem + SM_K16);
     const uint32_t heads_addr = smem_u32(smem + SM_HEADS);
     Cursor c[2];
     c[0].init(a, ps0, n_pairslots); c[1].init(a, ps0 + 1, n_pairslots);
     int jb[2] = {0, 0};
     uint32_t n = 0, kcnt[2] = {0u, 0u}, acnt[2] = {0u, 0u};
-#ifdef C3D_KERNEL_PROF
-    const bool prof = (a.debug & 2) != 0;
-#else
-    constexpr bool prof = false;
-#endif
-    long long t_ready = 0, t_full = 0, t_issue = 0, t_small = 0, t_mark = clock64(), t_begin = t_mark;
-    long long t_rk[4] = {0, 0, 0, 0};
-#define C3D_PPROF(acc) do { if (prof) { const long long now_ = clock64(); acc += now_ - t_mark; t_mark = now_; } } while (0)
     uint32_t n_shared = 0;                 // first ring stage of slot 0's layer job when slot 1 re-reads the same weights
+    C3D_PROF_DECL(8);                      // 0 issue, 1 wait a_ready (layer jobs), 2 wait a_ready (narrow jobs), 3 wait kfull, 4 wait full
     while (c[0].valid() || c[1].valid()) {
       const bool shared = same_weights(a, c[0], c[1]);
+#pragma unroll
       for (int s = 0; s < 2; ++s) {
         if (!c[s].valid()) continue;
         const int j = jb[s], kind = job_kind(j, D);
         const uint32_t tacc = tmem_base + (uint32_t)s * 256u;
-        C3D_PPROF(t_issue);
-#ifdef C3D_KERNEL_PROF
-        const bool tl_on = prof && blockIdx.x == 0 && s == 0 && (acnt[0] == 47u || acnt[0] == 48u);
-        if (tl_on && acnt[0] == 48u) {   // job after the logged one: when did its a_ready show up?
-          mbar_wait_cluster(&misc->a_ready[s], acnt[s] & 1u);
-          C3D_TL(6);
-          printf("c3d timeline slot0 job47 (kind %d): a_ready seen 0 | k16 issued %lld | last mma issued %lld | acc_full seen by epilogue %lld | "
-                 "epilogue stores done %lld | arrive done %lld | next a_ready seen %lld\n", job_kind(47 % JOBS, D), misc->tl[1] - misc->tl[0],
-                 misc->tl[2] - misc->tl[0], misc->tl[3] - misc->tl[0], misc->tl[4] - misc->tl[0], misc->tl[5] - misc->tl[0], misc->tl[6] - misc->tl[0]);
-        }
-#endif
+        const uint32_t act_addr = act_base + (uint32_t)s * ACT_BYTES, aux_addr = aux_base + (uint32_t)s * AUX_BYTES;
+        const uint32_t k16_addr = k16_base + (uint32_t)s * K16_BYTES;
+        C3D_PROF(0);
         mbar_wait_cluster(&misc->a_ready[s], acnt[s] & 1u);
-#ifdef C3D_KERNEL_PROF
-        if (tl_on && acnt[0] == 47u) C3D_TL(0);
-#endif
+        C3D_PROF(kind <= 1 ? 1 : 2);
         acnt[s]++;
-        if (prof) { const long long now_ = clock64(); t_rk[kind] += now_ - t_mark; }
-        C3D_PPROF(t_ready);
         tc_fence_after();
         if (kind <= 1) {
           mbar_wait_cluster(&misc->kfull[s], kcnt[s] & 1u);
+          C3D_PROF(3);
           kcnt[s]++;
-          C3D_PPROF(t_full);
           tc_fence_after();
-          umma_bf16_ss_pair(tacc, umma_desc_kmajor_k16(aux_addr[s]), umma_desc_kmajor_k16(k16_addr[s]), idesc_l, 0u);
-          umma_commit_pair(&misc->kempty[s], (uint16_t)0x3);
-#ifdef C3D_KERNEL_PROF
-          if (tl_on && acnt[0] == 48u) C3D_TL(1);
-#endif
-          if (kind == 1) {
-            const bool reuse = shared && s == 1;     // the stages slot 0 just used hold my weights too: no wait, I release them
-            if (s == 0) n_shared = n;
-            for (int kc = 0; kc < NCHUNK; ++kc) {
-              const uint32_t m = reuse ? n_shared + kc : n + kc;
-              const uint32_t st = m % NSTAGE, ph = (m / NSTAGE) & 1u;
-              if (!reuse) {
-                C3D_PPROF(t_issue);
-                mbar_wait_cluster(&misc->full[st], ph);
-                C3D_PPROF(t_full);
-                tc_fence_after();
-              }
-              const uint64_t ad = umma_desc_kmajor_sw128(act_addr[s] + kc * ACT_CHUNK);
-              const uint64_t bd = umma_desc_kmajor_sw128(stage_base + st * STAGE_BYTES);
+          const bool reuse = shared && s == 1;       // the stages slot 0 just used hold my weights too: no wait, I release them
+          if (kind == 1 && s == 0) n_shared = n;
+          const uint32_t n0 = reuse ? n_shared : n;
+          const uint64_t auxd = umma_desc_kmajor_k16(aux_addr);
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) umma_bf16_ss_pair(tacc, ad + 2 * kk, bd + 2 * kk, idesc_l, 1u);
-              if (!(shared && s == 0)) umma_commit_pair(&misc->empty[st], (uint16_t)0x3);
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t th = tacc + (uint32_t)h * 128u;
+            if (issue) {
+              umma_bf16_ss_pair(th, auxd, umma_desc_kmajor_k16(k16_addr + (uint32_t)h * 2048u), idesc_l, 0u);
+              if (h == 1) umma_commit_pair(&misc->kempty[s], (uint16_t)0x3);
             }
-            if (!reuse) n += NCHUNK;
+            if (kind == 1) {
+#pragma unroll
+              for (int kc = 0; kc < NCHUNK; ++kc) {
+                const uint32_t m = n0 + (uint32_t)(h * NCHUNK + kc);
+                const uint32_t st = m % NSTAGE, ph = (m / NSTAGE) & 1u;
+                if (!reuse) {
+                  C3D_PROF(0);
+                  mbar_wait_cluster(&misc->full[st], ph);
+                  C3D_PROF(4);
+                  tc_fence_after();
+                }
+                if (issue) {
+                  const uint64_t ad = umma_desc_kmajor_sw128(act_addr + kc * ACT_CHUNK);
+                  const uint64_t bd = umma_desc_kmajor_sw128(stage_base + st * STAGE_BYTES);
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk) umma_bf16_ss_pair(th, ad + 2 * kk, bd + 2 * kk, idesc_l, 1u);
+                  if (!(shared && s == 0)) umma_commit_pair(&misc->empty[st], (uint16_t)0x3);
+                  // half 1 has consumed K-chunks 0, 1: half 0's outputs may overwrite them
+                  if (h == 1 && kc == 1) umma_commit_pair(&misc->act_free[s], (uint16_t)0x3);
+                }
+              }
+            } else if (h == 1) {
+              if (issue) umma_commit_pair(&misc->act_free[s], (uint16_t)0x3);
+            }
+            if (issue) umma_commit_pair(&misc->acc_full[s][h], (uint16_t)0x3);
           }
-          umma_commit_pair(&misc->acc_full[s], (uint16_t)0x3);
-#ifdef C3D_KERNEL_PROF
-          if (tl_on && acnt[0] == 48u) C3D_TL(2);
-#endif
-          if (kind == 0) C3D_PPROF(t_small);
-        } else {
+          if (kind == 1 && !reuse) n += NSTAGE;
+        } else if (issue) {
           // These narrow MMAs are latency-bound when chained on one accumulator, so consecutive K-steps go to different
           // partial accumulators (summed by the epilogue): 2 per channel half for the compositing, 4 for the heads.
-          // (the issuing thread is the bottleneck of these jobs: descriptors are base + immediate, loops fully unrolled)
           if (kind == 3) {                  // compositing: F^T[c][ray] = sum_p feat[p][c] * Wgt[ray][p], per channel half
-            const uint64_t fa = umma_desc_mnmajor_sw128(act_addr[s], ACT_CHUNK), wb = umma_desc_kmajor_sw128(aux_addr[s]);
+            const uint64_t fa = umma_desc_mnmajor_sw128(act_addr, ACT_CHUNK), wb = umma_desc_kmajor_sw128(aux_addr);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
 #pragma unroll
@@ -379,29 +346,30 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_pair_kernel(c
                                   desc_at(wb, (ks >> 2) * 2048 + (ks & 3) * 32), idesc_c, ks >= 2);
           }
           const uint32_t dcol = kind == 3 ? 128u : 0u;         // heads: sdf (job D) / rgb (job D+2)
-          const uint64_t ha = umma_desc_kmajor_sw128(act_addr[s]), hb = umma_desc_kmajor_sw128(heads_addr);
+          const uint64_t ha = umma_desc_kmajor_sw128(act_addr), hb = umma_desc_kmajor_sw128(heads_addr);
 #pragma unroll
           for (int ks = 0; ks < 16; ++ks)
             umma_bf16_ss_pair(tacc + dcol + (uint32_t)(ks & 3) * 16u, desc_at(ha, (ks >> 2) * ACT_CHUNK + (ks & 3) * 32),
                               desc_at(hb, (ks >> 2) * 1024 + (ks & 3) * 32), idesc_h, ks >= 4);
-          umma_commit_pair(&misc->acc_full[s], (uint16_t)0x3);
-          C3D_PPROF(t_small);
+          umma_commit_pair(&misc->acc_full[s][0], (uint16_t)0x3);
         }
+        __syncwarp();
         if (++jb[s] == JOBS) { jb[s] = 0; c[s].next_tile(a); }
       }
     }
-    if (prof && (blockIdx.x % 42 == 0)) {
-      C3D_PPROF(t_issue);
-      printf("c3d prof pair mma[blk %d]: total %lld  wait_a_ready %lld (before L0 %lld, layers %lld, sdf %lld, post %lld)  wait_full %lld  issue %lld  issue_small_jobs %lld\n",
-             (int)blockIdx.x, clock64() - t_begin, t_ready, t_rk[0], t_rk[1], t_rk[2], t_rk[3], t_full, t_issue, t_small);
-    }
+#ifdef C3D_KERNEL_PROF
+    C3D_PROF(0);
+    if (blockIdx.x % 42 == 0 && issue)
+      printf("c3d prof pair mma[blk %d]: total %lld  issue %lld  wait_a_ready layers %lld narrow %lld  wait_kfull %lld  wait_full %lld\n", (int)blockIdx.x,
+             clock64() - prof_begin, prof_t[0], prof_t[1], prof_t[2], prof_t[3], prof_t[4]);
+#endif
    }
   } else if (warp >= 4) {
     // ============================================================ epilogue groups (both CTAs)
-    const int s = (warp - 4) / kEgw;
-    const int te = (int)threadIdx.x - 128 - s * kEgw * 32;
+    const int s = (warp - 4) / EGW;
+    const int te = (int)threadIdx.x - 128 - s * EGW * 32;
     const int t = te & 127;                              // my point row of the tile = my TMEM lane
-    const int grp = te >> 7;                             // kEgw == 8: channel half of the layer stages
+    const int grp = te >> 7;                             // my 64 columns of each accumulator half
     const bool ptg = grp == 0;                           // this thread also runs the per-point stages
     const int quad = warp & 3;
     const uint32_t bar_id = 1u + (uint32_t)s;
@@ -425,21 +393,10 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_pair_kernel(c
       if (lane == 0) { if (leader) mbar_arrive(&misc->a_ready[s]); else mbar_arrive_remote(ready_remote); }
     };
     float carry_f[2] = {0.f, 0.f};                       // partial feature sums of a ray continuing into the next tile
-    (void)ptg;
-    uint32_t jobcnt = 0;
-#ifdef C3D_KERNEL_PROF
-    const bool eprof = (a.debug & 2) != 0 && blockIdx.x < 2 && t == 0;
-#else
-    constexpr bool eprof = false;
-#endif
-    long long e_wait = 0, e_epi = 0, e_pt = 0, e_mark = clock64(), e_begin = e_mark;
-#define C3D_PEPROF(acc) do { if (eprof) { const long long now_ = clock64(); acc += now_ - e_mark; e_mark = now_; } } while (0)
+    uint32_t cnt[2] = {0u, 0u}, cntf = 0;                // completed phases of acc_full[s][0 / 1], act_free[s]
     Cursor cur;
     cur.init(a, ps0 + s, n_pairslots);
-    if (s == 1 && a.stagger > 0) {                       // desynchronise the two slots (see profiles/r01_fused.md)
-      const long long t0 = clock64();
-      while (clock64() - t0 < a.stagger) { }
-    }
+    C3D_PROF_DECL(8);   // 0 other (geometry, point stages, post), 1 wait acc h0, 2 wait act_free, 3 wait acc h1, 4 sines + stores h0, 5 h1, 6 arrive
 
     for (; cur.valid(); ) {
       const int u = cur.pu;
@@ -504,8 +461,8 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_pair_kernel(c
         for (int l = 0; l <= D; ++l) {
           if (l == D) {
             // ---------------------------------------------- sdf head -> alpha -> transmittance (thread = point)
-            mbar_wait(&misc->acc_full[s], jobcnt & 1u);
-            jobcnt++;
+            mbar_wait(&misc->acc_full[s][0], cnt[0] & 1u);
+            cnt[0]++;
             tc_fence_after();
             if (ptg) {
             {
@@ -540,53 +497,51 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_pair_kernel(c
             }
             arrive_ready();
           }
-          C3D_PEPROF(e_pt);
-          mbar_wait(&misc->acc_full[s], jobcnt & 1u);
-          C3D_PEPROF(e_wait);
-#ifdef C3D_KERNEL_PROF
-          const bool etl = (a.debug & 2) && blockIdx.x == 0 && s == 0 && t == 0 && jobcnt == 47u;
-          if (etl) C3D_TL(3);
-#endif
-          jobcnt++;
-          tc_fence_after();
-          if (l == D && ptg) {
-            // the view tile has been consumed: build Wgt[ray slot][point] (bf16, K-major SW128) in its place
-            const int myslot = rl - rl0;
-#pragma unroll
-            for (int jx = 0; jx < RAYS; ++jx)
-              st_bf16(aux_u32 + (uint32_t)((t >> 6) * 2048) + sw128_offset(jx, t & 63), jx == myslot ? wgt : 0.f);
-          }
-          {
-            // my point: 256 channels in 8 double chunks of 32, TMEM loads double-buffered
+          // my point: 64 channels of each accumulator half, TMEM loads double-buffered
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            C3D_PROF(h == 0 ? 0 : 4);
+            mbar_wait(&misc->acc_full[s][h], cnt[h] & 1u);
+            C3D_PROF(h == 0 ? 1 : 3);
+            cnt[h]++;
+            tc_fence_after();
+            const uint32_t tcol = tacc + (uint32_t)(h * 128 + grp * 64);
+            const uint32_t row = row_u32 + (uint32_t)(2 * h + grp) * ACT_CHUNK;   // channels 128 h + 64 grp .. + 63 = K-chunk 2 h + grp
             uint32_t v0[16], v1[16];
-            const int cp0 = kEgw == 8 ? grp * CPT : 0;
-            tmem_ld_32x16(tacc + cp0 * 32, v0);
-#pragma unroll 2
-            for (int cq = 0; cq < CPT; ++cq) {             // channels 32 cp .. 32 cp + 31: chunk cp >> 1, units 4 (cp & 1) ..
-              const int cp = cp0 + cq;
-              const uint32_t row = row_u32 + (uint32_t)(cp >> 1) * ACT_CHUNK;
+            tmem_ld_32x16(tcol, v0);
+            if (h == 0) {
+              // K-chunks 0, 1 (and the aux tile) are still read by the job's half-1 MMAs until act_free
+              C3D_PROF(4);
+              mbar_wait(&misc->act_free[s], cntf & 1u);
+              C3D_PROF(2);
+              cntf++;
+              if (l == D && ptg) {
+                // the view tile has been consumed: build Wgt[ray slot][point] (bf16, K-major SW128) in its place
+                const int myslot = rl - rl0;
+#pragma unroll
+                for (int jx = 0; jx < RAYS; ++jx)
+                  st_bf16(aux_u32 + (uint32_t)((t >> 6) * 2048) + sw128_offset(jx, t & 63), jx == myslot ? wgt : 0.f);
+              }
+            }
+#pragma unroll
+            for (int cq = 0; cq < 2; ++cq) {               // 32 channels per iteration: units 4 cq .. 4 cq + 3 of my row
               tmem_ld_wait();
-              tmem_ld_32x16(tacc + cp * 32 + 16, v1);
-              epilogue16(v0, row, (cp & 1) * 4, r7, a.debug);
+              tmem_ld_32x16(tcol + cq * 32 + 16, v1);
+              epilogue16(v0, row, 4 * cq, r7);
               tmem_ld_wait();
-              if (cq < CPT - 1) tmem_ld_32x16(tacc + (cp + 1) * 32, v0);
-              epilogue16(v1, row, (cp & 1) * 4 + 2, r7, a.debug);
+              if (cq < 1) tmem_ld_32x16(tcol + (cq + 1) * 32, v0);
+              epilogue16(v1, row, 4 * cq + 2, r7);
             }
           }
-#ifdef C3D_KERNEL_PROF
-          if (etl) C3D_TL(4);
-#endif
+          C3D_PROF(5);
           arrive_ready();
-#ifdef C3D_KERNEL_PROF
-          if (etl) C3D_TL(5);
-#endif
-          C3D_PEPROF(e_epi);
+          C3D_PROF(6);
         }
 
         // ------------------------------------------------ post job: composited features (thread = channel) + rgb (thread = point)
         {
-          mbar_wait(&misc->acc_full[s], jobcnt & 1u);
-          jobcnt++;
+          mbar_wait(&misc->acc_full[s][0], cnt[0] & 1u);
+          cnt[0]++;
           tc_fence_after();
           float rgbv[3] = {brgb0, brgb1, brgb2};         // raw rgb of my point: 4 partial sums
           if (ptg) {
@@ -600,9 +555,8 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_pair_kernel(c
             }
           }
           const int tile_end = min((tile + 1) * TILE, npts);      // first point index beyond this tile
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            if (kEgw == 8 && hh != grp) continue;        // 8 warps per slot: one channel half per thread
+          {
+            const int hh = grp;                          // one channel half per thread: lane t <-> channel t + 128 hh
             uint32_t fv[16], fw[16];                     // my CTA's 16 ray-slot columns of channel t + 128 hh, 2 partial sums
             tmem_ld_32x16(tacc + (uint32_t)(hh * 2) * 32u + rank * 16u, fv);
             tmem_ld_32x16(tacc + (uint32_t)(hh * 2 + 1) * 32u + rank * 16u, fw);
@@ -662,11 +616,12 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_pair_kernel(c
         }
       }  // tiles
     }    // pair-units
-    if (eprof) {
-      C3D_PEPROF(e_pt);
-      printf("c3d prof pair eg(blk %d slot %d): total %lld  wait_acc_full(layers) %lld  epilogue %lld  other(point stages, sdf/post waits) %lld\n",
-             (int)blockIdx.x, s, clock64() - e_begin, e_wait, e_epi, e_pt);
-    }
+#ifdef C3D_KERNEL_PROF
+    C3D_PROF(0);
+    if (blockIdx.x < 2 && t == 0)
+      printf("c3d prof pair eg[blk %d slot %d grp %d]: total %lld  other %lld  wait acc_h0 %lld act_free %lld acc_h1 %lld  sines h0 %lld h1 %lld  arrive %lld\n",
+             (int)blockIdx.x, s, grp, clock64() - prof_begin, prof_t[0], prof_t[1], prof_t[2], prof_t[3], prof_t[4], prof_t[5], prof_t[6]);
+#endif
   }
 
   tc_fence_before();

@@ -191,9 +191,9 @@ __global__ void __launch_bounds__(SP_THREADS) style_prep_kernel(const uint8_t* _
 
 // ------------------------------------------------------------------------------------------
 // Per-image weight images of the CTA-pair forward kernel (fused_pair_sm100.cuh): FiLM folded into the GEMM operands.
-//   wimg[b][idx 0..D-1][kc 0..3][half 0..1] : 16 KB stage images [128 rows n][64 k] bf16, K-major SWIZZLE_128B,
-//                                             value bf16(gamma_{b,idx+1}[n] * W_{idx+1}[n][k]),  n = 128 half + row
-//   kimg[b][L 0..D][half 0..1]              : 4 KB K16 images [128 rows n][16 slots], UMMA K-major no-swizzle:
+//   wimg[b][idx 0..D-1][half 0..1][kc 0..3][rank 0..1] : 8 KB stage images [64 rows n][64 k] bf16, K-major SWIZZLE_128B,
+//                                             value bf16(gamma_{b,idx+1}[n] * W_{idx+1}[n][k]),  n = 128 half + 64 rank + row
+//   kimg[b][L 0..D][rank 0..1][half 0..1]   : 2 KB K16 images [64 rows n][16 slots], UMMA K-major no-swizzle:
 //        L = 0     slots 4j..4j+3 = (hi, hi, lo, hi) of gamma W0[n][j]   (x point tile (hi, mid, hi, lo))
 //        L = D     slots j and 3+j = bf16(gamma Wview[n][256+j])         (x view tile (hi x3, lo x3))
 //        all L     slots 12, 13 = hi / lo of the shift gamma b + beta    (x the two "ones" slots of either tile)
@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(256) film_weights_kernel(const uint8_t* __rest
   const float gamma = film[((size_t)b * (D + 1) + idx + 1) * W + n].x;
   const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(blob + L.w32) + (size_t)idx * W * W +
                                                       (size_t)n * W + kc * 64 + q * 32);
-  uint8_t* dst = wimg + (((size_t)b * D + idx) * 8 + blockIdx.x) * 16384 + (size_t)i * 128;
+  // piece (half, kc, rank = i >> 6): [64 rows][64 k], 8 KB; pieces ordered [half][kc][rank] (fused_pair_sm100.cuh)
+  uint8_t* dst = wimg + ((size_t)b * D + idx) * 131072 + (size_t)((half * 4 + kc) * 2 + (i >> 6)) * 8192 + (size_t)(i & 63) * 128;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const float4 x = src[2 * u], y = src[2 * u + 1];
@@ -241,7 +242,8 @@ __global__ void __launch_bounds__(256) film_k16_kernel(const uint8_t* __restrict
   }
   const float sh = bf(f.y);
   s[12] = sh; s[13] = f.y - sh;
-  uint8_t* dst = kimg + (((size_t)b * (D + 1) + l) * 2 + half) * 4096 + k16_offset(i, 0);
+  // [rank = i >> 6][half][64 rows][16]: a CTA of the pair copies its 4 KB (both channel halves) with one bulk copy
+  uint8_t* dst = kimg + ((((size_t)b * (D + 1) + l) * 2 + (i >> 6)) * 2 + half) * 2048 + k16_offset(i & 63, 0);
   *reinterpret_cast<uint4*>(dst) = make_uint4(ptx::pack_bf16x2(s[0], s[1]), ptx::pack_bf16x2(s[2], s[3]),
                                               ptx::pack_bf16x2(s[4], s[5]), ptx::pack_bf16x2(s[6], s[7]));
   *reinterpret_cast<uint4*>(dst + 128) = make_uint4(ptx::pack_bf16x2(s[8], s[9]), ptx::pack_bf16x2(s[10], s[11]),

@@ -16,6 +16,7 @@ import os
 
 import torch
 import torch.nn as nn
+from torch.autograd.function import once_differentiable
 
 from . import _abi
 
@@ -68,7 +69,13 @@ class _SirenParams(nn.Module):
 
 
 def _f32c(t):
-    return t.detach().to(torch.float32).contiguous()
+    return _aligned(t.detach().to(torch.float32).contiguous())
+
+
+def _aligned(t):
+    """The C ABI wants 16-byte aligned pointers; a contiguous view with a storage offset (e.g. the reference's ray
+    chunks `rays_d[:, i:i+n]` at batch 1, model_v3.py:1233-1249) may not be -- copy those."""
+    return t.clone() if t.data_ptr() % 16 else t
 
 
 # ---------------------------------------------------------------------------------------------
@@ -96,6 +103,7 @@ class _NerfFn(torch.autograd.Function):
         return outs
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g_rgb, g_feat, g_sdf, g_mask, g_xyz, g_z):
         styles, a0, a1, a2, a3, near, far = ctx.saved_tensors
         a2 = a2 if ctx.has[0] else None
@@ -123,6 +131,7 @@ class _EikonalFn(torch.autograd.Function):
         return grads[1]
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g_eik):
         styles, pts, rays_d, viewdirs, z_vals, near, far = ctx.saved_tensors
         needs = ctx.needs_input_grad
@@ -147,6 +156,12 @@ class NerfBranch(nn.Module):
         self.sigmoid_beta = nn.Parameter(0.1 * torch.ones(1))
         self.network = _SirenParams(N_layers_renderer, hidden_dim, style_dim, input_dim, view_dim)
         self._cache = None          # (key, packed blob); never pickled / deep-copied
+        # The packed blob is re-derived from the parameters on EVERY call unless `cache_packed` is set.  Tensor version
+        # counters cannot be trusted as a cache key: writes through `.data` (the reference's EMA update,
+        # exp/cips3d/utils.py:79, every training iteration) do not bump them.  Serving code that knows its weights are
+        # frozen sets `cache_packed = True` (then the key is (data_ptr, _version) per parameter) or calls
+        # `invalidate_cache()` after weight surgery.
+        self.cache_packed = False
 
     # -- construction helpers ------------------------------------------------------------------
     @classmethod
@@ -155,7 +170,14 @@ class NerfBranch(nn.Module):
         m = cls(renderer.N_layers_renderer, precision=precision)
         m.load_state_dict(renderer.state_dict(), strict=True)
         p = next(renderer.parameters())
-        return m.to(p.device)
+        m = m.to(p.device)
+        # a frozen / eval generator (projector_v9.py:68 `deepcopy(G).eval().requires_grad_(False)`) stays frozen / eval:
+        # otherwise every call would take the parameter-gradient path
+        src = dict(renderer.named_parameters())
+        for name, q in m.named_parameters():
+            q.requires_grad_(src[name].requires_grad)
+        m.train(renderer.training)
+        return m
 
     def __getstate__(self):
         d = self.__dict__.copy()
@@ -193,14 +215,19 @@ class NerfBranch(nn.Module):
         raw.rgb_weight, raw.rgb_bias = rw.data_ptr(), rb.data_ptr()
         raw.sigma_weight, raw.sigma_bias, raw.sigmoid_beta = sw.data_ptr(), sb.data_ptr(), sbeta.data_ptr()
 
+    def invalidate_cache(self):
+        """Drop the packed blob (only matters with `cache_packed = True`)."""
+        self._cache = None
+
     def packed_weights(self):
-        """Kernel-layout weight blob, rebuilt when any parameter changed (keyed on tensor versions)."""
+        """Kernel-layout weight blob.  Re-packed (two small kernels, in stream order) on every call; with
+        `cache_packed = True` only when a parameter's (data_ptr, _version) changed."""
         ps = self._ordered_params()
         dev = ps[0].device
         if dev.type != "cuda":
             raise RuntimeError("NerfBranch parameters must live on a CUDA device (no CPU path)")
         key = tuple((p.data_ptr(), p._version) for p in ps)
-        if self._cache is not None and self._cache[0] == key:
+        if self.cache_packed and self._cache is not None and self._cache[0] == key:
             return self._cache[1]
         lib = _abi.load()
         D = self.N_layers_renderer
@@ -209,7 +236,11 @@ class NerfBranch(nn.Module):
         raw.D = D
         self._fill_param_struct(raw, keep)
         nbytes = lib.c3d_packed_bytes(D)
-        blob = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        old = self._cache[1] if self._cache is not None else None
+        # the blob is rewritten in place in stream order (earlier launches on this stream have consumed it)
+        blob = old if (old is not None and old.device == dev and old.numel() == nbytes
+                       and not torch.cuda.is_current_stream_capturing()) else \
+            torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _abi.check(lib.c3d_pack_weights(raw, _abi.ptr(blob), nbytes, torch.cuda.current_stream().cuda_stream),
                        "c3d_pack_weights")
@@ -217,15 +248,17 @@ class NerfBranch(nn.Module):
         return blob
 
     # -- launches ---------------------------------------------------------------------------------
-    def _mode(self):
+    def _mode(self, n_samples=None):
         if self.precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
+        if n_samples is not None and n_samples < _abi.MIN_SAMPLES_BF16:
+            return _abi.MODE_FP32          # the tensor-core tiling needs >= 8 samples per ray; fewer run the fp32 kernels
         return _abi.MODE_BF16 if self.precision == "bf16" else _abi.MODE_FP32
 
     def _fill_common(self, P, kind, meta, styles, a0, a1, a2, a3, near, far):
         b, n_rays, N, img_size, static_viewdirs, nchw = meta
         P.abi_version = _abi.ABI_VERSION
-        P.mode = self._mode()
+        P.mode = self._mode(N)
         P.input_kind = kind
         P.feat_layout = _abi.FEAT_NCHW if nchw else _abi.FEAT_NHWC
         P.batch, P.n_rays, P.n_samples, P.D = b, n_rays, N, self.N_layers_renderer
@@ -269,7 +302,7 @@ class NerfBranch(nn.Module):
         """c3d_nerf_forward_save: the forward of a differentiated step, run once in save mode.  Returns (outputs, workspace)
         or None when the path does not apply (fp32 mode, n_samples < 8, C3D_BWD=simt) or the whole-batch workspace exceeds
         the budget `C3D_SAVE_FWD_GB` (default 48 GiB of the 180 GB; 0 disables)."""
-        if self.precision != "bf16":
+        if self._mode(meta[2]) != _abi.MODE_BF16:
             return None
         budget = float(os.environ.get("C3D_SAVE_FWD_GB", "48")) * (1 << 30)
         if budget <= 0:
@@ -375,7 +408,6 @@ class NerfBranch(nn.Module):
             pg = _abi.ParamGrads()
             self._fill_param_struct(pg, g_all)
             B.g_params = C.cast(C.pointer(pg), C.c_void_p)
-            g_params = [g.to(p.dtype) if need else None for g, p, need in zip(g_all, self._ordered_params(), need_params)]
         if g_styles is None and not want_params:
             return None, g_params
         nws = lib.c3d_eikonal_workspace_bytes(B)
@@ -385,6 +417,8 @@ class NerfBranch(nn.Module):
             _abi.check(lib.c3d_eikonal_backward(B, g_eik.data_ptr(), torch.cuda.current_stream().cuda_stream),
                        "c3d_eikonal_backward")
         self.last_launch_count = lib.c3d_last_launch_count()
+        if want_params:                                              # after the launch: `.to` copies for non-fp32 parameters
+            g_params = [g.to(p.dtype) if need else None for g, p, need in zip(g_all, self._ordered_params(), need_params)]
         return g_styles, g_params
 
     def _run(self, kind, meta, styles, a0, a1, a2, a3, near, far):
@@ -414,7 +448,7 @@ class NerfBranch(nn.Module):
         lead = pts.shape[:-2]
         b, N = pts.shape[0], pts.shape[-2]
         n_rays = int(math.prod(lead[1:]))
-        c = lambda t, *s: t.to(torch.float32).reshape(*s).contiguous()
+        c = lambda t, *s: _aligned(t.to(torch.float32).reshape(*s).contiguous())
         meta = (b, n_rays, N, 0, False, False)
         rgb_map, feat, sdf, mask, xyz, _ = self._run(
             _abi.INPUT_POINTS, meta, c(styles, b, self.N_layers_renderer + 1, W), c(pts, b, n_rays, N, 3),
@@ -438,7 +472,7 @@ class NerfBranch(nn.Module):
         only `sdf` and `z_vals` -- the coarse pass of `render_hierarchical`."""
         b = cam_poses.shape[0]
         n_rays = img_size * img_size
-        c = lambda t, *s: t.to(torch.float32).reshape(*s).contiguous()
+        c = lambda t, *s: _aligned(t.to(torch.float32).reshape(*s).contiguous())
         if perturb and ray_offset is None:
             ray_offset = torch.rand(b, img_size, img_size, 1, device=cam_poses.device)   # nerf_utils.py:110
         ro = None if ray_offset is None else c(ray_offset, b, n_rays)
@@ -470,7 +504,7 @@ class NerfBranch(nn.Module):
         if N_samples + N_importance > 256:
             raise ValueError("N_samples + N_importance must be <= 256")
         b, n_rays, N2 = cam_poses.shape[0], img_size * img_size, N_samples + N_importance
-        c = lambda t, *s: t.to(torch.float32).reshape(*s).contiguous()
+        c = lambda t, *s: _aligned(t.to(torch.float32).reshape(*s).contiguous())
         with torch.no_grad():
             coarse = self.render(cam_poses, focal, near, far, styles, img_size=img_size, N_samples=N_samples,
                                  static_viewdirs=static_viewdirs, perturb=perturb, ray_offset=ray_offset,
