@@ -27,6 +27,8 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
 // bf16 forward: C3D_FWD=pair selects the CTA-pair kernel (fused_pair_sm100.cuh), C3D_FWD=v3 the single-CTA one.
 #ifndef C3D_FWD_DEFAULT_PAIR
 #define C3D_FWD_DEFAULT_PAIR 0
@@ -231,9 +233,10 @@ static int forward_pair(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
   a.unit_rays = ur;
   a.units_per_img = (p->n_rays + 2 * ur - 1) / (2 * ur);
   a.wimg = ws + w.wimg; a.kimg = ws + w.kimg;
-  film_weights_kernel<<<dim3(8, p->D, p->batch), 256, 0, st>>>(a.blob, a.L, a.film, ws + w.wimg);
+  static const bool split = env_int("C3D_PAIR_SPLIT", 0) != 0;   // half-split layer jobs (N = 128 MMAs): see fused_pair_sm100.cuh
+  film_weights_kernel<<<dim3(8, p->D, p->batch), 256, 0, st>>>(a.blob, a.L, a.film, ws + w.wimg, split ? 1 : 0);
   C3D_LAUNCH_CHECK();
-  film_k16_kernel<<<dim3(p->D + 1, p->batch), 256, 0, st>>>(a.blob, a.L, a.film, ws + w.kimg);
+  film_k16_kernel<<<dim3(p->D + 1, p->batch), 256, 0, st>>>(a.blob, a.L, a.film, ws + w.kimg, split ? 1 : 0);
   C3D_LAUNCH_CHECK();
   const long long total_pu = (long long)p->batch * a.units_per_img;
   int grid = nsm & ~1;
@@ -247,7 +250,7 @@ static int forward_pair(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  void (*kern)(const fused::Args) = pairk::fused_forward_pair_kernel;
+  void (*kern)(const fused::Args) = split ? pairk::fused_forward_pair_kernel<true> : pairk::fused_forward_pair_kernel<false>;
   C3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pairk::SMEM_BYTES));
   C3D_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   C3D_LAUNCH_CHECK();

@@ -49,8 +49,14 @@ using fused::ACT_CHUNK;
 constexpr int EGW = 8;                         // epilogue warps per slot: warp (quad, grp) owns lanes 32 quad.. and columns 64 grp..
                                                // of each accumulator half; grp 0 threads also run the per-point stages
 constexpr int NTHREADS = 128 + 2 * EGW * 32;   // 640
-constexpr int STAGE_BYTES = 64 * 128;          // [64 weight rows][64 k] bf16, K-major SWIZZLE_128B: this CTA's part of (half, K-chunk)
-constexpr int NSTAGE = 8;                      // one layer: 2 channel halves x 4 K-chunks
+// kSplit = true : a K = 256 layer is issued as two channel halves (N = 128 MMAs), stage = this CTA's [2 K-chunks][64 rows][64 k]
+//                  of (half, K-chunk pair)
+// kSplit = false: one N = 256 MMA per K-step, stage = this CTA's [128 rows][64 k] of a K-chunk
+// Either way 4 stages of 16 KB = 64 KB = one layer of this CTA's weight rows (the producer and the relay pay ~200 cycles per
+// stage, so 8 KB stages starved the issuer).
+constexpr int RING_BYTES = 65536;
+constexpr int STAGE_BYTES = 16384;
+constexpr int NSTAGE = 4;
 constexpr int RAYS = 16;                       // rays touching one tile (n_samples >= 8)
 constexpr int AUX_BYTES = 4096;                // per slot: point / view tile ([128][16] k16) or Wgt ([16][128] sw128)
 constexpr int K16_BYTES = 4096;                // per slot: this CTA's part of the layer's K16 image ([half 2][64 rows][16])
@@ -60,12 +66,14 @@ constexpr size_t KIMG_LAYER_BYTES = (size_t)W * 16 * 2;  // per image and layer 
 
 constexpr int SM_ACT = 0;
 constexpr int SM_STAGE = SM_ACT + 2 * ACT_BYTES;                 // 131072
-constexpr int SM_K16 = SM_STAGE + NSTAGE * STAGE_BYTES;          // 196608
+constexpr int SM_K16 = SM_STAGE + RING_BYTES;                    // 196608
 constexpr int SM_HEADS = SM_K16 + 2 * K16_BYTES;                 // 204800
 constexpr int SM_AUX = SM_HEADS + HEADS_BYTES;                   // 208896
 constexpr int SM_OM = SM_AUX + 2 * AUX_BYTES;                    // 217088  [slot][128] float
 constexpr int SM_RAYACC = SM_OM + 2 * TILE * 4;                  // 218112  [slot][RAYS*2][8] float
-constexpr int SM_MISC = SM_RAYACC + 2 * RAYS * 2 * 8 * 4;        // 220160
+constexpr int SM_WSIG = SM_RAYACC + 2 * RAYS * 2 * 8 * 4;        // 220160  sigma_linear.weight, fp32 [256]
+constexpr int SM_SDFP = SM_WSIG + W * 4;                         // 221184  [slot][128] float: sdf partial sums of column group 1
+constexpr int SM_MISC = SM_SDFP + 2 * TILE * 4;                  // 222208
 constexpr int SM_TOTAL = SM_MISC + 256;
 constexpr int SMEM_BYTES = SM_TOTAL + 1024;
 
@@ -88,6 +96,9 @@ struct Cursor {
   int pu, tile, ntiles, total, step;
   __device__ __forceinline__ void init(const Args& a, int ps, int nps) {
     total = a.batch * a.units_per_img; step = nps; pu = ps; tile = 0;
+#ifdef C3D_KERNEL_PROF
+    if ((a.debug & 16) && (ps & 1)) pu = total;      // experiment: odd pair-slots idle (one slot per pair runs alone)
+#endif
     ntiles = pu < total ? pu_tiles(a, pu) : 0;
   }
   __device__ __forceinline__ bool valid() const { return pu < total; }
@@ -100,10 +111,10 @@ struct Cursor {
 __device__ __forceinline__ bool same_weights(const Args& a, const Cursor& c0, const Cursor& c1) {
   return c0.valid() && c1.valid() && c0.pu / a.units_per_img == c1.pu / a.units_per_img;
 }
-// kind of job j: 0 = layer 0 (K16 only), 1 = K = 256 layer, 2 = sdf head, 3 = post
-__device__ __forceinline__ int job_kind(int j, int D) { return j == 0 ? 0 : (j == D ? 2 : (j == D + 2 ? 3 : 1)); }
-__device__ __forceinline__ int job_film_layer(int j, int D) { return j == 0 ? 0 : (j <= D - 1 ? j : D); }   // index into kimg
-__device__ __forceinline__ int job_w_layer(int j, int D) { return j <= D - 1 ? j - 1 : D - 1; }             // index into wimg
+// kind of job j: 0 = layer 0 (K16 only), 1 = K = 256 layer (hidden 1..D-1, view layer D), 3 = post
+__device__ __forceinline__ int job_kind(int j, int D) { return j == 0 ? 0 : (j == D + 1 ? 3 : 1); }
+__device__ __forceinline__ int job_film_layer(int j, int D) { return j; }        // jobs 0..D: index into kimg
+__device__ __forceinline__ int job_w_layer(int j, int D) { return j - 1; }       // jobs 1..D: index into wimg
 
 __device__ __forceinline__ void st_bf16(uint32_t smem_addr, float x) {
   uint32_t r;
@@ -146,14 +157,33 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], uint32_t row
 #define C3D_PROF(i) do { } while (0)
 #endif
 
+// the same for the last hidden layer: also the sdf head  sum_c wsig[c] * sin(...)  over these 16 channels, from the fp32 sines
+// (wsig: shared-memory address of the 16 weights; warp-uniform, so the loads are broadcasts)
+__device__ __forceinline__ void epilogue16_sdf(const uint32_t (&v)[16], uint32_t row_addr, int u0, int r7, const float4* wsig,
+                                               float (&acc)[4]) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = __sinf(__uint_as_float(v[g * 8 + i]));
+    const float4 wa = wsig[2 * g], wb = wsig[2 * g + 1];
+    acc[0] = fmaf(wa.x, o[0], acc[0]); acc[1] = fmaf(wa.y, o[1], acc[1]); acc[2] = fmaf(wa.z, o[2], acc[2]); acc[3] = fmaf(wa.w, o[3], acc[3]);
+    acc[0] = fmaf(wb.x, o[4], acc[0]); acc[1] = fmaf(wb.y, o[5], acc[1]); acc[2] = fmaf(wb.z, o[6], acc[2]); acc[3] = fmaf(wb.w, o[7], acc[3]);
+    st_v4(row_addr + (uint32_t)(((u0 + g) ^ r7) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+          pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  }
+}
+
+template <bool kSplit>
 __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const Args a) {
+  constexpr int NH = kSplit ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   Misc* misc = reinterpret_cast<Misc*>(smem + SM_MISC);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform role index
   const int lane = threadIdx.x & 31;
   const int D = a.D, N = a.n_samples;
-  const int JOBS = D + 3;
+  const int JOBS = D + 2;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int n_pairslots = (int)gridDim.x;          // 2 per cluster
@@ -183,6 +213,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
     }
     float* ra = reinterpret_cast<float*>(smem + SM_RAYACC);
     for (int i = threadIdx.x; i < 2 * RAYS * 2 * 8; i += NTHREADS) ra[i] = 0.f;
+    float* ws_ = reinterpret_cast<float*>(smem + SM_WSIG);
+    for (int i = threadIdx.x; i < W; i += NTHREADS) ws_[i] = reinterpret_cast<const float*>(a.blob + a.L.wsig)[i];
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -213,7 +245,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
           if (kind == 1 && !(shared && s == 1)) {
             const uint8_t* wl = a.wimg + (img * D + job_w_layer(j, D)) * WIMG_LAYER_BYTES + rank * STAGE_BYTES;
 #pragma unroll 1
-            for (int pc = 0; pc < NSTAGE; ++pc, ++n) {             // piece pc = half * 4 + K-chunk, in the order the issuer consumes
+            for (int pc = 0; pc < NSTAGE; ++pc, ++n) {             // piece pc = half * 2 + K-chunk pair / K-chunk, in the order the issuer consumes
               const uint32_t st = n % NSTAGE, ph = (n / NSTAGE) & 1u;
               mbar_wait(&misc->empty[st], ph ^ 1u);
               mbar_arrive_expect_tx(&misc->full[st], STAGE_BYTES);
@@ -262,7 +294,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
     // operand is then uniform by data flow and lives in uniform registers.  (With the loop inside `if (elect_one())`
     // ptxas wrapped each UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall -- ~170 cycles per MMA.)
     const bool issue = elect_one();
-    const uint32_t idesc_l = umma_idesc_bf16(256, 128, 0, 0);      // one channel half of a layer / K16 side product: both K-major
+    const uint32_t idesc_l = umma_idesc_bf16(256, kSplit ? 128 : 256, 0, 0);   // (one channel half of) a layer / K16 side product: both K-major
     const uint32_t idesc_h = umma_idesc_bf16(256, 16, 0, 0);       // heads: B = 8 rows of heads16 per CTA
     const uint32_t idesc_c = umma_idesc_bf16(256, 32, 1, 0);       // compositing: A = feat^T (MN-major view), B = Wgt
     const uint32_t act_base = smem_u32(smem + SM_ACT);
@@ -300,18 +332,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
           const uint32_t n0 = reuse ? n_shared : n;
           const uint64_t auxd = umma_desc_kmajor_k16(aux_addr);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < NH; ++h) {
             const uint32_t th = tacc + (uint32_t)h * 128u;
             if (issue) {
               umma_bf16_ss_pair(th, auxd, umma_desc_kmajor_k16(k16_addr + (uint32_t)h * 2048u), idesc_l, 0u);
-              if (h == 1) umma_commit_pair(&misc->kempty[s], (uint16_t)0x3);
+              if (h == NH - 1) umma_commit_pair(&misc->kempty[s], (uint16_t)0x3);
             }
             if (kind == 1) {
 #pragma unroll
               for (int kc = 0; kc < NCHUNK; ++kc) {
-                const uint32_t m = n0 + (uint32_t)(h * NCHUNK + kc);
+                const uint32_t m = n0 + (uint32_t)(kSplit ? h * 2 + (kc >> 1) : kc);
                 const uint32_t st = m % NSTAGE, ph = (m / NSTAGE) & 1u;
-                if (!reuse) {
+                const bool first = !kSplit || (kc & 1) == 0, last = !kSplit || (kc & 1) == 1;   // K-chunks of the stage
+                if (!reuse && first) {
                   C3D_PROF(0);
                   mbar_wait_cluster(&misc->full[st], ph);
                   C3D_PROF(4);
@@ -319,15 +352,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
                 }
                 if (issue) {
                   const uint64_t ad = umma_desc_kmajor_sw128(act_addr + kc * ACT_CHUNK);
-                  const uint64_t bd = umma_desc_kmajor_sw128(stage_base + st * STAGE_BYTES);
+                  const uint64_t bd = umma_desc_kmajor_sw128(stage_base + st * STAGE_BYTES + (kSplit ? (kc & 1) * 8192 : 0));
 #pragma unroll
                   for (int kk = 0; kk < 4; ++kk) umma_bf16_ss_pair(th, ad + 2 * kk, bd + 2 * kk, idesc_l, 1u);
-                  if (!(shared && s == 0)) umma_commit_pair(&misc->empty[st], (uint16_t)0x3);
+                  if (last && !(shared && s == 0)) umma_commit_pair(&misc->empty[st], (uint16_t)0x3);
                   // half 1 has consumed K-chunks 0, 1: half 0's outputs may overwrite them
-                  if (h == 1 && kc == 1) umma_commit_pair(&misc->act_free[s], (uint16_t)0x3);
+                  if (kSplit && h == 1 && kc == 1) umma_commit_pair(&misc->act_free[s], (uint16_t)0x3);
                 }
               }
-            } else if (h == 1) {
+            } else if (kSplit && h == 1) {
               if (issue) umma_commit_pair(&misc->act_free[s], (uint16_t)0x3);
             }
             if (issue) umma_commit_pair(&misc->acc_full[s][h], (uint16_t)0x3);
@@ -336,7 +369,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
         } else if (issue) {
           // These narrow MMAs are latency-bound when chained on one accumulator, so consecutive K-steps go to different
           // partial accumulators (summed by the epilogue): 2 per channel half for the compositing, 4 for the heads.
-          if (kind == 3) {                  // compositing: F^T[c][ray] = sum_p feat[p][c] * Wgt[ray][p], per channel half
+          {                                 // compositing: F^T[c][ray] = sum_p feat[p][c] * Wgt[ray][p], per channel half
             const uint64_t fa = umma_desc_mnmajor_sw128(act_addr, ACT_CHUNK), wb = umma_desc_kmajor_sw128(aux_addr);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
@@ -345,7 +378,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
                 umma_bf16_ss_pair(tacc + (uint32_t)(h * 2 + (ks & 1)) * 32u, desc_at(fa, 2 * h * ACT_CHUNK + ks * 2048),
                                   desc_at(wb, (ks >> 2) * 2048 + (ks & 3) * 32), idesc_c, ks >= 2);
           }
-          const uint32_t dcol = kind == 3 ? 128u : 0u;         // heads: sdf (job D) / rgb (job D+2)
+          const uint32_t dcol = 128u;                          // rgb head (rows 0..2 of heads16)
           const uint64_t ha = umma_desc_kmajor_sw128(act_addr), hb = umma_desc_kmajor_sw128(heads_addr);
 #pragma unroll
           for (int ks = 0; ks < 16; ++ks)
@@ -376,6 +409,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
     uint8_t* aux = smem + SM_AUX + s * AUX_BYTES;
     const uint32_t aux_u32 = smem_u32(aux);
     float* omS = reinterpret_cast<float*>(smem + SM_OM) + s * TILE;
+    float* sdfS = reinterpret_cast<float*>(smem + SM_SDFP) + s * TILE;
     float* rayacc = reinterpret_cast<float*>(smem + SM_RAYACC) + s * RAYS * 2 * 8;
     const uint32_t tacc = tmem_base + (uint32_t)s * 256u + ((uint32_t)(quad * 32) << 16);
     const float* scal = reinterpret_cast<const float*>(a.blob + a.L.scal);
@@ -457,59 +491,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
         arrive_ready();
 
         float sdf = 0.f, wgt = 0.f;
+        float sdfa[4] = {0.f, 0.f, 0.f, 0.f};                // partial sums of the sdf head over my channels
         // ------------------------------------------------ layers 0..D (D = view layer)
         for (int l = 0; l <= D; ++l) {
-          if (l == D) {
-            // ---------------------------------------------- sdf head -> alpha -> transmittance (thread = point)
-            mbar_wait(&misc->acc_full[s][0], cnt[0] & 1u);
-            cnt[0]++;
-            tc_fence_after();
-            if (ptg) {
-            {
-              uint32_t v4[4][4];                     // heads16 rows 4, 5 (hi / lo of sigma_linear.weight), 4 partial sums
-#pragma unroll
-              for (int pp = 0; pp < 4; ++pp) tmem_ld_32x4(tacc + pp * 16 + 4, v4[pp]);
-              tmem_ld_wait();
-              tc_fence_before();
-              sdf = bsig;
-#pragma unroll
-              for (int pp = 0; pp < 4; ++pp) sdf += __uint_as_float(v4[pp][0]) + __uint_as_float(v4[pp][1]);
-            }
-            if (valid) a.sdf[gray * N + k] = sdf;
-            const float sigma = sigmoid_precise(-sdf * inv_beta) * inv_beta;
-            const float alpha = 1.0f - expf(-sigma * dist);
-            const float om = 1.0f - alpha + 1e-10f;
-            omS[t] = valid ? om : 1.0f;
-            // view tile of the view layer's K16 product: slots 0..2 / 3..5 = hi / lo of the view direction, 12, 13 = 1
-            {
-              const float h0 = __bfloat162float(__float2bfloat16_rn(vx)), h1 = __bfloat162float(__float2bfloat16_rn(vy)),
-                          h2 = __bfloat162float(__float2bfloat16_rn(vz));
-              st_v4(aux_row, pack_bf16x2(h0, h1), pack_bf16x2(h2, vx - h0), pack_bf16x2(vy - h1, vz - h2), 0u);
-              st_v4(aux_row + 128, 0u, 0u, pack_bf16x2(1.0f, 1.0f), 0u);
-            }
-            named_bar_sync(bar_id, TILE);
-            const int first_row = t - k;
-            float T = first_row < 0 ? misc->carry[s] : 1.0f;
-            for (int m = max(first_row, 0); m < t; ++m) T *= omS[m];
-            wgt = valid ? alpha * T : 0.f;
-            named_bar_sync(bar_id, TILE);
-            if (t == TILE - 1) misc->carry[s] = (k == N - 1) ? 1.0f : T * om;
-            }
-            arrive_ready();
-          }
-          // my point: 64 channels of each accumulator half, TMEM loads double-buffered
+          // my point: kSplit: 64 channels of each accumulator half (K-chunk 2 h + grp); else channels 128 grp .. + 127
+          // (K-chunks 2 grp, 2 grp + 1); TMEM loads double-buffered
 #pragma unroll 1
           for (int h = 0; h < 2; ++h) {
             C3D_PROF(h == 0 ? 0 : 4);
-            mbar_wait(&misc->acc_full[s][h], cnt[h] & 1u);
+            if (kSplit || h == 0) {
+              mbar_wait(&misc->acc_full[s][h], cnt[h] & 1u);
+              cnt[h]++;
+              tc_fence_after();
+            }
             C3D_PROF(h == 0 ? 1 : 3);
-            cnt[h]++;
-            tc_fence_after();
-            const uint32_t tcol = tacc + (uint32_t)(h * 128 + grp * 64);
-            const uint32_t row = row_u32 + (uint32_t)(2 * h + grp) * ACT_CHUNK;   // channels 128 h + 64 grp .. + 63 = K-chunk 2 h + grp
+            const int chunk = kSplit ? 2 * h + grp : 2 * grp + h;
+            const uint32_t tcol = tacc + (uint32_t)chunk * 64u;
+            const uint32_t row = row_u32 + (uint32_t)chunk * ACT_CHUNK;
             uint32_t v0[16], v1[16];
             tmem_ld_32x16(tcol, v0);
-            if (h == 0) {
+            if (kSplit && h == 0) {
               // K-chunks 0, 1 (and the aux tile) are still read by the job's half-1 MMAs until act_free
               C3D_PROF(4);
               mbar_wait(&misc->act_free[s], cntf & 1u);
@@ -523,19 +524,72 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
                   st_bf16(aux_u32 + (uint32_t)((t >> 6) * 2048) + sw128_offset(jx, t & 63), jx == myslot ? wgt : 0.f);
               }
             }
+            if (!kSplit && h == 0 && l == D && ptg) {
+              const int myslot = rl - rl0;                 // all MMAs of the view layer are complete: aux is free
 #pragma unroll
-            for (int cq = 0; cq < 2; ++cq) {               // 32 channels per iteration: units 4 cq .. 4 cq + 3 of my row
-              tmem_ld_wait();
-              tmem_ld_32x16(tcol + cq * 32 + 16, v1);
-              epilogue16(v0, row, 4 * cq, r7);
-              tmem_ld_wait();
-              if (cq < 1) tmem_ld_32x16(tcol + (cq + 1) * 32, v0);
-              epilogue16(v1, row, 4 * cq + 2, r7);
+              for (int jx = 0; jx < RAYS; ++jx)
+                st_bf16(aux_u32 + (uint32_t)((t >> 6) * 2048) + sw128_offset(jx, t & 63), jx == myslot ? wgt : 0.f);
+            }
+            const float4* wsg = reinterpret_cast<const float4*>(smem + SM_WSIG) + chunk * 16;   // 64 weights of this K-chunk
+            if (l == D - 1) {
+#pragma unroll
+              for (int cq = 0; cq < 2; ++cq) {             // 32 channels per iteration: units 4 cq .. 4 cq + 3 of my row
+                tmem_ld_wait();
+                tmem_ld_32x16(tcol + cq * 32 + 16, v1);
+                epilogue16_sdf(v0, row, 4 * cq, r7, wsg + 8 * cq, sdfa);
+                tmem_ld_wait();
+                if (cq < 1) tmem_ld_32x16(tcol + (cq + 1) * 32, v0);
+                epilogue16_sdf(v1, row, 4 * cq + 2, r7, wsg + 8 * cq + 4, sdfa);
+              }
+            } else {
+#pragma unroll
+              for (int cq = 0; cq < 2; ++cq) {
+                tmem_ld_wait();
+                tmem_ld_32x16(tcol + cq * 32 + 16, v1);
+                epilogue16(v0, row, 4 * cq, r7);
+                tmem_ld_wait();
+                if (cq < 1) tmem_ld_32x16(tcol + (cq + 1) * 32, v0);
+                epilogue16(v1, row, 4 * cq + 2, r7);
+              }
             }
           }
           C3D_PROF(5);
-          arrive_ready();
-          C3D_PROF(6);
+          if (l == D - 1) {
+            const float sdfp = (sdfa[0] + sdfa[1]) + (sdfa[2] + sdfa[3]);
+            // the last hidden layer is stored: hand the tile to the view-layer job first (view tile in place of the point
+            // tile: slots 0..2 / 3..5 = hi / lo of the view direction, 12, 13 = 1), then -- under its MMAs -- density,
+            // alpha and transmittance of my point (thread = point; the column group 1 thread passes its half of the sdf sum)
+            if (ptg) {
+              const float h0 = __bfloat162float(__float2bfloat16_rn(vx)), h1 = __bfloat162float(__float2bfloat16_rn(vy)),
+                          h2 = __bfloat162float(__float2bfloat16_rn(vz));
+              st_v4(aux_row, pack_bf16x2(h0, h1), pack_bf16x2(h2, vx - h0), pack_bf16x2(vy - h1, vz - h2), 0u);
+              st_v4(aux_row + 128, 0u, 0u, pack_bf16x2(1.0f, 1.0f), 0u);
+            } else {
+              sdfS[t] = sdfp;
+            }
+            arrive_ready();
+            C3D_PROF(6);
+            named_bar_sync(bar_id + 2u, 2 * TILE);         // all 8 warps of the slot: the partial sums are written
+            if (ptg) {
+              sdf = bsig + sdfp + sdfS[t];
+              if (valid) a.sdf[gray * N + k] = sdf;
+              const float sigma = sigmoid_precise(-sdf * inv_beta) * inv_beta;
+              const float alpha = 1.0f - expf(-sigma * dist);
+              const float om = 1.0f - alpha + 1e-10f;
+              omS[t] = valid ? om : 1.0f;
+              named_bar_sync(bar_id, TILE);
+              const int first_row = t - k;
+              float T = first_row < 0 ? misc->carry[s] : 1.0f;
+              for (int m = max(first_row, 0); m < t; ++m) T *= omS[m];
+              wgt = valid ? alpha * T : 0.f;
+              named_bar_sync(bar_id, TILE);
+              if (t == TILE - 1) misc->carry[s] = (k == N - 1) ? 1.0f : T * om;
+            }
+            sdfa[0] = sdfa[1] = sdfa[2] = sdfa[3] = 0.f;
+          } else {
+            arrive_ready();
+            C3D_PROF(6);
+          }
         }
 
         // ------------------------------------------------ post job: composited features (thread = channel) + rgb (thread = point)
