@@ -169,6 +169,7 @@ def run_inversion(args, cfg, rank, world, local_rank):
     m = c3d.NerfBranch(D, precision=args.precision)
     m.load_state_dict({k: torch.from_numpy(v) for k, v in O.init_params(D, seed=0).items()}, strict=True)
     m = m.to(dev).eval().requires_grad_(False)
+    m.cache_packed = True                        # frozen weights: pack them once (the default re-packs on every call)
     g = torch.Generator().manual_seed(5 + rank)
     host_t = (torch.rand(n_t, 3, IMG, IMG, generator=g) * 2 - 1).pin_memory()
     tgt = host_t.to(dev)
@@ -337,6 +338,7 @@ def main():
     m = c3d.NerfBranch(D, precision=args.precision)
     m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
     m = m.to(dev).eval().requires_grad_(False)
+    m.cache_packed = True                        # serving: frozen weights are packed once (the default re-packs on every call)
     c2w, focal, near, far, styles = workload(cfg, seed_latent=1 + rank, seed_pose=2 + rank)
     B = c2w.shape[0]
     host = [torch.from_numpy(x).pin_memory() for x in (c2w, focal, near, far, styles)]

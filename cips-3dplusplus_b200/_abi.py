@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("C3D_LIB") or os.path.join(HERE, "libc3dpp.so")   # C3D_LIB: A/B builds (bench_tools)
 SRC = os.path.join(HERE, "csrc", "c3d_abi.cu")
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_LAYERS = 16
 MIN_SAMPLES_BF16 = 8     # fused::MIN_SAMPLES (csrc/fused_common.cuh)
 MODE_FP32, MODE_BF16 = 0, 1
@@ -89,6 +89,7 @@ EXPORTS = {
     "c3d_abi_version": (C.c_int, []),
     "c3d_last_error": (C.c_char_p, []),
     "c3d_last_launch_count": (C.c_int, []),
+    "c3d_set_option": (C.c_int, [C.c_char_p, C.c_char_p]),
     "c3d_packed_bytes": (C.c_size_t, [C.c_int32]),
     "c3d_pack_weights": (C.c_int, [C.POINTER(RawParams), _fp, C.c_size_t, _fp]),
     "c3d_workspace_bytes": (C.c_size_t, [C.POINTER(FwdParams)]),
@@ -146,6 +147,15 @@ def load():
         raise RuntimeError(f"libc3dpp.so ABI version {v} != binding {ABI_VERSION}; rebuild the library")
     _lib = lib
     return lib
+
+
+def set_options(**kw):
+    """Kernel-variant options for A/B runs and tests (c3d_set_option): fwd='pair'|'v3', cluster=1|2, grid=N, egw=4|8,
+    bwd='tc'|'simt', resample='auto'|'warp'|'lane', resample_rb=N, debug=mask.  The library reads the C3D_* environment
+    variables once at first use; after that only this call changes an option."""
+    lib = load()
+    for k, v in kw.items():
+        check(lib.c3d_set_option(k.encode(), str(v).encode()), "c3d_set_option")
 
 
 class C3DError(RuntimeError):

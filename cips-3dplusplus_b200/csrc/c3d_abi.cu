@@ -27,22 +27,75 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+// ------------------------------------------------------------------------------------------
+// Tuning options.  Read ONCE from the environment (first use), changed afterwards only through c3d_set_option -- no
+// getenv on the launch path.
+//   fwd       "pair" (default: CTA-pair kernel, fused_pair_sm100.cuh) | "v3" (single-CTA kernel, fused_bf16_sm100.cuh)
+//   cluster   1 | 2 (default)   single-CTA kernels: weight multicast across a cluster of 2
+//   grid      0 (default: one CTA per SM) | CTAs of the persistent kernels
+//   egw       4 (default) | 8   single-CTA forward: epilogue warps per slot
+//   bwd       "tc" (default) | "simt"   force the FP32-pipe backward
+//   resample  "auto" (default) | "warp" | "lane";  resample_rb  rays per block of the warp kernel (0 = auto)
+//   debug     bit mask for builds with -DC3D_KERNEL_PROF (ignored by release builds)
+// ------------------------------------------------------------------------------------------
+struct Options { int fwd_pair, cluster, grid, egw, bwd_simt, resample, resample_rb, debug; };
+static int parse_option(Options& o, const char* key, const char* val) {
+  if (!key || !val) return -1;
+  if (!strcmp(key, "fwd")) { if (!strcmp(val, "pair")) o.fwd_pair = 1; else if (!strcmp(val, "v3")) o.fwd_pair = 0; else return -1; }
+  else if (!strcmp(key, "cluster")) { const int v = atoi(val); if (v != 1 && v != 2) return -1; o.cluster = v; }
+  else if (!strcmp(key, "grid")) { const int v = atoi(val); if (v < 0) return -1; o.grid = v; }
+  else if (!strcmp(key, "egw")) { const int v = atoi(val); if (v != 4 && v != 8) return -1; o.egw = v; }
+  else if (!strcmp(key, "bwd")) { if (!strcmp(val, "simt")) o.bwd_simt = 1; else if (!strcmp(val, "tc")) o.bwd_simt = 0; else return -1; }
+  else if (!strcmp(key, "resample")) {
+    if (!strcmp(val, "auto")) o.resample = 0; else if (!strcmp(val, "warp")) o.resample = 1; else if (!strcmp(val, "lane")) o.resample = 2; else return -1;
+  }
+  else if (!strcmp(key, "resample_rb")) { const int v = atoi(val); if (v < 0 || v % 4) return -1; o.resample_rb = v; }
+  else if (!strcmp(key, "debug")) o.debug = atoi(val);
+  else return -1;
+  return 0;
+}
+static Options& options() {
+  static Options o = [] {
+    Options d{1, 2, 0, 4, 0, 0, 0, 0};
+    const char* keys[][2] = {{"C3D_FWD", "fwd"}, {"C3D_CLUSTER", "cluster"}, {"C3D_GRID", "grid"}, {"C3D_EGW", "egw"}, {"C3D_BWD", "bwd"},
+                             {"C3D_RESAMPLE", "resample"}, {"C3D_RESAMPLE_RB", "resample_rb"}, {"C3D_DEBUG", "debug"}};
+    for (auto& k : keys) { const char* e = getenv(k[0]); if (e) parse_option(d, k[1], e); }
+    return d;
+  }();
+  return o;
+}
 
-// bf16 forward: C3D_FWD=pair selects the CTA-pair kernel (fused_pair_sm100.cuh), C3D_FWD=v3 the single-CTA one.
-#ifndef C3D_FWD_DEFAULT_PAIR
-#define C3D_FWD_DEFAULT_PAIR 0
-#endif
+// per-device facts and one-time function attributes
+constexpr int MAX_DEV = 64;
+static int device_sms(int* dev_out = nullptr) {
+  static int sms[MAX_DEV] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  if (dev_out) *dev_out = dev;
+  int& n = sms[dev & (MAX_DEV - 1)];
+  if (n == 0 && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  return n;
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize once per (call site, device): `slot` indexes the kernels sharing a call site
+#define C3D_SMEM_ATTR(kern, bytes, slot, nslots)                                                              \
+  do {                                                                                                        \
+    static int done_[MAX_DEV][nslots] = {};                                                                   \
+    int dev_ = 0;                                                                                             \
+    device_sms(&dev_);                                                                                        \
+    int& d_ = done_[dev_ & (MAX_DEV - 1)][slot];                                                              \
+    if (d_ < (int)(bytes)) {                                                                                  \
+      C3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));        \
+      d_ = (int)(bytes);                                                                                      \
+    }                                                                                                         \
+  } while (0)
 // density-only pass: none of the four map outputs is requested (only sdf / z_vals_out)
 static bool fwd_sdf_only(const c3d_fwd_params* p) { return !p->rgb_map && !p->feature_map && !p->mask && !p->xyz; }
 
+// the plain bf16 forward runs the CTA-pair kernel; the density-only pass (and the save-mode forward of the backward) run the
+// single-CTA kernel, which has those modes
 static bool fwd_uses_pair(const c3d_fwd_params* p) {
   if (fwd_sdf_only(p)) return false;
-  const char* e = getenv("C3D_FWD");
-  bool pair = C3D_FWD_DEFAULT_PAIR != 0;
-  if (e && strcmp(e, "v3") == 0) pair = false;
-  if (e && strcmp(e, "pair") == 0) pair = true;
-  return pair && p->mode == C3D_MODE_BF16 && p->n_samples >= fused::MIN_SAMPLES;
+  return options().fwd_pair && p->mode == C3D_MODE_BF16 && p->n_samples >= fused::MIN_SAMPLES;
 }
 
 struct FwdWs {
@@ -142,11 +195,7 @@ static int gcd_(int a, int b) { return b ? gcd_(b, a % b) : a; }
 // Work unit = whole rays whose points fill whole 128-row tiles when possible (u0 rays); about 6 tiles per unit for
 // large batches, fewer when that would leave slots of the persistent grid without work (small batches).
 static int unit_rays_for(const c3d_fwd_params* p) {
-  static int nsm = 0;
-  if (nsm == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) nsm = 148;
-  }
+  const int nsm = device_sms();
   const int u0 = 128 / gcd_(p->n_samples, 128);
   int ur = u0;
   while (ur * p->n_samples < 6 * 128) ur += u0;
@@ -174,26 +223,20 @@ static void fused_fill_args(fused::Args& a, const c3d_fwd_params* p, const float
   a.rgb_map = p->rgb_map; a.feature_map = p->feature_map; a.sdf = p->sdf; a.mask = p->mask; a.xyz = p->xyz;
   a.z_vals_out = p->z_vals_out;
   a.sdf_only = fwd_sdf_only(p) ? 1 : 0;
-  { const char* d = getenv("C3D_DEBUG"); a.debug = d ? atoi(d) : 0; }
+  a.debug = options().debug;
 }
 
 // kind: 0 forward, 1 forward + save (backward support), 2 backward
 static int fused_launch(const fused::Args& a, int kind, cudaStream_t st) {
-  int dev = 0, nsm = 0;
-  C3D_CUDA(cudaGetDevice(&dev));
-  C3D_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  const char* env = getenv("C3D_CLUSTER");
-  int cluster = env ? atoi(env) : 2;
-  if (cluster != 1 && cluster != 2) cluster = 2;
+  const int nsm = device_sms();
+  const int cluster = options().cluster;
   const long long total_units = (long long)a.batch * a.units_per_img;
   int grid = nsm;
   if ((long long)grid * 2 > total_units) grid = (int)((total_units + 1) / 2);
   if (grid < 1) grid = 1;
   if (cluster == 2) grid = (grid + 1) & ~1;
-  const char* genv = getenv("C3D_GRID");
-  if (genv && atoi(genv) > 0) { grid = atoi(genv); if (cluster == 2) grid = (grid + 1) & ~1; }
-  const char* eenv = getenv("C3D_EGW");
-  const int egw = (kind == 0 && eenv && atoi(eenv) == 8) ? 8 : 4;   // epilogue warps per slot (tuning knob; 4 measured best)
+  if (options().grid > 0) { grid = options().grid; if (cluster == 2) grid = (grid + 1) & ~1; }
+  const int egw = (kind == 0 && options().egw == 8) ? 8 : 4;   // epilogue warps per slot (tuning knob; 4 measured best)
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
@@ -205,11 +248,13 @@ static int fused_launch(const fused::Args& a, int kind, cudaStream_t st) {
   attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   void (*kern)(const fused::Args);
-  if (kind == 2) kern = cluster == 2 ? fusedbwd::fused_backward_kernel<2> : fusedbwd::fused_backward_kernel<1>;
-  else if (kind == 1) kern = cluster == 2 ? fused::fused_forward_kernel<2, 4, true> : fused::fused_forward_kernel<1, 4, true>;
-  else if (egw == 8) kern = cluster == 2 ? fused::fused_forward_kernel<2, 8> : fused::fused_forward_kernel<1, 8>;
-  else kern = cluster == 2 ? fused::fused_forward_kernel<2, 4> : fused::fused_forward_kernel<1, 4>;
-  C3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
+  int variant;                                       // index of `kern` among the eight kernels of this call site
+  if (kind == 2) { kern = cluster == 2 ? fusedbwd::fused_backward_kernel<2> : fusedbwd::fused_backward_kernel<1>; variant = 0; }
+  else if (kind == 1) { kern = cluster == 2 ? fused::fused_forward_kernel<2, 4, true> : fused::fused_forward_kernel<1, 4, true>; variant = 2; }
+  else if (egw == 8) { kern = cluster == 2 ? fused::fused_forward_kernel<2, 8> : fused::fused_forward_kernel<1, 8>; variant = 4; }
+  else { kern = cluster == 2 ? fused::fused_forward_kernel<2, 4> : fused::fused_forward_kernel<1, 4>; variant = 6; }
+  variant += cluster == 2 ? 1 : 0;
+  C3D_SMEM_ATTR(kern, cfg.dynamicSmemBytes, variant, 8);
   C3D_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   C3D_LAUNCH_CHECK();
   return C3D_OK;
@@ -217,9 +262,7 @@ static int fused_launch(const fused::Args& a, int kind, cudaStream_t st) {
 
 // CTA-pair forward: per-image weight images, then one persistent launch of 2-CTA clusters (one CTA per SM).
 static int forward_pair(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st) {
-  int dev = 0, nsm = 0;
-  C3D_CUDA(cudaGetDevice(&dev));
-  C3D_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  const int nsm = device_sms();
   uint8_t* ws = reinterpret_cast<uint8_t*>(p->workspace);
   fused::Args a;
   fused_fill_args(a, p, reinterpret_cast<const float2*>(ws + w.film), reinterpret_cast<const float4*>(ws + w.first),
@@ -233,16 +276,14 @@ static int forward_pair(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
   a.unit_rays = ur;
   a.units_per_img = (p->n_rays + 2 * ur - 1) / (2 * ur);
   a.wimg = ws + w.wimg; a.kimg = ws + w.kimg;
-  static const bool split = env_int("C3D_PAIR_SPLIT", 0) != 0;   // half-split layer jobs (N = 128 MMAs): see fused_pair_sm100.cuh
-  film_weights_kernel<<<dim3(8, p->D, p->batch), 256, 0, st>>>(a.blob, a.L, a.film, ws + w.wimg, split ? 1 : 0);
+  film_weights_kernel<<<dim3(8, p->D, p->batch), 256, 0, st>>>(a.blob, a.L, a.film, ws + w.wimg);
   C3D_LAUNCH_CHECK();
-  film_k16_kernel<<<dim3(p->D + 1, p->batch), 256, 0, st>>>(a.blob, a.L, a.film, ws + w.kimg, split ? 1 : 0);
+  film_k16_kernel<<<dim3(p->D + 1, p->batch), 256, 0, st>>>(a.blob, a.L, a.film, ws + w.kimg);
   C3D_LAUNCH_CHECK();
   const long long total_pu = (long long)p->batch * a.units_per_img;
   int grid = nsm & ~1;
   if ((long long)grid > ((total_pu + 1) & ~1ll)) grid = (int)((total_pu + 1) & ~1ll);
-  const char* genv = getenv("C3D_GRID");
-  if (genv && atoi(genv) > 0) grid = (atoi(genv) + 1) & ~1;
+  if (options().grid > 0) grid = (options().grid + 1) & ~1;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(pairk::NTHREADS); cfg.dynamicSmemBytes = pairk::SMEM_BYTES; cfg.stream = st;
@@ -250,8 +291,8 @@ static int forward_pair(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  void (*kern)(const fused::Args) = split ? pairk::fused_forward_pair_kernel<true> : pairk::fused_forward_pair_kernel<false>;
-  C3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pairk::SMEM_BYTES));
+  void (*kern)(const fused::Args) = pairk::fused_forward_pair_kernel;
+  C3D_SMEM_ATTR(kern, pairk::SMEM_BYTES, 0, 1);
   C3D_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   C3D_LAUNCH_CHECK();
   return C3D_OK;
@@ -272,7 +313,7 @@ static int forward_fp32(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
   uint8_t* ws = reinterpret_cast<uint8_t*>(p->workspace);
   uint8_t* ck = ws + w.chunk;
   const size_t P = (size_t)p->n_rays * p->n_samples, R = (size_t)p->n_rays;
-  C3D_CUDA(cudaFuncSetAttribute(mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F32_SMEM));
+  C3D_SMEM_ATTR(mlp_fp32_kernel, F32_SMEM, 0, 1);
   for (int i0 = 0; i0 < p->batch; i0 += w.chunk_imgs) {
     const int ni = (p->batch - i0 < w.chunk_imgs) ? p->batch - i0 : w.chunk_imgs;
     const float *pts, *rays_d, *viewdirs, *z_vals;
@@ -328,6 +369,13 @@ using namespace c3d;
 extern "C" {
 
 int c3d_abi_version(void) { return C3D_ABI_VERSION; }
+
+int c3d_set_option(const char* key, const char* value) {
+  Options o = options();
+  if (parse_option(o, key, value) != 0) return fail(C3D_ERR_ARG, "c3d_set_option: unknown option or value %s=%s", key ? key : "(null)", value ? value : "(null)");
+  options() = o;
+  return C3D_OK;
+}
 const char* c3d_last_error(void) { return g_err; }
 int c3d_last_launch_count(void) { return g_launches; }
 
@@ -444,8 +492,7 @@ int c3d_sample_pdf(const c3d_resample_params* p, c3d_stream_t stream) {
   // lanes = rays when 128 (or 64) rays' working sets fit shared memory twice per SM, else lanes = samples
   // (C3D_RESAMPLE=warp|lane forces one of them for A/B runs)
   {
-    const char* e = getenv("C3D_RESAMPLE");
-    const bool force_warp = e && strcmp(e, "warp") == 0;
+    const bool force_warp = options().resample == 1;
     for (int tpb = 128; tpb >= 64 && !force_warp; tpb >>= 1) {
       const resample::LaneLayout LL = resample::make_lane_layout(q.n_samples, q.n_importance, q.pts_merged != nullptr, tpb);
       const size_t smem = (size_t)LL.total * sizeof(float);
@@ -454,31 +501,27 @@ int c3d_sample_pdf(const c3d_resample_params* p, c3d_stream_t stream) {
       C3D_CHECK_ARG(blocks < (1ll << 31), "too many rays");
       cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
       if (tpb == 128) {
-        C3D_CUDA(cudaFuncSetAttribute(resample::sample_pdf_lane_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        C3D_SMEM_ATTR(resample::sample_pdf_lane_kernel<128>, smem, 0, 1);
         resample::sample_pdf_lane_kernel<128><<<(unsigned)blocks, 128, smem, st>>>(q, LL);
       } else {
-        C3D_CUDA(cudaFuncSetAttribute(resample::sample_pdf_lane_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        C3D_SMEM_ATTR(resample::sample_pdf_lane_kernel<64>, smem, 0, 1);
         resample::sample_pdf_lane_kernel<64><<<(unsigned)blocks, 64, smem, st>>>(q, LL);
       }
       C3D_LAUNCH_CHECK();
       return C3D_OK;
     }
-    C3D_CHECK_ARG(!(e && strcmp(e, "lane") == 0), "C3D_RESAMPLE=lane: the working set does not fit shared memory");
+    C3D_CHECK_ARG(options().resample != 2, "resample=lane: the working set does not fit shared memory");
   }
-  static int rb_env = -1;
-  if (rb_env < 0) { const char* e = getenv("C3D_RESAMPLE_RB"); rb_env = e ? atoi(e) : 0; }
-  C3D_CHECK_ARG(rb_env % 4 == 0, "C3D_RESAMPLE_RB must be a multiple of 4");
+  const int rb_env = options().resample_rb;
   const resample::Layout L = resample::make_layout(q.n_samples, q.n_importance, q.u != nullptr, q.rays_o != nullptr,
                                                    q.rays_d != nullptr, q.z_fine != nullptr, q.z_merged != nullptr,
                                                    q.pts_merged != nullptr, rb_env);
   const size_t smem = (size_t)L.total * sizeof(float);
   C3D_CHECK_ARG(smem <= 200 * 1024, "resampling chunk does not fit shared memory (%zu bytes)", smem);
-  C3D_CUDA(cudaFuncSetAttribute(resample::sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  C3D_SMEM_ATTR(resample::sample_pdf_kernel, smem, 0, 1);
   const long long n_chunks = (q.n_rays + L.RB - 1) / L.RB;
   C3D_CHECK_ARG(n_chunks < (1ll << 31), "too many rays");
-  int dev = 0, sms = 148;
-  C3D_CUDA(cudaGetDevice(&dev));
-  C3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int sms = device_sms();
   const int per_sm = smem <= 110 * 1024 ? 2 : 1;
   const unsigned grid = (unsigned)(n_chunks < (long long)sms * per_sm ? n_chunks : (long long)sms * per_sm);
   resample::sample_pdf_kernel<<<grid, resample::THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(q, L, (int)n_chunks);
@@ -616,8 +659,7 @@ static BwdWs bwd_ws(const c3d_bwd_params* bp) {
 // bf16 mode differentiates through the tensor-core kernels (forward with save + fused backward); fp32 mode and
 // n_samples < 8 use the FP32-pipe kernels.  C3D_BWD=simt forces the latter (A/B runs).
 static bool bwd_uses_tensor_path(const c3d_bwd_params* bp) {
-  const char* e = getenv("C3D_BWD");
-  if (e && strcmp(e, "simt") == 0) return false;
+  if (options().bwd_simt) return false;
   if (bp->g_params) return false;                    // parameter gradients come from the FP32-pipe kernels
   return bp->fwd.mode == C3D_MODE_BF16 && bp->fwd.n_samples >= fused::MIN_SAMPLES;
 }
@@ -739,9 +781,9 @@ static int backward_simt(const c3d_bwd_params* bp, cudaStream_t st) {
                          reinterpret_cast<float*>(ws + w.first), reinterpret_cast<float*>(view), st);
   if (rc != C3D_OK) return rc;
   C3D_CUDA(cudaMemsetAsync(g_film, 0, (size_t)p->batch * (D + 1) * W * sizeof(float2), st));
-  C3D_CUDA(cudaFuncSetAttribute(mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F32_SMEM));
-  C3D_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
-  C3D_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
+  C3D_SMEM_ATTR(mlp_fp32_kernel, F32_SMEM, 0, 1);
+  C3D_SMEM_ATTR(mlp_bwd_kernel<false>, BWD_SMEM, 0, 1);
+  C3D_SMEM_ATTR(mlp_bwd_kernel<true>, BWD_SMEM, 0, 1);
   const c3d_param_grads* pg = bp->g_params;
   if (pg) {                                          // everything below accumulates with atomics
     for (int l = 0; l < D; ++l) C3D_CUDA(cudaMemsetAsync(pg->pts_weight[l], 0, sizeof(float) * W * (l == 0 ? 3 : W), st));
@@ -1091,9 +1133,9 @@ int c3d_eikonal_backward(const c3d_bwd_params* bp, const float* g_eik, c3d_strea
     C3D_CUDA(cudaMemsetAsync(pg->sigma_bias, 0, sizeof(float), st));
     C3D_CUDA(cudaMemsetAsync(pg->sigmoid_beta, 0, sizeof(float), st));
   }
-  C3D_CUDA(cudaFuncSetAttribute(mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F32_SMEM));
-  C3D_CUDA(cudaFuncSetAttribute(eik_tangent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EIKT_SMEM));
-  C3D_CUDA(cudaFuncSetAttribute(eik_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EIKB_SMEM));
+  C3D_SMEM_ATTR(mlp_fp32_kernel, F32_SMEM, 0, 1);
+  C3D_SMEM_ATTR(eik_tangent_kernel, EIKT_SMEM, 0, 1);
+  C3D_SMEM_ATTR(eik_bwd_kernel, EIKB_SMEM, 0, 1);
   for (int i0 = 0; i0 < p->batch; i0 += w.chunk_imgs) {
     const int ni = (p->batch - i0 < w.chunk_imgs) ? p->batch - i0 : w.chunk_imgs;
     const float* pts = p->pts + (size_t)i0 * P * 3;

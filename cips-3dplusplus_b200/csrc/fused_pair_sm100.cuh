@@ -2,36 +2,39 @@
 //
 // Reference semantics: exp/cips3d/volume_renderer.py:133-160,192-283, exp/cips3d/nerf_utils.py:17-218,230-338.
 //
-// Structure (profiles/r02_fused.md has the measurements behind each choice)
+// Structure (profiles/r02_fused.md and profiles/r02_micro.md have the measurements behind each choice)
 //   * FiLM is folded into the GEMM.  film_weights_kernel (kernels_aux.cuh) writes, per image, bf16(gamma_c * W_l[c][k]) in
 //     the stage layout plus a K = 16 side image holding the shift (gamma b + beta, hi/lo split, multiplied by two "ones"
 //     slots of the point tile), the layer-0 weights and the view-direction columns.  The accumulator is the SIREN argument
 //     itself, so the epilogue is sin -> bf16 -> store with no per-channel constants.
 //   * Orientation D[point][channel] = H * W'^T: TMEM lanes are points.  A thread owns one point of its tile in every
 //     stage (geometry, layer epilogues, sdf / transmittance, rgb) and writes its own rows of the K-major activation tile.
-//   * Two CTAs of a cluster form a pair and issue tcgen05.mma.cta_group::2 (M = 256 points = 128 per CTA): every CTA
-//     stages only its half of the weight rows and never exchanges activations, so a 64 KB ring holds a WHOLE layer.
-//     Both slots of a pair run the same layer back to back from the same ring stages (slot 1 trails slot 0 by one job),
-//     which streams every layer once per two tiles and leaves the refill a full job of slack.
-//   * The per-SM bound of this kernel is the SFU, not the tensor pipe: a 128-point tile-layer needs 2048 tensor cycles
-//     and 32768 MUFU.SIN = 2076 SFU cycles (sm_probe M1), and 9 sine layers face 8 K = 256 layers at D = 8.  The job
-//     structure therefore exists to keep the epilogue warps fed: a K = 256 layer is issued as two channel halves
-//     (N = 128 each, accumulator columns 0..127 / 128..255 of the slot); half 0 is committed on its own, so its sines
-//     run under half 1's MMAs.  The activation tile is updated in place: half 0's outputs overwrite K-chunks 0, 1, which
-//     half 1's MMAs still read -- half 1 consumes those chunks first and a third commit (act_free) releases them.
+//   * Two CTAs of a cluster form a pair and issue tcgen05.mma.cta_group::2 (M = 256 points = 128 per CTA, N = 256): every
+//     CTA stages only its 128 weight rows and never exchanges activations.  Per 128 points and layer an SM then moves
+//     224 KB through shared memory (the single-CTA kernel: 448 KB -- 3500 cycles at 128 B/clk against 2048 tensor cycles,
+//     which is what bounds it), and a 64 KB ring holds a WHOLE layer, so slot 1 re-reads the stages slot 0 consumed: one
+//     stream of the layer per two tiles, the refill has a full job of slack.
+//   * Per SM a 128-point tile-layer costs 2048 tensor cycles and 32768 MUFU.SIN = 2080 SFU cycles (sm_probe M1): both
+//     pipes are needed all the time; with two accumulator slots (all 512 TMEM columns) the dependency chain
+//     MMA -> sines -> MMA of a slot leaves each of them about half busy.  Two variants that shorten the chain were built
+//     and measured slower (profiles/r02_fused.md): N = 128 half-layer jobs (the activation tile is then read twice: shared
+//     memory binds) and a mid-epilogue hand-off with an event-driven issuer (mbarrier polling latency).
+//   * The sdf head runs on the FP32 pipe inside the last hidden layer's epilogue (fp32 sines, 128 FFMA per thread), and
+//     density -> alpha -> transmittance run under the view layer's MMAs: no separate job on the chain.
 //
-// Roles per CTA (640 threads): warp 0 weight producer (bulk copies of its halves), warp 1 MMA issuer (leader CTA) or
-// barrier relay (peer CTA: forwards "my stage landed" to the leader), warp 2 TMEM allocator, warps 4-11 / 12-19 epilogue
-// group of slot 0 / 1 (8 warps: two per sub-partition, what the SFU needs to stay saturated while one waits on TMEM).
-// Barriers the leader waits on (full, kfull, a_ready) collect arrivals from both CTAs; barriers signalled by
-// tcgen05.commit (empty, kempty, acc_full, act_free) are multicast to both.
+// Roles per CTA (640 threads): warp 0 weight producer (bulk copies of its halves), warp 1 MMA issuer (leader CTA; the
+// whole warp runs the control flow, one elected lane executes the tcgen05 instructions so every operand stays in uniform
+// registers -- with the loop inside `if (elect_one())` ptxas wrapped each UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY
+// waterfall) or barrier relay (peer CTA: forwards "my stage landed" to the leader), warp 2 TMEM allocator, warps 4-11 /
+// 12-19 epilogue group of slot 0 / 1 (8 warps: two per sub-partition, what the SFU needs to stay saturated).  Barriers the
+// leader waits on (full, kfull, a_ready) collect arrivals from both CTAs; barriers signalled by tcgen05.commit (empty,
+// kempty, acc_full) are multicast to both.
 //
-// Per pair-tile (128 points per CTA) the issuer runs D+3 jobs:
-//   job 0       layer 0    : per half a K = 16 product of the point tile (hi, mid, hi, lo per coordinate, ones) with the K16 image
-//   job 1..D-1  hidden l   : per half K16 product (shift) + 16 x (256x128x16), A = activation tile, B = weight ring
-//   job D       sdf head   : 16 x (256x16x16), B = heads16 (8 rows per CTA)
-//   job D+1     view layer : per half K16 product (view direction, shift) + 16 x (256x128x16)
-//   job D+2     post       : compositing MMAs (A = feat^T as MN-major view, B = Wgt; N = 32, each CTA reads its own 16
+// Per pair-tile (128 points per CTA) the issuer runs D+2 jobs:
+//   job 0       layer 0    : K = 16 product of the point tile (hi, mid, hi, lo per coordinate, ones) with the K16 image
+//   job 1..D-1  hidden l   : K16 product (shift) + 16 x (256x256x16), A = activation tile, B = weight ring
+//   job D       view layer : K16 product (view direction, shift) + 16 x (256x256x16)
+//   job D+1     post       : compositing MMAs (A = feat^T as MN-major view, B = Wgt; N = 32, each CTA reads its own 16
 //                            columns) + rgb head
 #pragma once
 #include "c3d_common.cuh"
@@ -49,11 +52,8 @@ using fused::ACT_CHUNK;
 constexpr int EGW = 8;                         // epilogue warps per slot: warp (quad, grp) owns lanes 32 quad.. and columns 64 grp..
                                                // of each accumulator half; grp 0 threads also run the per-point stages
 constexpr int NTHREADS = 128 + 2 * EGW * 32;   // 640
-// kSplit = true : a K = 256 layer is issued as two channel halves (N = 128 MMAs), stage = this CTA's [2 K-chunks][64 rows][64 k]
-//                  of (half, K-chunk pair)
-// kSplit = false: one N = 256 MMA per K-step, stage = this CTA's [128 rows][64 k] of a K-chunk
-// Either way 4 stages of 16 KB = 64 KB = one layer of this CTA's weight rows (the producer and the relay pay ~200 cycles per
-// stage, so 8 KB stages starved the issuer).
+// 4 stages of 16 KB ([128 rows][64 k] of a K-chunk) = 64 KB = one layer of this CTA's weight rows (the producer and the relay pay
+// ~200 cycles per stage: 8 KB stages starved the issuer).
 constexpr int RING_BYTES = 65536;
 constexpr int STAGE_BYTES = 16384;
 constexpr int NSTAGE = 4;
@@ -79,8 +79,7 @@ constexpr int SMEM_BYTES = SM_TOTAL + 1024;
 
 struct Misc {
   uint64_t full[NSTAGE], empty[NSTAGE], kfull[2], kempty[2], a_ready[2];
-  uint64_t acc_full[2][2];   // [slot][half]; the narrow jobs (sdf head, post) signal half 0 only
-  uint64_t act_free[2];      // [slot]: the job's MMAs no longer read K-chunks 0, 1 of the activation tile (nor the aux tile)
+  uint64_t acc_full[2];      // [slot]: the job's MMAs are complete
   uint32_t tmem_base;
   float carry[2];
 };
@@ -174,9 +173,7 @@ __device__ __forceinline__ void epilogue16_sdf(const uint32_t (&v)[16], uint32_t
   }
 }
 
-template <bool kSplit>
 __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const Args a) {
-  constexpr int NH = kSplit ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   Misc* misc = reinterpret_cast<Misc*>(smem + SM_MISC);
@@ -195,9 +192,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
       mbar_init(&misc->kfull[i], leader ? 2 : 1);
       mbar_init(&misc->kempty[i], 1);
       mbar_init(&misc->a_ready[i], 2 * EGW);       // one arrival per epilogue warp of both CTAs (leader's copy is used)
-      mbar_init(&misc->acc_full[i][0], 1);
-      mbar_init(&misc->acc_full[i][1], 1);
-      mbar_init(&misc->act_free[i], 1);
+      mbar_init(&misc->acc_full[i], 1);
     }
     misc->carry[0] = misc->carry[1] = 1.0f;
     fence_mbar_init();
@@ -294,7 +289,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
     // operand is then uniform by data flow and lives in uniform registers.  (With the loop inside `if (elect_one())`
     // ptxas wrapped each UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall -- ~170 cycles per MMA.)
     const bool issue = elect_one();
-    const uint32_t idesc_l = umma_idesc_bf16(256, kSplit ? 128 : 256, 0, 0);   // (one channel half of) a layer / K16 side product: both K-major
+    const uint32_t idesc_l = umma_idesc_bf16(256, 256, 0, 0);      // layers and K16 side products: both K-major
     const uint32_t idesc_h = umma_idesc_bf16(256, 16, 0, 0);       // heads: B = 8 rows of heads16 per CTA
     const uint32_t idesc_c = umma_idesc_bf16(256, 32, 1, 0);       // compositing: A = feat^T (MN-major view), B = Wgt
     const uint32_t act_base = smem_u32(smem + SM_ACT);
@@ -331,40 +326,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
           if (kind == 1 && s == 0) n_shared = n;
           const uint32_t n0 = reuse ? n_shared : n;
           const uint64_t auxd = umma_desc_kmajor_k16(aux_addr);
-#pragma unroll
-          for (int h = 0; h < NH; ++h) {
-            const uint32_t th = tacc + (uint32_t)h * 128u;
-            if (issue) {
-              umma_bf16_ss_pair(th, auxd, umma_desc_kmajor_k16(k16_addr + (uint32_t)h * 2048u), idesc_l, 0u);
-              if (h == NH - 1) umma_commit_pair(&misc->kempty[s], (uint16_t)0x3);
-            }
-            if (kind == 1) {
-#pragma unroll
-              for (int kc = 0; kc < NCHUNK; ++kc) {
-                const uint32_t m = n0 + (uint32_t)(kSplit ? h * 2 + (kc >> 1) : kc);
-                const uint32_t st = m % NSTAGE, ph = (m / NSTAGE) & 1u;
-                const bool first = !kSplit || (kc & 1) == 0, last = !kSplit || (kc & 1) == 1;   // K-chunks of the stage
-                if (!reuse && first) {
-                  C3D_PROF(0);
-                  mbar_wait_cluster(&misc->full[st], ph);
-                  C3D_PROF(4);
-                  tc_fence_after();
-                }
-                if (issue) {
-                  const uint64_t ad = umma_desc_kmajor_sw128(act_addr + kc * ACT_CHUNK);
-                  const uint64_t bd = umma_desc_kmajor_sw128(stage_base + st * STAGE_BYTES + (kSplit ? (kc & 1) * 8192 : 0));
-#pragma unroll
-                  for (int kk = 0; kk < 4; ++kk) umma_bf16_ss_pair(th, ad + 2 * kk, bd + 2 * kk, idesc_l, 1u);
-                  if (last && !(shared && s == 0)) umma_commit_pair(&misc->empty[st], (uint16_t)0x3);
-                  // half 1 has consumed K-chunks 0, 1: half 0's outputs may overwrite them
-                  if (kSplit && h == 1 && kc == 1) umma_commit_pair(&misc->act_free[s], (uint16_t)0x3);
-                }
-              }
-            } else if (kSplit && h == 1) {
-              if (issue) umma_commit_pair(&misc->act_free[s], (uint16_t)0x3);
-            }
-            if (issue) umma_commit_pair(&misc->acc_full[s][h], (uint16_t)0x3);
+          if (issue) {
+            umma_bf16_ss_pair(tacc, auxd, umma_desc_kmajor_k16(k16_addr), idesc_l, 0u);
+            umma_commit_pair(&misc->kempty[s], (uint16_t)0x3);
           }
+          if (kind == 1) {
+#pragma unroll
+            for (int kc = 0; kc < NCHUNK; ++kc) {
+              const uint32_t m = n0 + (uint32_t)kc;
+              const uint32_t st = m % NSTAGE, ph = (m / NSTAGE) & 1u;
+              if (!reuse) {
+                C3D_PROF(0);
+                mbar_wait_cluster(&misc->full[st], ph);
+                C3D_PROF(4);
+                tc_fence_after();
+              }
+              if (issue) {
+                const uint64_t ad = umma_desc_kmajor_sw128(act_addr + kc * ACT_CHUNK);
+                const uint64_t bd = umma_desc_kmajor_sw128(stage_base + st * STAGE_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) umma_bf16_ss_pair(tacc, ad + 2 * kk, bd + 2 * kk, idesc_l, 1u);
+                if (!(shared && s == 0)) umma_commit_pair(&misc->empty[st], (uint16_t)0x3);
+              }
+            }
+          }
+          if (issue) umma_commit_pair(&misc->acc_full[s], (uint16_t)0x3);
           if (kind == 1 && !reuse) n += NSTAGE;
         } else if (issue) {
           // These narrow MMAs are latency-bound when chained on one accumulator, so consecutive K-steps go to different
@@ -384,7 +370,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
           for (int ks = 0; ks < 16; ++ks)
             umma_bf16_ss_pair(tacc + dcol + (uint32_t)(ks & 3) * 16u, desc_at(ha, (ks >> 2) * ACT_CHUNK + (ks & 3) * 32),
                               desc_at(hb, (ks >> 2) * 1024 + (ks & 3) * 32), idesc_h, ks >= 4);
-          umma_commit_pair(&misc->acc_full[s][0], (uint16_t)0x3);
+          umma_commit_pair(&misc->acc_full[s], (uint16_t)0x3);
         }
         __syncwarp();
         if (++jb[s] == JOBS) { jb[s] = 0; c[s].next_tile(a); }
@@ -427,10 +413,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
       if (lane == 0) { if (leader) mbar_arrive(&misc->a_ready[s]); else mbar_arrive_remote(ready_remote); }
     };
     float carry_f[2] = {0.f, 0.f};                       // partial feature sums of a ray continuing into the next tile
-    uint32_t cnt[2] = {0u, 0u}, cntf = 0;                // completed phases of acc_full[s][0 / 1], act_free[s]
+    uint32_t cnt = 0;                                    // completed phases of acc_full[s]
     Cursor cur;
     cur.init(a, ps0 + s, n_pairslots);
-    C3D_PROF_DECL(8);   // 0 other (geometry, point stages, post), 1 wait acc h0, 2 wait act_free, 3 wait acc h1, 4 sines + stores h0, 5 h1, 6 arrive
+    C3D_PROF_DECL(8);   // 0 other (geometry, point stages, post), 1 wait acc, 4 sines + stores first K-chunk, 5 second, 6 arrive
 
     for (; cur.valid(); ) {
       const int u = cur.pu;
@@ -494,42 +480,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
         float sdfa[4] = {0.f, 0.f, 0.f, 0.f};                // partial sums of the sdf head over my channels
         // ------------------------------------------------ layers 0..D (D = view layer)
         for (int l = 0; l <= D; ++l) {
-          // my point: kSplit: 64 channels of each accumulator half (K-chunk 2 h + grp); else channels 128 grp .. + 127
-          // (K-chunks 2 grp, 2 grp + 1); TMEM loads double-buffered
+          // my point: channels 128 grp .. + 127 (K-chunks 2 grp, 2 grp + 1 of the next layer's input); TMEM loads double-buffered
 #pragma unroll 1
           for (int h = 0; h < 2; ++h) {
             C3D_PROF(h == 0 ? 0 : 4);
-            if (kSplit || h == 0) {
-              mbar_wait(&misc->acc_full[s][h], cnt[h] & 1u);
-              cnt[h]++;
+            if (h == 0) {
+              mbar_wait(&misc->acc_full[s], cnt & 1u);
+              cnt++;
               tc_fence_after();
-            }
-            C3D_PROF(h == 0 ? 1 : 3);
-            const int chunk = kSplit ? 2 * h + grp : 2 * grp + h;
-            const uint32_t tcol = tacc + (uint32_t)chunk * 64u;
-            const uint32_t row = row_u32 + (uint32_t)chunk * ACT_CHUNK;
-            uint32_t v0[16], v1[16];
-            tmem_ld_32x16(tcol, v0);
-            if (kSplit && h == 0) {
-              // K-chunks 0, 1 (and the aux tile) are still read by the job's half-1 MMAs until act_free
-              C3D_PROF(4);
-              mbar_wait(&misc->act_free[s], cntf & 1u);
-              C3D_PROF(2);
-              cntf++;
               if (l == D && ptg) {
-                // the view tile has been consumed: build Wgt[ray slot][point] (bf16, K-major SW128) in its place
+                // all MMAs of the view layer are complete: the view tile has been consumed, build Wgt[ray slot][point]
+                // (bf16, K-major SW128) in its place
                 const int myslot = rl - rl0;
 #pragma unroll
                 for (int jx = 0; jx < RAYS; ++jx)
                   st_bf16(aux_u32 + (uint32_t)((t >> 6) * 2048) + sw128_offset(jx, t & 63), jx == myslot ? wgt : 0.f);
               }
             }
-            if (!kSplit && h == 0 && l == D && ptg) {
-              const int myslot = rl - rl0;                 // all MMAs of the view layer are complete: aux is free
-#pragma unroll
-              for (int jx = 0; jx < RAYS; ++jx)
-                st_bf16(aux_u32 + (uint32_t)((t >> 6) * 2048) + sw128_offset(jx, t & 63), jx == myslot ? wgt : 0.f);
-            }
+            C3D_PROF(h == 0 ? 1 : 3);
+            const int chunk = 2 * grp + h;
+            const uint32_t tcol = tacc + (uint32_t)chunk * 64u;
+            const uint32_t row = row_u32 + (uint32_t)chunk * ACT_CHUNK;
+            uint32_t v0[16], v1[16];
+            tmem_ld_32x16(tcol, v0);
             const float4* wsg = reinterpret_cast<const float4*>(smem + SM_WSIG) + chunk * 16;   // 64 weights of this K-chunk
             if (l == D - 1) {
 #pragma unroll
@@ -594,8 +567,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
 
         // ------------------------------------------------ post job: composited features (thread = channel) + rgb (thread = point)
         {
-          mbar_wait(&misc->acc_full[s][0], cnt[0] & 1u);
-          cnt[0]++;
+          mbar_wait(&misc->acc_full[s], cnt & 1u);
+          cnt++;
           tc_fence_after();
           float rgbv[3] = {brgb0, brgb1, brgb2};         // raw rgb of my point: 4 partial sums
           if (ptg) {
@@ -673,7 +646,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
 #ifdef C3D_KERNEL_PROF
     C3D_PROF(0);
     if (blockIdx.x < 2 && t == 0)
-      printf("c3d prof pair eg[blk %d slot %d grp %d]: total %lld  other %lld  wait acc_h0 %lld act_free %lld acc_h1 %lld  sines h0 %lld h1 %lld  arrive %lld\n",
+      printf("c3d prof pair eg[blk %d slot %d grp %d]: total %lld  other %lld  wait acc %lld (%lld %lld)  sines chunk 0 %lld chunk 1 %lld  arrive %lld\n",
              (int)blockIdx.x, s, grp, clock64() - prof_begin, prof_t[0], prof_t[1], prof_t[2], prof_t[3], prof_t[4], prof_t[5], prof_t[6]);
 #endif
   }

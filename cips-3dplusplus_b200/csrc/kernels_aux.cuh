@@ -191,26 +191,22 @@ __global__ void __launch_bounds__(SP_THREADS) style_prep_kernel(const uint8_t* _
 
 // ------------------------------------------------------------------------------------------
 // Per-image weight images of the CTA-pair forward kernel (fused_pair_sm100.cuh): FiLM folded into the GEMM operands.
-//   wimg[b][idx 0..D-1][half 0..1][kc 0..3][rank 0..1] : 8 KB stage images [64 rows n][64 k] bf16, K-major SWIZZLE_128B,
-//                                             value bf16(gamma_{b,idx+1}[n] * W_{idx+1}[n][k]),  n = 128 half + 64 rank + row
-//   kimg[b][L 0..D][rank 0..1][half 0..1]   : 2 KB K16 images [64 rows n][16 slots], UMMA K-major no-swizzle:
+//   wimg[b][idx 0..D-1][kc 0..3][half 0..1] : 16 KB stage images [128 rows n][64 k] bf16, K-major SWIZZLE_128B,
+//                                             value bf16(gamma_{b,idx+1}[n] * W_{idx+1}[n][k]),  n = 128 half + row
+//   kimg[b][L 0..D][half 0..1]              : 4 KB K16 images [128 rows n][16 slots], UMMA K-major no-swizzle:
 //        L = 0     slots 4j..4j+3 = (hi, hi, lo, hi) of gamma W0[n][j]   (x point tile (hi, mid, hi, lo))
 //        L = D     slots j and 3+j = bf16(gamma Wview[n][256+j])         (x view tile (hi x3, lo x3))
 //        all L     slots 12, 13 = hi / lo of the shift gamma b + beta    (x the two "ones" slots of either tile)
 // ------------------------------------------------------------------------------------------
 // grid (8 = kc*2 + half, D, batch), block 256: thread = (row, 32-element half of the 64-wide K-chunk)
 __global__ void __launch_bounds__(256) film_weights_kernel(const uint8_t* __restrict__ blob, PackedLayout L,
-                                                            const float2* __restrict__ film, uint8_t* __restrict__ wimg, int split) {
+                                                            const float2* __restrict__ film, uint8_t* __restrict__ wimg) {
   const int D = L.D, idx = blockIdx.y, b = blockIdx.z, kc = blockIdx.x >> 1, half = blockIdx.x & 1;
   const int i = threadIdx.x >> 1, q = threadIdx.x & 1, n = half * 128 + i;
   const float gamma = film[((size_t)b * (D + 1) + idx + 1) * W + n].x;
   const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(blob + L.w32) + (size_t)idx * W * W +
                                                       (size_t)n * W + kc * 64 + q * 32);
-  // split : stage (half, kc >> 1, rank = i >> 6) = [kc & 1][64 rows][64 k], 16 KB; stages ordered [half][kc pair][rank]
-  // whole : stage (kc, rank = half) = [128 rows][64 k], 16 KB; stages ordered [kc][rank]              (fused_pair_sm100.cuh)
-  uint8_t* dst = wimg + ((size_t)b * D + idx) * 131072 +
-                 (split ? (size_t)((half * 2 + (kc >> 1)) * 2 + (i >> 6)) * 16384 + (size_t)(kc & 1) * 8192 + (size_t)(i & 63) * 128
-                        : (size_t)(kc * 2 + half) * 16384 + (size_t)i * 128);
+  uint8_t* dst = wimg + (((size_t)b * D + idx) * 8 + blockIdx.x) * 16384 + (size_t)i * 128;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const float4 x = src[2 * u], y = src[2 * u + 1];
@@ -223,7 +219,7 @@ __global__ void __launch_bounds__(256) film_weights_kernel(const uint8_t* __rest
 
 // grid (D+1, batch), block 256 (thread = output channel n)
 __global__ void __launch_bounds__(256) film_k16_kernel(const uint8_t* __restrict__ blob, PackedLayout L,
-                                                        const float2* __restrict__ film, uint8_t* __restrict__ kimg, int split) {
+                                                        const float2* __restrict__ film, uint8_t* __restrict__ kimg) {
   const int D = L.D, l = blockIdx.x, b = blockIdx.y, n = threadIdx.x, half = n >> 7, i = n & 127;
   const float2 f = film[((size_t)b * (D + 1) + l) * W + n];
   float s[16];
@@ -245,9 +241,7 @@ __global__ void __launch_bounds__(256) film_k16_kernel(const uint8_t* __restrict
   }
   const float sh = bf(f.y);
   s[12] = sh; s[13] = f.y - sh;
-  // split: [rank = i >> 6][half][64 rows][16]; whole: [rank = half][128 rows][16] -- a CTA of the pair copies its 4 KB with one bulk copy
-  uint8_t* dst = kimg + ((size_t)b * (D + 1) + l) * 8192 +
-                 (split ? (size_t)((i >> 6) * 2 + half) * 2048 + k16_offset(i & 63, 0) : (size_t)half * 4096 + k16_offset(i, 0));
+  uint8_t* dst = kimg + (((size_t)b * (D + 1) + l) * 2 + half) * 4096 + k16_offset(i, 0);
   *reinterpret_cast<uint4*>(dst) = make_uint4(ptx::pack_bf16x2(s[0], s[1]), ptx::pack_bf16x2(s[2], s[3]),
                                               ptx::pack_bf16x2(s[4], s[5]), ptx::pack_bf16x2(s[6], s[7]));
   *reinterpret_cast<uint4*>(dst + 128) = make_uint4(ptx::pack_bf16x2(s[8], s[9]), ptx::pack_bf16x2(s[10], s[11]),

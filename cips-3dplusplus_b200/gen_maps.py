@@ -108,6 +108,7 @@ def main():
     m = NerfBranch(a.layers)
     m.load_state_dict(torch.load(a.weights, map_location="cpu"), strict=True)
     m = m.cuda().eval().requires_grad_(False)
+    m.cache_packed = True                            # frozen checkpoint: pack the weights once
     cam = dict(fov_ang=a.fov, dist_radius=a.dist_radius, azim_range=a.azim_range, elev_range=a.elev_range, uniform=a.uniform)
     out = gen_maps(m, gaussian_styles(a.layers), cam, a.num_imgs, a.batch_gpu, out_dir=a.out, rank=rank, world_size=world,
                    N_samples=a.n_samples, seed=a.seed, N_importance=a.n_importance)

@@ -84,6 +84,9 @@ class FlipInversion:
         self.loss_fn, self.clip, self.shared_latent, self.static_viewdirs = loss_fn, clip, shared_latent, static_viewdirs
         # clipping + both Adam updates as one kernel (CUDA tensors); False (or C3D_INV_FUSED=0, for A/B runs): torch.optim
         self.fused_update = fused_update and os.environ.get("C3D_INV_FUSED", "1") != "0"
+        # stage 1 optimises latents and cameras only: with a frozen renderer the packed weights are built once
+        if hasattr(renderer, "cache_packed") and not any(p.requires_grad for p in renderer.parameters()):
+            renderer.cache_packed = True
 
     def render_thumbs(self, w, azim, elev):
         """w (n, D+1, 256); azim, elev (n, 2, 1) -> thumbs (n*2, 3, S, S), differentiable."""

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define C3D_ABI_VERSION 8
+#define C3D_ABI_VERSION 9
 #define C3D_MAX_LAYERS 16
 #define C3D_W 256
 
@@ -211,6 +211,14 @@ typedef struct c3d_resample_params {
 
 int c3d_abi_version(void);
 const char* c3d_last_error(void);
+
+/* Tuning options (kernel variants for A/B runs and tests; the defaults are what ships).  The library reads the matching
+ * C3D_* environment variables once, at first use; afterwards only this call changes an option -- nothing on the launch path
+ * touches the environment.  Keys / values: "fwd" = "pair" | "v3"; "cluster" = "1" | "2"; "grid" = CTAs (0: one per SM);
+ * "egw" = "4" | "8"; "bwd" = "tc" | "simt"; "resample" = "auto" | "warp" | "lane"; "resample_rb" = rays per block;
+ * "debug" = bit mask (development builds).  Process-wide, not thread-safe against concurrent launches.
+ * Replaces: nothing in the reference (its path is Python -> ATen). */
+int c3d_set_option(const char* key, const char* value);
 
 size_t c3d_packed_bytes(int32_t D);
 int c3d_pack_weights(const c3d_raw_params* raw, void* packed, size_t packed_bytes, c3d_stream_t stream);

@@ -44,3 +44,12 @@ def rel_l2(a, b):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _default_kernel_options():
+    """Kernel-variant options set by a test (c3d_set_option is process-wide) do not leak into the next one."""
+    yield
+    import cips3dpp_b200 as c3d
+    if c3d._abi._lib is not None:
+        c3d._abi.set_options(fwd="pair", cluster=2, grid=0, egw=4, bwd="tc", resample="auto", resample_rb=0, debug=0)
