@@ -223,6 +223,7 @@ static void fused_fill_args(fused::Args& a, const c3d_fwd_params* p, const float
   a.rgb_map = p->rgb_map; a.feature_map = p->feature_map; a.sdf = p->sdf; a.mask = p->mask; a.xyz = p->xyz;
   a.z_vals_out = p->z_vals_out;
   a.sdf_only = fwd_sdf_only(p) ? 1 : 0;
+  a.feat_nchw = p->feat_layout == C3D_FEAT_NCHW ? 1 : 0;
   a.debug = options().debug;
 }
 
@@ -407,7 +408,8 @@ int c3d_pack_weights(const c3d_raw_params* raw, void* packed, size_t packed_byte
 size_t c3d_workspace_bytes(const c3d_fwd_params* p) {
   if (!p || p->batch < 1 || p->n_rays < 1 || p->n_samples < 1 || p->D < 1) return 0;
   FwdWs w = fwd_ws(p);
-  size_t extra = (p->feat_layout == C3D_FEAT_NCHW) ? align_up((size_t)p->batch * p->n_rays * W * 4, 256) : 0;
+  // (b, 256, hw) features: the tensor-core kernels write them directly; only the fp32 parity path stages + transposes
+  size_t extra = (p->feat_layout == C3D_FEAT_NCHW && p->mode == C3D_MODE_FP32) ? align_up((size_t)p->batch * p->n_rays * W * 4, 256) : 0;
   return w.total + extra;
 }
 
@@ -429,7 +431,9 @@ int c3d_nerf_forward(const c3d_fwd_params* p, c3d_stream_t stream) {
                          reinterpret_cast<float*>(ws + w.first), reinterpret_cast<float*>(ws + w.view), st);
   if (rc != C3D_OK) return rc;
   float* feat_out = p->feature_map;
-  const bool nchw = p->feat_layout == C3D_FEAT_NCHW && !fwd_sdf_only(p);
+  // channel-major features come straight from the compositing epilogue of the tensor-core kernels (no extra launch, no
+  // extra bytes); the fp32 parity path composites one warp per ray and goes through a staging buffer + transposition
+  const bool nchw = p->feat_layout == C3D_FEAT_NCHW && !fwd_sdf_only(p) && p->mode == C3D_MODE_FP32;
   if (nchw) {
     C3D_CHECK_ARG(p->workspace_bytes >= c3d_workspace_bytes(p), "workspace too small for NCHW staging");
     feat_out = reinterpret_cast<float*>(ws + w.total);
@@ -963,10 +967,11 @@ static int backward_tc(const c3d_bwd_params* bp, cudaStream_t st, int phases) {
       q.pts = p->pts + (size_t)i0 * P * 3; q.rays_d = p->rays_d + (size_t)i0 * R * 3;
       q.viewdirs = p->viewdirs + (size_t)i0 * R * 3; q.z_vals = p->z_vals + (size_t)i0 * P;
     }
-    const bool nchw = p->feat_layout == C3D_FEAT_NCHW;
-    q.feat_layout = C3D_FEAT_NHWC;
+    // the caller's feature_map (either layout) is written by the save-mode forward itself; the recompute pass writes a
+    // scratch copy in (b, hw, 256)
+    if (!user_out) q.feat_layout = C3D_FEAT_NHWC;
     q.rgb_map = user_out ? p->rgb_map : reinterpret_cast<float*>(ck + w.c_orgb);
-    q.feature_map = (user_out && !nchw) ? p->feature_map : reinterpret_cast<float*>(ck + w.c_ofeat);
+    q.feature_map = user_out ? p->feature_map : reinterpret_cast<float*>(ck + w.c_ofeat);
     q.mask = user_out ? p->mask : reinterpret_cast<float*>(ck + w.c_omask);
     q.xyz = user_out ? p->xyz : reinterpret_cast<float*>(ck + w.c_oxyz);
     q.sdf = reinterpret_cast<float*>(ck + w.c_sdfpt); q.z_vals_out = nullptr;
@@ -987,11 +992,6 @@ static int backward_tc(const c3d_bwd_params* bp, cudaStream_t st, int phases) {
         C3D_CUDA(cudaMemcpyAsync(p->sdf, q.sdf, (size_t)ni * P * 4, cudaMemcpyDeviceToDevice, st));
         if (poses && p->z_vals_out)
           C3D_CUDA(cudaMemcpyAsync(p->z_vals_out, q.z_vals, (size_t)ni * P * 4, cudaMemcpyDeviceToDevice, st));
-        if (nchw) {
-          dim3 grid((unsigned)((p->n_rays + 31) / 32), W / 32, (unsigned)ni);
-          nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, st>>>(q.feature_map, p->feature_map, p->n_rays);
-          C3D_LAUNCH_CHECK();
-        }
       }
     }
     if (!(phases & 2)) continue;

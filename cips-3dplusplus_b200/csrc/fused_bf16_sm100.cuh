@@ -43,7 +43,8 @@ constexpr int SM_WK16 = SM_HEADS + (int)RGB16_BYTES;             // 204800
 constexpr int SM_AUX = SM_WK16 + (int)W0IMG_BYTES;               // 212992  [slot][4096]
 constexpr int SM_OM = SM_AUX + 2 * AUX_BYTES;                    // 221184  [slot][128] float
 constexpr int SM_RAYACC = SM_OM + 2 * TILE * 4;                  // 222208  [slot][RAYS*2][8] float
-constexpr int SM_MISC = SM_RAYACC + 2 * RAYS * 2 * 8 * 4;        // 224256
+constexpr int SM_PART = SM_RAYACC + 2 * RAYS * 2 * 8 * 4;        // 224256  [slot][RAYS][4 warps][8] float: per-warp ray sums
+constexpr int SM_MISC = SM_PART + 2 * RAYS * 4 * 8 * 4;          // 228352
 constexpr int SM_TOTAL = SM_MISC + 256;
 constexpr int SMEM_BYTES = SM_TOTAL + 1024;
 
@@ -146,6 +147,8 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
     for (int i = threadIdx.x; i < (int)(RGB16_BYTES + W0IMG_BYTES) / 16; i += NTHREADS) dst[i] = src[i];
     float* ra = reinterpret_cast<float*>(smem + SM_RAYACC);
     for (int i = threadIdx.x; i < 2 * RAYS * 2 * 8; i += NTHREADS) ra[i] = 0.f;
+    float* rp = reinterpret_cast<float*>(smem + SM_PART);
+    for (int i = threadIdx.x; i < 2 * RAYS * 4 * 8; i += NTHREADS) rp[i] = 0.f;
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -306,6 +309,7 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
     const uint32_t aux_u32 = smem_u32(aux);
     float* omS = reinterpret_cast<float*>(smem + SM_OM) + s * TILE;
     float* rayacc = reinterpret_cast<float*>(smem + SM_RAYACC) + s * RAYS * 2 * 8;
+    float* raypart = reinterpret_cast<float*>(smem + SM_PART) + s * RAYS * 4 * 8;
     const uint32_t tacc = tmem_base + (uint32_t)s * 256u + ((uint32_t)(quad * 32) << 16);
     const float* scal = reinterpret_cast<const float*>(a.blob + a.L.scal);
     const float bsig = scal[0], brgb0 = scal[1], brgb1 = scal[2], brgb2 = scal[3];
@@ -503,14 +507,19 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
             tmem_ld_wait();
 #pragma unroll
             for (int jx = 0; jx < 16; ++jx) fv[jx] = __float_as_uint(__uint_as_float(fv[jx]) + __uint_as_float(fw[jx]));
-            float* fbase = a.feature_map + ((size_t)img * a.n_rays + r0 + rl0) * W + t + TILE * h;
+            // thread = channel t + 128 h, fv[jx] = ray slot jx.  (b, hw, 256): a warp writes 32 consecutive channels of a
+            // ray; (b, 256, hw): a thread writes up to 16 consecutive rays of its channel
+            const int ch = t + TILE * h;
+            float* fbase = a.feat_nchw ? a.feature_map + ((size_t)img * W + ch) * a.n_rays + r0 + rl0
+                                       : a.feature_map + ((size_t)img * a.n_rays + r0 + rl0) * W + ch;
+            const size_t fstride = a.feat_nchw ? 1 : W;
 #pragma unroll
             for (int jx = 0; jx < RAYS; ++jx) {
               const int rbeg = (rl0 + jx) * N, rend = rbeg + N;      // point range of ray slot jx inside the unit
               if (rbeg < tile_end) {                                  // uniform: the slot is in use
                 float fvv = __uint_as_float(fv[jx]);
                 if (jx == 0) fvv += carry_f[hh];
-                if (rend <= tile_end) fbase[(size_t)jx * W] = fvv;    // ray complete
+                if (rend <= tile_end) fbase[(size_t)jx * fstride] = fvv;    // ray complete
                 if (rend >= tile_end) carry_f[hh] = rend > tile_end ? fvv : 0.f;   // last slot of the tile
               }
             }
@@ -539,13 +548,26 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
               if (same) vals[jx] += y;
             }
           }
+          // The head lane of every (ray, warp) segment parks its partial sums in part[ray slot][warp]; after the barrier the
+          // thread of the ray's last point in this tile adds the (at most four) partials in warp order to the ray's running
+          // sums -- a fixed order, so the maps are bit-reproducible (shared-memory atomics were not for N > 32).
           const int rprev = __shfl_up_sync(0xffffffffu, rl, 1);
           float* racc = rayacc + (rl & (2 * RAYS - 1)) * 8;
+          float* part = raypart + (rl - rl0) * 32;
           if (valid && (lane == 0 || rprev != rl)) {
 #pragma unroll
-            for (int jx = 0; jx < 6; ++jx) atomicAdd(racc + jx, vals[jx]);
+            for (int jx = 0; jx < 6; ++jx) part[quad * 8 + jx] = vals[jx];
           }
           named_bar_sync(bar_id, TILE);
+          if (valid && (k == N - 1 || q == tile_end - 1)) {
+#pragma unroll
+            for (int jx = 0; jx < 6; ++jx) {
+              float acc = racc[jx];
+#pragma unroll
+              for (int w4 = 0; w4 < 4; ++w4) { acc += part[w4 * 8 + jx]; part[w4 * 8 + jx] = 0.f; }
+              racc[jx] = acc;
+            }
+          }
           if (valid && k == N - 1) {
             const float x = racc[3], y = racc[4], z = racc[5];
             float* o3 = a.rgb_map + gray * 3;

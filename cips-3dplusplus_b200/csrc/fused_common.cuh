@@ -21,6 +21,8 @@ struct Args {
   const float* cam_poses; const float* focal; const float* near; const float* far; const float* ray_offset;
   const float* pts; const float* rays_d; const float* viewdirs; const float* z_vals;
   float* rgb_map; float* feature_map; float* sdf; float* mask; float* xyz; float* z_vals_out;
+  int feat_nchw; // feature_map layout: 0 = (b, hw, 256) as the reference returns it, 1 = (b, 256, hw) as the decoder wants it
+                 // (model_v3.py:1014); written directly from the compositing epilogue either way
   int sdf_only;  // density-only pass (coarse pass of the two-pass render): the tile ends after the sdf head -- no view layer,
                  // no rgb head, no compositing; only `sdf` (and `z_vals_out`) are written
   int debug;   // bit 0: producer skips the weight copies (timing experiments only; results are garbage)

@@ -73,7 +73,8 @@ constexpr int SM_OM = SM_AUX + 2 * AUX_BYTES;                    // 217088  [slo
 constexpr int SM_RAYACC = SM_OM + 2 * TILE * 4;                  // 218112  [slot][RAYS*2][8] float
 constexpr int SM_WSIG = SM_RAYACC + 2 * RAYS * 2 * 8 * 4;        // 220160  sigma_linear.weight, fp32 [256]
 constexpr int SM_SDFP = SM_WSIG + W * 4;                         // 221184  [slot][128] float: sdf partial sums of column group 1
-constexpr int SM_MISC = SM_SDFP + 2 * TILE * 4;                  // 222208
+constexpr int SM_PART = SM_SDFP + 2 * TILE * 4;                  // 222208  [slot][RAYS][4 warps][8] float: per-warp ray sums
+constexpr int SM_MISC = SM_PART + 2 * RAYS * 4 * 8 * 4;          // 226304
 constexpr int SM_TOTAL = SM_MISC + 256;
 constexpr int SMEM_BYTES = SM_TOTAL + 1024;
 
@@ -208,6 +209,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
     }
     float* ra = reinterpret_cast<float*>(smem + SM_RAYACC);
     for (int i = threadIdx.x; i < 2 * RAYS * 2 * 8; i += NTHREADS) ra[i] = 0.f;
+    float* rp = reinterpret_cast<float*>(smem + SM_PART);
+    for (int i = threadIdx.x; i < 2 * RAYS * 4 * 8; i += NTHREADS) rp[i] = 0.f;
     float* ws_ = reinterpret_cast<float*>(smem + SM_WSIG);
     for (int i = threadIdx.x; i < W; i += NTHREADS) ws_[i] = reinterpret_cast<const float*>(a.blob + a.L.wsig)[i];
     fence_proxy_async_smem();
@@ -397,6 +400,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
     float* omS = reinterpret_cast<float*>(smem + SM_OM) + s * TILE;
     float* sdfS = reinterpret_cast<float*>(smem + SM_SDFP) + s * TILE;
     float* rayacc = reinterpret_cast<float*>(smem + SM_RAYACC) + s * RAYS * 2 * 8;
+    float* raypart = reinterpret_cast<float*>(smem + SM_PART) + s * RAYS * 4 * 8;
     const uint32_t tacc = tmem_base + (uint32_t)s * 256u + ((uint32_t)(quad * 32) << 16);
     const float* scal = reinterpret_cast<const float*>(a.blob + a.L.scal);
     const float bsig = scal[0], brgb0 = scal[1], brgb1 = scal[2], brgb2 = scal[3];
@@ -590,14 +594,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
             tmem_ld_wait();
 #pragma unroll
             for (int jx = 0; jx < 16; ++jx) fv[jx] = __float_as_uint(__uint_as_float(fv[jx]) + __uint_as_float(fw[jx]));
-            float* fbase = a.feature_map + ((size_t)img * a.n_rays + min(r0 + rl0, a.n_rays - 1)) * W + t + TILE * hh;
+            // thread = channel t + 128 hh, fv[jx] = ray slot jx.  (b, hw, 256): a warp writes 32 consecutive channels of a
+            // ray (128 B); (b, 256, hw): a thread writes up to 16 consecutive rays of its channel (64 B)
+            const int ray0 = min(r0 + rl0, a.n_rays - 1), ch = t + TILE * hh;
+            float* fbase = a.feat_nchw ? a.feature_map + ((size_t)img * W + ch) * a.n_rays + ray0
+                                       : a.feature_map + ((size_t)img * a.n_rays + ray0) * W + ch;
+            const size_t fstride = a.feat_nchw ? 1 : W;
 #pragma unroll
             for (int jx = 0; jx < RAYS; ++jx) {
               const int rbeg = (rl0 + jx) * N, rend = rbeg + N;      // point range of ray slot jx inside the unit
               if (rbeg < tile_end) {                                  // uniform: the slot is in use
                 float fvv = __uint_as_float(fv[jx]);
                 if (jx == 0) fvv += carry_f[hh];
-                if (rend <= tile_end) fbase[(size_t)jx * W] = fvv;    // ray complete
+                if (rend <= tile_end) fbase[(size_t)jx * fstride] = fvv;    // ray complete
                 if (rend >= tile_end) carry_f[hh] = rend > tile_end ? fvv : 0.f;   // last slot of the tile
               }
             }
@@ -621,13 +630,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
               if (same) vals[jx] += y;
             }
           }
+          // The head lane of every (ray, warp) segment parks its partial sums in part[ray slot][warp]; after the barrier the
+          // thread of the ray's last point in this tile adds the (at most four) partials in warp order to the ray's running
+          // sums -- a fixed order, so the maps are bit-reproducible (shared-memory atomics were not for N > 32).
           const int rprev = __shfl_up_sync(0xffffffffu, rl, 1);
           float* racc = rayacc + (rl & (2 * RAYS - 1)) * 8;
+          float* part = raypart + (rl - rl0) * 32;
           if (valid && (lane == 0 || rprev != rl)) {
 #pragma unroll
-            for (int jx = 0; jx < 6; ++jx) atomicAdd(racc + jx, vals[jx]);
+            for (int jx = 0; jx < 6; ++jx) part[quad * 8 + jx] = vals[jx];
           }
           named_bar_sync(bar_id, TILE);
+          if (valid && (k == N - 1 || q == tile_end - 1)) {
+#pragma unroll
+            for (int jx = 0; jx < 6; ++jx) {
+              float acc = racc[jx];
+#pragma unroll
+              for (int w4 = 0; w4 < 4; ++w4) { acc += part[w4 * 8 + jx]; part[w4 * 8 + jx] = 0.f; }
+              racc[jx] = acc;
+            }
+          }
           if (valid && k == N - 1) {
             const float x = racc[3], y = racc[4], z = racc[5];
             float* o3 = a.rgb_map + gray * 3;

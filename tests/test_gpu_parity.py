@@ -239,6 +239,27 @@ def test_render_from_poses_matches_reference_golden(case, precision):
     assert np.abs(g("mask")[..., 1] - c["mask"][..., 1]).max() < (DEPTH_ABS if precision == "fp32" else 2e-3)
 
 
+@pytest.mark.parametrize("fwd", ["pair", "v3"])
+@pytest.mark.parametrize("case,img_size", [("ffhq_d8_n24_b2_wplus_perturb", 64), ("cars_d6_n36_b2_beta", 24), ("ffhq_d2_n128_static", 9)])
+def test_channel_major_features_come_from_the_kernel(case, img_size, fwd):
+    """bf16 mode: `features_nchw=True` (the layout the decoder consumes, model_v3.py:1014) is written by the compositing
+    epilogue itself -- bit-identical to the transpose of the default layout, no extra launch, no staging workspace."""
+    import cips3dpp_b200 as c3d
+    c3d._abi.set_options(fwd=fwd)
+    c = load_case(case)
+    m = _module(int(c["D"]), "bf16", c["sigmoid_beta"])
+    args = (_t(c["c2w"]), _t(c["focal"]) * img_size / 64, _t(c["near"]), _t(c["far"]), _t(c["styles"]))
+    kw = dict(img_size=img_size, N_samples=int(c["N"]), static_viewdirs=bool(c["static_viewdirs"]))
+    with torch.no_grad():
+        a = m.render(*args, **kw)
+        la = m.last_launch_count
+        b = m.render(*args, features_nchw=True, **kw)
+        lb = m.last_launch_count
+    assert b["feature_map"].shape == (a["feature_map"].shape[0], 256, img_size * img_size)
+    assert torch.equal(a["feature_map"].transpose(1, 2), b["feature_map"])
+    assert torch.equal(a["rgb_map"], b["rgb_map"]) and la == lb
+
+
 def test_render_nchw_and_perturb_consistency():
     """features_nchw is the transpose of the default layout; perturbed sampling equals POINTS mode fed with
     the depths the kernel reports."""
