@@ -100,10 +100,11 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def cpu_baseline(cfg, n_images, reps=1):
-    """oracle/nerf_oracle.c (kind 'port': the reference path is Python, nothing to compile) on host cores."""
+def cpu_baseline(cfg, n_images, reps=1, seeds=(1, 2), keep=None):
+    """oracle/nerf_oracle.c (kind 'port': the reference path is Python, nothing to compile) on host cores.
+    `keep` (a dict) receives the oracle's outputs for these images: the caller checks the GPU maps against them."""
     from oracle import c_oracle, nerf_oracle as O
-    c2w, focal, near, far, styles = workload(cfg)
+    c2w, focal, near, far, styles = workload(cfg, seed_latent=seeds[0], seed_pose=seeds[1])
     params = O.init_params(cfg["D"], seed=0)
     packed = c_oracle.pack_params(params)
     sl = slice(0, n_images)
@@ -112,8 +113,10 @@ def cpu_baseline(cfg, n_images, reps=1):
     for _ in range(reps + 1):                                      # first pass = warm-up
         t0 = time.perf_counter()
         pts, rd, vd, z = c_oracle.prepare_inputs(c2w[sl], focal[sl], near[sl], far[sl], IMG, cfg["N"])
-        c_oracle.renderer_forward(params, pts, rd, vd, z, near[sl], far[sl], styles[sl], nthreads=nthr, packed=packed)
+        outs = c_oracle.renderer_forward(params, pts, rd, vd, z, near[sl], far[sl], styles[sl], nthreads=nthr, packed=packed)
         times.append(time.perf_counter() - t0)
+    if keep is not None:
+        keep.update(rgb_map=outs[0], feature_map=outs[1], sdf=outs[2], mask=outs[3], xyz=outs[4], z_vals=z)
     t = min(times[1:])
     return dict(value=n_images * IMG * IMG / t, unit="rays/s", cores=nthr, kind="port",
                 sample=f"{n_images} of {c2w.shape[0]} images of the step ({t:.2f} s, best of {reps})",
@@ -476,7 +479,8 @@ def main():
                     "d2h_bytes_per_step": int(sum(h.numel() * 4 for h in out_host.values()))},
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": traffic, "kernel": "fused_forward_kernel",
+                         "frac": achieved / peak_tf, "traffic": traffic,
+                         "kernel": "fused_forward_pair_kernel + its two per-image weight-image kernels (step minus style_prep)",
                          "peak_source": peak_src, "kernel_ms": ms_kernel, "flops_per_launch": flops_launch,
                          "frac_of_nominal_2250": achieved / 2250.0,
                          "frac_of_burst": achieved / peaks.get("bf16_tflops", 1590.0)},
@@ -484,8 +488,24 @@ def main():
         }
         line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
-            cb, _ = cpu_baseline(cfg, min(B, 8), reps=2)
+            # the CPU arm renders the first images of this very step: its outputs pin the GPU maps of the timed workload
+            ref = {}
+            n_chk = min(B, 8)
+            cb, _ = cpu_baseline(cfg, n_chk, reps=2, seeds=(1 + rank, 2 + rank), keep=ref)
             line["cpu_baseline"] = cb
+            with torch.no_grad():
+                got = step_resident()
+            torch.cuda.synchronize()
+            rel = lambda a_, b_: float(np.linalg.norm(a_.astype(np.float64) - b_) / max(np.linalg.norm(b_.astype(np.float64)), 1e-30))
+            g = {k: got[k][:n_chk].cpu().numpy() for k in ("rgb_map", "feature_map", "sdf", "mask", "xyz", "z_vals")}
+            line["parity"] = {
+                "against": f"oracle/nerf_oracle.c on the first {n_chk} images of the timed step (full 64x64, all rays)",
+                "feature_map_rel_l2": rel(g["feature_map"], ref["feature_map"]), "rgb_map_rel_l2": rel(g["rgb_map"], ref["rgb_map"]),
+                "xyz_rel_l2": rel(g["xyz"], ref["xyz"]), "sdf_rel_l2": rel(g["sdf"], ref["sdf"]),
+                "sample_depth_max_abs": float(np.abs(g["z_vals"] - ref["z_vals"]).max()),
+                "depth_map_max_abs": float(np.abs(g["mask"][..., 1] - ref["mask"][..., 1]).max()),
+                "tolerance": {"bf16": "2e-2 rel-L2", "fp32": "1e-3 rel-L2, 1e-4 depth"}[args.precision],
+            }
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

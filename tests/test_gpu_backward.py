@@ -9,7 +9,14 @@ from conftest import GRAD_CASES, load_case, load_weights, rel_l2
 
 pytestmark = pytest.mark.gpu
 GRAD_REL = 1e-3          # fp32 mode (FP32-pipe backward)
-GRAD_REL_BF16 = 5e-2     # bf16 mode (tensor-core backward of the bf16 forward; measured 3.3e-2 at D=8, ~1e-2 at D=2)
+# bf16 mode: the tensor-core backward differentiates the bf16 forward, whose rounding grows layer by layer; SURVEY 8(d)'s 2e-2
+# holds at the shipped depth D = 2 and for the camera-side gradients at D = 8, not for styles / pts at D = 8.  Bounds per
+# tensor = measured on B200 + 25 % (measured: D=2 styles 5.8e-3, pts 7.2e-3, rays_d 2.1e-3, viewdirs 4.2e-3; D=8 styles
+# 3.26e-2, pts 3.01e-2, rays_d 8.8e-3, viewdirs 1.17e-2; eikonal term 5.0e-3 / 2.46e-2).
+GRAD_REL_BF16 = {
+    "ffhq_d2_n24_grads": dict(styles=7.5e-3, pts=9e-3, rays_d=2.7e-3, viewdirs=5.5e-3, eikonal=6.5e-3),
+    "ffhq_d8_n24_grads_static": dict(styles=4.1e-2, pts=3.8e-2, rays_d=1.1e-2, viewdirs=1.5e-2, eikonal=3.1e-2),
+}
 
 
 def _dev():
@@ -45,7 +52,8 @@ def test_gradients_match_reference_autograd(case, precision):
                 rays_d=rel_l2(rays_d.grad.cpu().numpy(), c["g_rays_d"]),
                 viewdirs=rel_l2(viewdirs.grad.cpu().numpy(), c["g_viewdirs"]))
     print(case, precision, errs)
-    assert max(errs.values()) < (GRAD_REL if precision == "fp32" else GRAD_REL_BF16), errs
+    for k, e in errs.items():
+        assert e < (GRAD_REL if precision == "fp32" else GRAD_REL_BF16[case][k]), (k, errs)
 
 
 def _volume_integration_torch(rgb, sdf, feat, z, rd, pts, beta):
@@ -263,8 +271,8 @@ def test_eikonal_term_matches_reference(case, precision):
     assert eik.shape == ref.shape
     err = rel_l2(eik.cpu().numpy(), ref)
     print(case, precision, "eikonal rel-L2", err)
-    assert err < (GRAD_REL if precision == "fp32" else GRAD_REL_BF16)
-    assert rel_l2(out[2].cpu().numpy(), c["sdf"]) < (1e-3 if precision == "fp32" else 5e-2)
+    assert err < (GRAD_REL if precision == "fp32" else GRAD_REL_BF16[case]["eikonal"])
+    assert rel_l2(out[2].cpu().numpy(), c["sdf"]) < (1e-3 if precision == "fp32" else 7.5e-3)
 
 
 @pytest.mark.parametrize("case", GRAD_CASES)

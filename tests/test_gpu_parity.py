@@ -213,10 +213,11 @@ def test_forward_bf16_matches_reference_golden(case, cluster, monkeypatch):
     c, (rgb_map, feat, sdf, mask, xyz), m = _run_points(case, "bf16")
     errs = dict(feat=rel_l2(feat, c["feature_map"]), rgb=rel_l2(rgb_map, c["rgb_map"]), sdf=rel_l2(sdf, c["sdf"]),
                 xyz=rel_l2(xyz, c["xyz"]), depth=float(np.abs(mask[..., 1] - c["mask"][..., 1]).max()))
-    print(case, cluster, errs)
+    print("GOLD", case, cluster, {k: f"{v:.3e}" for k, v in errs.items()})
     assert errs["feat"] < BF16_REL and errs["rgb"] < BF16_REL, errs
-    assert errs["xyz"] < BF16_REL and errs["sdf"] < 5e-2, errs
-    assert errs["depth"] < 2e-3, errs
+    # measured on B200 over all six cases and three kernel variants: sdf <= 6.0e-3, xyz <= 2.4e-3, depth map <= 1.2e-3
+    assert errs["xyz"] < 3e-3 and errs["sdf"] < 7.5e-3, errs
+    assert errs["depth"] < 1.5e-3, errs
     assert m.last_launch_count == (4 if cluster == "pair" else 2)   # style_prep (+ 2 weight-image kernels) + fused kernel
 
 
@@ -355,8 +356,12 @@ def test_forward_edge_shapes_match_oracle(D, N, R, b, mode, monkeypatch):
         out = m(pts=_t(pts), rays_d=_t(d), viewdirs=_t(vd), z_vals=_t(z), near=_t(near), far=_t(far), styles=_t(styles))
     torch.cuda.synchronize()
     ref = O.renderer_forward(params, pts, d, vd, z, near, far, styles)
-    # bf16 rounding is amplified layer by layer (measured rel-L2 1e-2 at D = 8, 5e-2 at D = 16 with random-init weights)
-    tol = FP32_REL if precision == "fp32" else (3e-2 if D <= 8 else 1e-1)
+    # bf16 rounding is amplified layer by layer.  Bounds = measured on B200 (both bf16 kernels) + 20 %: every depth the
+    # reference ships (D <= 8) stays inside the north star's 2e-2 for the maps; D = 16 (no reference config) is beyond it.
+    # sdf is a relative error over values that cross zero: the single-ray D = 8 case measures 3.7e-2.
+    maps_bf16 = {1: 3e-3, 2: 4.5e-3, 3: 5e-3, 6: 9e-3, 8: 1.2e-2, 16: 6.5e-2}[D]
+    sdf_bf16 = {1: 1.5e-3, 2: 3.3e-3, 3: 5e-3, 6: 6e-3, 8: 4.5e-2, 16: 5.2e-2}[D]
+    tol = FP32_REL if precision == "fp32" else maps_bf16
     names = ("rgb_map", "feature_map", "sdf", "mask", "xyz")
     for name, got, want in zip(names, out[:5], ref):
         got = got.cpu().numpy()
@@ -365,7 +370,8 @@ def test_forward_edge_shapes_match_oracle(D, N, R, b, mode, monkeypatch):
         if name == "mask":
             assert np.abs(got - want).max() < (2e-4 if precision == "fp32" else (2e-2 if D <= 8 else 6e-2)), name
         else:
-            lim = tol if name != "sdf" or precision == "fp32" else max(tol, 5e-2) * (1 if D <= 8 else 2)
+            lim = tol if name != "sdf" or precision == "fp32" else sdf_bf16
+            print("EDGE", D, N, R, b, mode, name, f"{rel_l2(got, want):.3e}")
             assert rel_l2(got, want) < lim, (name, rel_l2(got, want))
 
 
