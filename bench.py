@@ -31,6 +31,11 @@ CONFIGS = {
                  desc="FFHQ v10 NeRF branch 64x64 at the shipped r1024 depth D=2, N=24, 32 latents x 8-pose yaw sweep"),
     "c3": dict(D=2, N=128, latents=8, sweep=1, fov=6.0, radius=0.12, azim=0.3, elev=0.15,
                desc="FFHQ v10 multi-view render NeRF branch 64x64, D=2, N=128, 8 images (BASELINE configs[2], NeRF part)"),
+    # BASELINE configs[2] for real: the unmodified reference Generator (mapping networks, ray chunking, re-layout, modulated-
+    # conv decoder to 1024 x 1024; modules from oracle/_ref, see oracle/make_ref.sh) around the B200 NeRF branch
+    "c3full": dict(D=2, N=128, latents=8, sweep=1, fov=6.0, radius=0.12, azim=0.3, elev=0.15,
+                   desc="FFHQ v10 full multi-view render 1024x1024: B200 NeRF branch at 64x64 (D=2, N=128) + the reference's "
+                        "modulated-conv decoder, 8 images per GPU, sharded by latent (BASELINE configs[2])"),
     "c4": dict(D=6, N=24, latents=32, sweep=1, fov=15.0, radius=0.3, azim=3.14, elev=0.0837,
                desc="CompCars v10 NeRF branch 64x64, D=6, N=24, batch 32 (BASELINE configs[3])"),
     "c1": dict(D=8, N=24, latents=1, sweep=1, fov=6.0, radius=0.12, azim=0.0, elev=0.0,
@@ -238,6 +243,150 @@ def run_inversion(args, cfg, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_full_render(args, cfg, rank, world, local_rank):
+    """BASELINE configs[2]: the reference `model_v3.Generator.forward` (exp/cips3d/models/model_v3.py:875-1042; called by the
+    apps at render_video_web_v10.py:1806-1824) with `use_b200_nerf_branch(G)`: 8 latents per GPU, 64 x 64 rays, N = 128
+    samples, the reference decoder up to 1024 x 1024.  A step = one `G.forward` over the rank's 8 images.  value = rays/s of
+    the whole pipeline with inputs resident; e2e = latents / cameras from pinned host memory in, the 1024 x 1024 images back to
+    pinned host memory.  The same generator with the reference's own renderer is timed beside it on the same GPU
+    (`reference_on_gpu`), and its CPU run is the `cpu_baseline` (kind "reference": the live PyTorch reference).
+    The decoder's two `op` CUDA extensions are pure-torch stand-ins in every arm (tests/ref_stubs.py)."""
+    import copy
+    import torch
+    import torch.distributed as dist
+    import cips3dpp_b200 as c3d
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ref_stubs
+    if not ref_stubs.available():
+        if rank == 0:
+            print(json.dumps({"metric": "nerf_branch_rays_per_s", "unavailable": "reference modules not found (run oracle/make_ref.sh "
+                              "in the build container: oracle/_ref travels with the snapshot)", "config": {"workload": cfg["desc"]}}))
+        return
+    model_v3, nerf_utils = ref_stubs.import_model_v3()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    D, N, B = cfg["D"], cfg["N"], cfg["latents"]
+    torch.manual_seed(0)
+    G_ref = ref_stubs.build_generator(model_v3, D=D, size_end=1024, upsample_list=(128, 256, 512, 1024)).to(dev).eval().requires_grad_(False)
+    G = c3d.use_b200_nerf_branch(copy.deepcopy(G_ref), precision=args.precision)
+    G.renderer.cache_packed = True
+    g = torch.Generator().manual_seed(11 + rank)                        # each rank renders its own latents (sharded by latent)
+    host = dict(z0=torch.randn(B, 256, generator=g).pin_memory(), z1=torch.randn(B, 256, generator=g).pin_memory(),
+                loc=torch.stack([cfg["azim"] * (2 * torch.rand(B, generator=g) - 1),
+                                 cfg["elev"] * (2 * torch.rand(B, generator=g) - 1)], 1).pin_memory())
+    torch.manual_seed(1)
+    noise = G.create_noise_bufs(start_size=IMG, device=dev)
+    nerf_cfg = dict(N_samples=N, perturb=False, static_viewdirs=False)
+    out_host = torch.empty(B, 3, 1024, 1024).pin_memory()
+
+    def forward(gen, z0, z1, loc):
+        pose, focal, near, far, _ = nerf_utils.Camera.generate_camera_params(img_size=IMG, device=dev, locations=loc,
+                                                                             fov_ang=cfg["fov"], dist_radius=cfg["radius"])
+        return gen(zs=[z0, z1], cam_poses=pose, focals=focal, img_size=IMG, near=near, far=far, truncation=1, return_xyz=True,
+                   noise_bufs=noise, nerf_cfg=nerf_cfg)
+    res = {k: v.to(dev) for k, v in host.items()}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        with torch.no_grad():
+            for _ in range(warmup):
+                fn()
+            sync()
+            evs = []
+            for _ in range(steps):
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream); fn(); e1.record(stream)
+                evs.append((e0, e1))
+            sync()
+        return float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+    def step():
+        return forward(G, res["z0"], res["z1"], res["loc"])
+
+    def step_e2e():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        out_host.copy_(forward(G, d["z0"], d["z1"], d["loc"])["rgb"], non_blocking=True)
+
+    def step_branch():                                                   # the NeRF branch of the same step, alone
+        pose, focal, near, far, _ = nerf_utils.Camera.generate_camera_params(img_size=IMG, device=dev, locations=res["loc"],
+                                                                             fov_ang=cfg["fov"], dist_radius=cfg["radius"])
+        return G.renderer.render(pose, focal, near, far, styles_b, img_size=IMG, N_samples=N)
+    styles_b = torch.zeros(B, D + 1, 256, device=dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_step = timed(step, args.steps, max(args.warmup, 3))
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    launches = G.renderer.last_launch_count
+    ms_e2e = timed(step_e2e, args.steps, 2)
+    ms_branch = timed(step_branch, args.steps, 2)
+    ms_ref_gpu = timed(lambda: forward(G_ref, res["z0"], res["z1"], res["loc"]), max(2, args.steps // 2), 2)
+    with torch.no_grad():
+        a_, r_ = step(), forward(G_ref, res["z0"], res["z1"], res["loc"])
+    rel = lambda x, y: float((x.double() - y.double()).norm() / y.double().norm())
+    parity = {"against": "the same reference Generator with its own VolumeFeatureRenderer, same GPU, same inputs",
+              "rgb_1024_rel_l2": rel(a_["rgb"], r_["rgb"]), "thumb_rgb_rel_l2": rel(a_["thumb_rgb"], r_["thumb_rgb"]),
+              "xyz_rel_l2": rel(a_["xyz"], r_["xyz"]), "depth_max_abs": float((a_["depth"] - r_["depth"]).abs().max())}
+    if world > 1:
+        t = torch.tensor([ms_step, ms_e2e, ms_branch], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, ms_e2e, ms_branch = (float(x) for x in t)
+    if rank == 0:
+        rays = B * IMG * IMG
+        line = {
+            "metric": "nerf_branch_rays_per_s", "value": world * rays / (ms_step * 1e-3), "unit": "rays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "images_per_s": world * B / (ms_step * 1e-3),
+            "config": {"workload": cfg["desc"], "images_per_gpu": B, "rays_per_image": IMG * IMG, "samples_per_ray": N, "layers": D,
+                       "image_size": 1024, "weights": "random-init (reference constructors)",
+                       "decoder": "reference modules, `op` CUDA extensions replaced by pure-torch stand-ins in every arm",
+                       "l2": "flushed (256 MiB write) between timed steps, outside the event pair"},
+            "e2e": {"value": world * rays / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(sum(v.numel() * 4 for v in host.values())), "d2h_bytes_per_step": int(out_host.numel() * 4)},
+            "gpu_launches": int(launches * args.steps),
+            "breakdown_ms": {"nerf_branch": ms_branch, "mapping_decoder_and_glue": ms_step - ms_branch},
+            "reference_on_gpu": {"ms_per_step": ms_ref_gpu, "images_per_s": B / (ms_ref_gpu * 1e-3),
+                                 "what": "the same Generator with the reference's PyTorch VolumeFeatureRenderer (fp32, cuBLAS + ATen)"},
+            "parity": parity,
+            "roofline": {"bound": "tensor", "kernel": "fused_forward_pair_kernel (NeRF-branch part of the step)", "unit": "TFLOP/s",
+                         "achieved": None, "peak": None, "frac": None, "traffic": None},
+            "clocks": sampler.summary(),
+        }
+        from oracle import nerf_oracle as O
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        ach = O.flops_per_point(D) * rays * N / (ms_branch * 1e-3) / 1e12
+        line["roofline"].update(achieved=ach, peak=peak_tf, frac=ach / peak_tf,
+                                peak_source="measured sustained (MEASURED_PEAKS.json)" if peaks else "fallback")
+        if world == 1 and not args.no_cpu_baseline:
+            G_cpu = copy.deepcopy(G_ref).cpu()
+            noise_cpu = [n.cpu() for n in noise]
+            torch.set_num_threads(host_threads())
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                pose, focal, near, far, _ = nerf_utils.Camera.generate_camera_params(img_size=IMG, device="cpu", locations=host["loc"][:1],
+                                                                                     fov_ang=cfg["fov"], dist_radius=cfg["radius"])
+                G_cpu(zs=[host["z0"][:1], host["z1"][:1]], cam_poses=pose, focals=focal, img_size=IMG, near=near, far=far,
+                      truncation=1, return_xyz=True, noise_bufs=noise_cpu, nerf_cfg=nerf_cfg)
+            tc = time.perf_counter() - t0
+            line["cpu_baseline"] = dict(value=IMG * IMG / tc, unit="rays/s", cores=host_threads(), kind="reference",
+                                        sample=f"1 of the step's {B} images through the live PyTorch reference Generator on the host "
+                                               f"cores ({tc:.1f} s)", images_per_s=1 / tc)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def side_measurements(m, params, devt, D, N, dev, timed):
     """Two side lines SURVEY.md section 8(d) asks for, at N=1 only, outside the headline timed region:
     (1) the standalone compositing kernel against the HBM roofline on reference-layout inputs
@@ -321,6 +470,9 @@ def main():
         return
     if args.config == "c5":
         run_inversion(args, cfg, rank, world, local_rank)
+        return
+    if args.config == "c3full":
+        run_full_render(args, cfg, rank, world, local_rank)
         return
 
     import torch
