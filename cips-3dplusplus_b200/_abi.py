@@ -9,12 +9,13 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("C3D_LIB") or os.path.join(HERE, "libc3dpp.so")   # C3D_LIB: A/B builds (bench_tools)
 SRC = os.path.join(HERE, "csrc", "c3d_abi.cu")
-ABI_VERSION = 9
+ABI_VERSION = 10
 MAX_LAYERS = 16
+MAX_PEERS = 16
 MIN_SAMPLES_BF16 = 8     # fused::MIN_SAMPLES (csrc/fused_common.cuh)
 MODE_FP32, MODE_BF16 = 0, 1
 INPUT_POSES, INPUT_POINTS = 0, 1
-FEAT_NHWC, FEAT_NCHW = 0, 1
+FEAT_NHWC, FEAT_NCHW, FEAT_NCHW_BF16 = 0, 1, 2
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC"]
@@ -39,13 +40,18 @@ class ParamGrads(C.Structure):
                             "sigma_weight", "sigma_bias", "sigmoid_beta")]
 
 
+class GatherOut(C.Structure):
+    _fields_ = [("n_peers", C.c_int32), ("image_offset", C.c_int32)] + \
+        [(n, _fp * MAX_PEERS) for n in ("feature_map", "rgb_map", "mask", "xyz")]
+
+
 class FwdParams(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("abi_version", "mode", "input_kind", "feat_layout", "batch", "n_rays",
                                          "n_samples", "D", "img_size", "static_viewdirs")] + \
         [(n, _fp) for n in ("packed", "styles", "cam_poses", "focal", "near", "far", "ray_offset",
                             "pts", "rays_d", "viewdirs", "z_vals",
                             "rgb_map", "feature_map", "sdf", "mask", "xyz", "z_vals_out", "workspace")] + \
-        [("workspace_bytes", C.c_size_t)]
+        [("workspace_bytes", C.c_size_t), ("gather", C.POINTER(GatherOut))]
 
 
 class BwdParams(C.Structure):

@@ -89,7 +89,7 @@ static int device_sms(int* dev_out = nullptr) {
     }                                                                                                         \
   } while (0)
 // density-only pass: none of the four map outputs is requested (only sdf / z_vals_out)
-static bool fwd_sdf_only(const c3d_fwd_params* p) { return !p->rgb_map && !p->feature_map && !p->mask && !p->xyz; }
+static bool fwd_sdf_only(const c3d_fwd_params* p) { return !p->gather && !p->rgb_map && !p->feature_map && !p->mask && !p->xyz; }
 
 // the plain bf16 forward runs the CTA-pair kernel; the density-only pass (and the save-mode forward of the backward) run the
 // single-CTA kernel, which has those modes
@@ -151,8 +151,18 @@ static int validate_fwd(const c3d_fwd_params* p) {
   C3D_CHECK_ARG(p->D >= 1 && p->D <= C3D_MAX_LAYERS, "D=%d outside [1,%d]", p->D, C3D_MAX_LAYERS);
   C3D_CHECK_ARG((long long)p->batch * p->n_rays * p->n_samples < (1ll << 31), "batch*n_rays*n_samples overflows int32");
   C3D_CHECK_ARG(p->packed && p->styles && p->near && p->far, "packed/styles/near/far must be non-NULL");
-  C3D_CHECK_ARG(p->sdf && ((p->rgb_map && p->feature_map && p->mask && p->xyz) || fwd_sdf_only(p)),
+  C3D_CHECK_ARG(p->sdf && ((p->rgb_map && p->feature_map && p->mask && p->xyz) || fwd_sdf_only(p) || p->gather),
                 "outputs: sdf plus either all of rgb_map / feature_map / mask / xyz, or none of them (density-only pass)");
+  if (p->gather) {
+    const c3d_gather_out* g = p->gather;
+    C3D_CHECK_ARG(fwd_uses_pair(p), "the fused all-gather is part of the bf16 CTA-pair forward kernel (MODE_BF16, n_samples >= %d, "
+                                    "option fwd=pair)", fused::MIN_SAMPLES);
+    C3D_CHECK_ARG(g->n_peers >= 1 && g->n_peers <= C3D_MAX_PEERS && g->image_offset >= 0, "gather: n_peers=%d image_offset=%d",
+                  g->n_peers, g->image_offset);
+    for (int i = 0; i < g->n_peers; ++i)
+      C3D_CHECK_ARG(g->feature_map[i] && g->rgb_map[i] && g->mask[i] && g->xyz[i] && aligned16(g->feature_map[i]) &&
+                    aligned16(g->rgb_map[i]) && aligned16(g->mask[i]) && aligned16(g->xyz[i]), "gather: destination %d is NULL or unaligned", i);
+  }
   if (p->input_kind == C3D_INPUT_POSES) {
     C3D_CHECK_ARG(p->cam_poses && p->focal, "POSES input needs cam_poses and focal");
     C3D_CHECK_ARG(p->img_size >= 1 && p->n_rays == p->img_size * p->img_size, "n_rays=%d != img_size^2 (%d)", p->n_rays, p->img_size);
@@ -162,7 +172,10 @@ static int validate_fwd(const c3d_fwd_params* p) {
   const void* ptrs[] = {p->packed, p->styles, p->cam_poses, p->pts, p->rays_d, p->viewdirs, p->z_vals, p->rgb_map,
                         p->feature_map, p->sdf, p->mask, p->xyz, p->workspace};
   for (const void* q : ptrs) C3D_CHECK_ARG(aligned16(q), "pointer %p is not 16-byte aligned", q);
-  C3D_CHECK_ARG(p->feat_layout == C3D_FEAT_NHWC || p->feat_layout == C3D_FEAT_NCHW, "bad feat_layout %d", p->feat_layout);
+  C3D_CHECK_ARG(p->feat_layout == C3D_FEAT_NHWC || p->feat_layout == C3D_FEAT_NCHW || p->feat_layout == C3D_FEAT_NCHW_BF16,
+                "bad feat_layout %d", p->feat_layout);
+  C3D_CHECK_ARG(p->feat_layout != C3D_FEAT_NCHW_BF16 || (p->mode == C3D_MODE_BF16 && p->n_samples >= fused::MIN_SAMPLES),
+                "bf16 feature maps come from the tensor-core kernels only (MODE_BF16, n_samples >= %d)", fused::MIN_SAMPLES);
   const FwdWs w = fwd_ws(p);
   C3D_CHECK_ARG(p->workspace && p->workspace_bytes >= w.total, "workspace too small: %zu < %zu", p->workspace_bytes, w.total);
   return C3D_OK;
@@ -223,7 +236,14 @@ static void fused_fill_args(fused::Args& a, const c3d_fwd_params* p, const float
   a.rgb_map = p->rgb_map; a.feature_map = p->feature_map; a.sdf = p->sdf; a.mask = p->mask; a.xyz = p->xyz;
   a.z_vals_out = p->z_vals_out;
   a.sdf_only = fwd_sdf_only(p) ? 1 : 0;
-  a.feat_nchw = p->feat_layout == C3D_FEAT_NCHW ? 1 : 0;
+  a.feat_nchw = p->feat_layout == C3D_FEAT_NCHW ? 1 : (p->feat_layout == C3D_FEAT_NCHW_BF16 ? 2 : 0);
+  if (p->gather) {
+    a.n_peers = p->gather->n_peers; a.gather_off = p->gather->image_offset;
+    for (int i = 0; i < a.n_peers; ++i) {
+      a.peer_feat[i] = p->gather->feature_map[i]; a.peer_rgb[i] = p->gather->rgb_map[i];
+      a.peer_mask[i] = p->gather->mask[i]; a.peer_xyz[i] = p->gather->xyz[i];
+    }
+  }
   a.debug = options().debug;
 }
 

@@ -512,14 +512,18 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
             const int ch = t + TILE * h;
             float* fbase = a.feat_nchw ? a.feature_map + ((size_t)img * W + ch) * a.n_rays + r0 + rl0
                                        : a.feature_map + ((size_t)img * a.n_rays + r0 + rl0) * W + ch;
+            __nv_bfloat16* hbase = reinterpret_cast<__nv_bfloat16*>(a.feature_map) + ((size_t)img * W + ch) * a.n_rays + r0 + rl0;
             const size_t fstride = a.feat_nchw ? 1 : W;
+            const bool fbf16 = a.feat_nchw == 2;          // (b, 256, hw) bf16: the decoder hand-off at half the bytes
 #pragma unroll
             for (int jx = 0; jx < RAYS; ++jx) {
               const int rbeg = (rl0 + jx) * N, rend = rbeg + N;      // point range of ray slot jx inside the unit
               if (rbeg < tile_end) {                                  // uniform: the slot is in use
                 float fvv = __uint_as_float(fv[jx]);
                 if (jx == 0) fvv += carry_f[hh];
-                if (rend <= tile_end) fbase[(size_t)jx * fstride] = fvv;    // ray complete
+                if (rend <= tile_end) {                                       // ray complete
+                  if (fbf16) hbase[jx] = __float2bfloat16_rn(fvv); else fbase[(size_t)jx * fstride] = fvv;
+                }
                 if (rend >= tile_end) carry_f[hh] = rend > tile_end ? fvv : 0.f;   // last slot of the tile
               }
             }

@@ -23,6 +23,10 @@ struct Args {
   float* rgb_map; float* feature_map; float* sdf; float* mask; float* xyz; float* z_vals_out;
   int feat_nchw; // feature_map layout: 0 = (b, hw, 256) as the reference returns it, 1 = (b, 256, hw) as the decoder wants it
                  // (model_v3.py:1014); written directly from the compositing epilogue either way
+  // fused all-gather (c3d_gather_out): the maps of image `img` go to image `gather_off + img` of every peer's gathered tensors
+  // (peer memory mapped over NVLink); n_peers == 0: the four pointers above
+  int n_peers, gather_off;
+  void* peer_feat[C3D_MAX_PEERS]; float* peer_rgb[C3D_MAX_PEERS]; float* peer_mask[C3D_MAX_PEERS]; float* peer_xyz[C3D_MAX_PEERS];
   int sdf_only;  // density-only pass (coarse pass of the two-pass render): the tile ends after the sdf head -- no view layer,
                  // no rgb head, no compositing; only `sdf` (and `z_vals_out`) are written
   int debug;   // bit 0: producer skips the weight copies (timing experiments only; results are garbage)

@@ -597,16 +597,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
             // thread = channel t + 128 hh, fv[jx] = ray slot jx.  (b, hw, 256): a warp writes 32 consecutive channels of a
             // ray (128 B); (b, 256, hw): a thread writes up to 16 consecutive rays of its channel (64 B)
             const int ray0 = min(r0 + rl0, a.n_rays - 1), ch = t + TILE * hh;
-            float* fbase = a.feat_nchw ? a.feature_map + ((size_t)img * W + ch) * a.n_rays + ray0
-                                       : a.feature_map + ((size_t)img * a.n_rays + ray0) * W + ch;
+            // destination(s): this rank's feature_map, or -- fused all-gather -- image gather_off + img of every peer's gathered
+            // tensor (peer memory over NVLink; plain stores, visible to the peers once the kernel has completed)
+            const int ndst = a.n_peers > 0 ? a.n_peers : 1;
+            const size_t gimg = (size_t)(a.n_peers > 0 ? a.gather_off : 0) + img;
+            const size_t foff = a.feat_nchw ? (gimg * W + ch) * a.n_rays + ray0 : (gimg * a.n_rays + ray0) * W + ch;
             const size_t fstride = a.feat_nchw ? 1 : W;
+            const bool fbf16 = a.feat_nchw == 2;          // (b, 256, hw) bf16: the decoder hand-off at half the bytes
 #pragma unroll
             for (int jx = 0; jx < RAYS; ++jx) {
               const int rbeg = (rl0 + jx) * N, rend = rbeg + N;      // point range of ray slot jx inside the unit
               if (rbeg < tile_end) {                                  // uniform: the slot is in use
                 float fvv = __uint_as_float(fv[jx]);
                 if (jx == 0) fvv += carry_f[hh];
-                if (rend <= tile_end) fbase[(size_t)jx * fstride] = fvv;    // ray complete
+                if (rend <= tile_end) {                               // ray complete
+                  for (int pr = 0; pr < ndst; ++pr) {
+                    void* fb = a.n_peers > 0 ? a.peer_feat[pr] : (void*)a.feature_map;
+                    if (fbf16) reinterpret_cast<__nv_bfloat16*>(fb)[foff + jx] = __float2bfloat16_rn(fvv);
+                    else reinterpret_cast<float*>(fb)[foff + (size_t)jx * fstride] = fvv;
+                  }
+                }
                 if (rend >= tile_end) carry_f[hh] = rend > tile_end ? fvv : 0.f;   // last slot of the tile
               }
             }
@@ -652,12 +662,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
           }
           if (valid && k == N - 1) {
             const float x = racc[3], y = racc[4], z = racc[5];
-            float* o3 = a.rgb_map + gray * 3;
-            o3[0] = -1.0f + 2.0f * racc[0]; o3[1] = -1.0f + 2.0f * racc[1]; o3[2] = -1.0f + 2.0f * racc[2];
-            float* x3 = a.xyz + gray * 3;
-            x3[0] = x; x3[1] = y; x3[2] = z;
-            a.mask[gray * 2 + 0] = wgt;
-            a.mask[gray * 2 + 1] = -sqrtf(x * x + y * y + z * z);
+            const int ndst = a.n_peers > 0 ? a.n_peers : 1;
+            const size_t gr = gray + (a.n_peers > 0 ? (size_t)a.gather_off * a.n_rays : 0);
+            for (int pr = 0; pr < ndst; ++pr) {
+              float* o3 = (a.n_peers > 0 ? a.peer_rgb[pr] : a.rgb_map) + gr * 3;
+              o3[0] = -1.0f + 2.0f * racc[0]; o3[1] = -1.0f + 2.0f * racc[1]; o3[2] = -1.0f + 2.0f * racc[2];
+              float* x3 = (a.n_peers > 0 ? a.peer_xyz[pr] : a.xyz) + gr * 3;
+              x3[0] = x; x3[1] = y; x3[2] = z;
+              float* m2 = (a.n_peers > 0 ? a.peer_mask[pr] : a.mask) + gr * 2;
+              m2[0] = wgt;
+              m2[1] = -sqrtf(x * x + y * y + z * z);
+            }
 #pragma unroll
             for (int jx = 0; jx < 6; ++jx) racc[jx] = 0.f;
           }

@@ -40,3 +40,62 @@ def allreduce_grads(tensors, group=None):
         t.copy_(flat[o:o + n].view_as(t))
         o += n
     return tensors
+
+
+class GatheredMaps:
+    """Peer-mapped (symmetric-memory) destination of the FUSED all-gather of rendered maps: `NerfBranch.render(..., gather=gm)`
+    makes the kernel's compositing epilogue store every finished ray straight into these tensors ON EVERY RANK (plain stores
+    into peer memory over NVLink / NVSwitch), so no collective runs after the kernel and no SM is taken from the render.
+
+    One process per GPU, equal shards: rank r's images land at [r * batch_per_rank, (r + 1) * batch_per_rank).  After the
+    launch, `barrier()` (cross-rank, on the current stream) makes every rank's stores visible before any rank reads; use two
+    instances alternately when the next step should render while the previous result is still being consumed.
+    Tensors (the full batch of all ranks): feature_map (B, 256, hw) bfloat16 [features='bf16'], float32 [features='nchw'] or
+    (B, hw, 256) float32 [features='nhwc']; rgb_map (B, hw, 3); mask (B, hw, 2); xyz (B, hw, 3)."""
+
+    def __init__(self, batch_per_rank: int, n_rays: int, features: str = "bf16", group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _abi
+        group = dist.group.WORLD if group is None else group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > _abi.MAX_PEERS:
+            raise ValueError(f"at most {_abi.MAX_PEERS} peers")
+        self.batch_per_rank, self.n_rays, self.features = batch_per_rank, n_rays, features
+        B = self.world * batch_per_rank
+        fdt = torch.bfloat16 if features == "bf16" else torch.float32
+        fshape = (B, n_rays, 256) if features == "nhwc" else (B, 256, n_rays)
+        spec = [("feature_map", fshape, fdt), ("rgb_map", (B, n_rays, 3), torch.float32), ("mask", (B, n_rays, 2), torch.float32),
+                ("xyz", (B, n_rays, 3), torch.float32)]
+        offs, total = {}, 0
+        for name, shape, dt in spec:
+            offs[name] = total
+            n = 1
+            for d in shape:
+                n *= d
+            total += (n * torch.empty((), dtype=dt).element_size() + 255) // 256 * 256
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self._arena = symm_mem.empty(total, dtype=torch.uint8, device=dev)
+        self._hdl = symm_mem.rendezvous(self._arena, group)
+        base = [int(p) for p in self._hdl.buffer_ptrs]
+        self._ptrs = {name: [b + offs[name] for b in base] for name, _, _ in spec}
+        for name, shape, dt in spec:
+            n = 1
+            for d in shape:
+                n *= d
+            nbytes = n * torch.empty((), dtype=dt).element_size()
+            setattr(self, name, self._arena[offs[name]: offs[name] + nbytes].view(dt).view(shape))
+        self.layout = {"nhwc": _abi.FEAT_NHWC, "nchw": _abi.FEAT_NCHW, "bf16": _abi.FEAT_NCHW_BF16}[features]
+
+    def struct(self):
+        from . import _abi
+        g = _abi.GatherOut()
+        g.n_peers, g.image_offset = self.world, self.rank * self.batch_per_rank
+        for name in ("feature_map", "rgb_map", "mask", "xyz"):
+            arr = getattr(g, name)
+            for i, p in enumerate(self._ptrs[name]):
+                arr[i] = p
+        return g
+
+    def barrier(self):
+        """Cross-rank barrier on the current CUDA stream: all ranks' stores into this rank's tensors are complete after it."""
+        self._hdl.barrier()

@@ -260,7 +260,7 @@ class NerfBranch(nn.Module):
         P.abi_version = _abi.ABI_VERSION
         P.mode = self._mode(N)
         P.input_kind = kind
-        P.feat_layout = _abi.FEAT_NCHW if nchw else _abi.FEAT_NHWC
+        P.feat_layout = int(nchw)                                  # _abi.FEAT_NHWC / FEAT_NCHW / FEAT_NCHW_BF16
         P.batch, P.n_rays, P.n_samples, P.D = b, n_rays, N, self.N_layers_renderer
         P.img_size, P.static_viewdirs = img_size, int(static_viewdirs)
         P.packed = self.packed_weights().data_ptr()
@@ -271,7 +271,7 @@ class NerfBranch(nn.Module):
             P.cam_poses, P.focal = a0.data_ptr(), a1.data_ptr()
             P.ray_offset = a2.data_ptr() if a2 is not None else None
 
-    def _launch_forward(self, kind, meta, styles, a0, a1, a2, a3, near, far, density_only=False):
+    def _launch_forward(self, kind, meta, styles, a0, a1, a2, a3, near, far, density_only=False, gather=None):
         lib = _abi.load()
         b, n_rays, N, img_size, static_viewdirs, nchw = meta
         dev = styles.device
@@ -283,9 +283,15 @@ class NerfBranch(nn.Module):
         if density_only:                                            # map pointers stay NULL: the kernel stops after the sdf head
             rgb_map = feat = mask = xyz = None
             P.sdf = sdf.data_ptr()
+        elif gather is not None:                                    # fused all-gather: the maps go to every peer's tensors
+            rgb_map = feat = mask = xyz = None
+            P.sdf = sdf.data_ptr()
+            gstruct = gather.struct()
+            P.gather = C.pointer(gstruct)
         else:
             rgb_map = torch.empty(b, n_rays, 3, **f)
-            feat = torch.empty((b, W, n_rays) if nchw else (b, n_rays, W), **f)
+            feat = torch.empty((b, W, n_rays) if nchw else (b, n_rays, W), device=dev,
+                               dtype=torch.bfloat16 if nchw == _abi.FEAT_NCHW_BF16 else torch.float32)
             mask = torch.empty(b, n_rays, 2, **f)
             xyz = torch.empty(b, n_rays, 3, **f)
             P.rgb_map, P.feature_map, P.sdf, P.mask, P.xyz = (t.data_ptr() for t in (rgb_map, feat, sdf, mask, xyz))
@@ -430,6 +436,8 @@ class NerfBranch(nn.Module):
             any(t.requires_grad for t in tensors) or any(p.requires_grad for p in self.parameters()))
         if not need_grad:
             return self._launch_forward(kind, meta, styles, a0, a1, a2, a3, near, far)
+        if meta[5] == _abi.FEAT_NCHW_BF16:
+            raise RuntimeError("features_nchw='bf16' is an inference-only hand-off (no backward): render under torch.no_grad()")
         params = [p for p in self._ordered_params()]
         return _NerfFn.apply(self, kind, meta, styles, a0, a1, a2, a3, near, far, *params)
 
@@ -465,10 +473,12 @@ class NerfBranch(nn.Module):
         return rgb_map, feat, sdf, mask, xyz, eik
 
     def render(self, cam_poses, focal, near, far, styles, img_size=64, N_samples=24, static_viewdirs=False,
-               perturb=False, ray_offset=None, features_nchw=False, density_only=False):
+               perturb=False, ray_offset=None, features_nchw=False, density_only=False, gather=None):
         """Fused fast path = Render.prepare_nerf_inputs (nerf_utils.py:172-218) + forward, rays generated
         in-kernel.  cam_poses (b,3,4), focal/near/far (b,1,1) or (b,).  Returns a dict of maps; `z_vals`
-        are the sample depths the kernel used.  `density_only=True` (no autograd) stops after the sdf head and returns
+        are the sample depths the kernel used.  `features_nchw`: False -> feature_map (b, hw, 256) as the reference's
+        renderer returns it; True -> (b, 256, hw), the layout the decoder consumes (model_v3.py:1014); "bf16" -> the same in
+        bfloat16 (inference only) -- each written directly by the kernel's compositing epilogue.  `density_only=True` (no autograd) stops after the sdf head and returns
         only `sdf` and `z_vals` -- the coarse pass of `render_hierarchical`."""
         b = cam_poses.shape[0]
         n_rays = img_size * img_size
@@ -476,7 +486,10 @@ class NerfBranch(nn.Module):
         if perturb and ray_offset is None:
             ray_offset = torch.rand(b, img_size, img_size, 1, device=cam_poses.device)   # nerf_utils.py:110
         ro = None if ray_offset is None else c(ray_offset, b, n_rays)
-        meta = (b, n_rays, N_samples, img_size, bool(static_viewdirs), bool(features_nchw))
+        if features_nchw == "bf16" and self._mode(N_samples) != _abi.MODE_BF16:
+            raise ValueError("features_nchw='bf16' needs precision='bf16' and N_samples >= 8 (it comes from the tensor-core kernels)")
+        layout = _abi.FEAT_NCHW_BF16 if features_nchw == "bf16" else (_abi.FEAT_NCHW if features_nchw else _abi.FEAT_NHWC)
+        meta = (b, n_rays, N_samples, img_size, bool(static_viewdirs), layout)
         args = (_abi.INPUT_POSES, meta, c(styles, b, self.N_layers_renderer + 1, W), c(cam_poses, b, 3, 4), c(focal, b),
                 ro, None, c(near, b), c(far, b))
         if density_only:
@@ -485,6 +498,18 @@ class NerfBranch(nn.Module):
             with torch.no_grad():
                 out = self._launch_forward(*args, density_only=True)
             return dict(sdf=out[2], z_vals=out[5])
+        if gather is not None:
+            # multi-GPU serving: `gather` is a dist.GatheredMaps -- the kernel writes rgb_map / feature_map / mask / xyz of this
+            # rank's images into the gathered tensors of EVERY rank (peer memory); inference only, bf16 mode.  The caller runs
+            # gather.barrier() before reading gather.feature_map etc.
+            if any(t.device.type != "cuda" for t in (styles, cam_poses)):
+                raise RuntimeError("NerfBranch needs CUDA tensors: there is no CPU fallback")
+            if b != gather.batch_per_rank or n_rays != gather.n_rays:
+                raise ValueError("gather buffers were sized for another batch / image size")
+            meta = meta[:5] + (gather.layout,)
+            with torch.no_grad():
+                out = self._launch_forward(args[0], meta, *args[2:], gather=gather)
+            return dict(sdf=out[2], z_vals=out[5], gathered=gather)
         rgb_map, feat, sdf, mask, xyz, z = self._run(*args)
         return dict(rgb_map=rgb_map, feature_map=feat, sdf=sdf, mask=mask, xyz=xyz, z_vals=z)
 

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define C3D_ABI_VERSION 9
+#define C3D_ABI_VERSION 10
 #define C3D_MAX_LAYERS 16
 #define C3D_W 256
 
@@ -43,7 +43,10 @@ typedef struct CUstream_st* c3d_stream_t; /* == cudaStream_t */
 enum { C3D_OK = 0, C3D_ERR_ARG = -1, C3D_ERR_CUDA = -2, C3D_ERR_UNSUPPORTED = -3 };
 enum { C3D_MODE_FP32 = 0, C3D_MODE_BF16 = 1 };          /* arithmetic of the point MLP */
 enum { C3D_INPUT_POSES = 0, C3D_INPUT_POINTS = 1 };
-enum { C3D_FEAT_NHWC = 0, C3D_FEAT_NCHW = 1 };          /* feature_map (b,hw,256) or (b,256,hw) */
+/* feature_map layout: (b,hw,256) fp32 as the reference's renderer returns it; (b,256,hw) fp32 as the decoder consumes it
+ * (model_v3.py:1014); (b,256,hw) bf16 -- the same hand-off at half the bytes (inference only: MODE_BF16, no backward).  The
+ * tensor-core kernels write any of them straight from the compositing epilogue. */
+enum { C3D_FEAT_NHWC = 0, C3D_FEAT_NCHW = 1, C3D_FEAT_NCHW_BF16 = 2 };
 
 /* Reference state_dict tensors (names: SURVEY.md 3.4), fp32, contiguous, row-major (out,in). */
 typedef struct c3d_raw_params {
@@ -90,6 +93,24 @@ typedef struct c3d_param_grads {
   float* sigmoid_beta;
 } c3d_param_grads;
 
+/* Fused all-gather of the rendered maps (multi-GPU serving: every rank ends up with every rank's maps; what the reference
+ * does with torch.distributed around its generator, scripts/gen_images.py:57-91, train_v10.py evaluation).  Instead of a
+ * collective after the kernel, the compositing epilogue of the bf16 forward kernel stores every finished ray straight into
+ * the GATHERED tensors of all peers -- pointers into peer memory mapped over NVLink / NVSwitch (CUDA IPC, symmetric
+ * memory; this rank included) -- so the transfer rides under the render and needs no SMs of its own.  The caller owns
+ * the buffers, places them identically on every rank, and synchronises the ranks (a barrier after the launch has
+ * completed) before any rank reads.  Layouts / dtypes as c3d_fwd_params (feature_map per feat_layout), leading dimension
+ * = all images of all ranks; this call's first image lands at index image_offset. */
+#define C3D_MAX_PEERS 16
+typedef struct c3d_gather_out {
+  int32_t n_peers;                       /* destinations, 1..C3D_MAX_PEERS (this rank is one of them) */
+  int32_t image_offset;                  /* index of this call's image 0 in the gathered tensors */
+  void* feature_map[C3D_MAX_PEERS];      /* per destination: base of the gathered feature tensor */
+  float* rgb_map[C3D_MAX_PEERS];
+  float* mask[C3D_MAX_PEERS];
+  float* xyz[C3D_MAX_PEERS];
+} c3d_gather_out;
+
 typedef struct c3d_fwd_params {
   int32_t abi_version;       /* C3D_ABI_VERSION */
   int32_t mode;              /* C3D_MODE_* */
@@ -124,6 +145,9 @@ typedef struct c3d_fwd_params {
   float* z_vals_out;         /* optional (POSES): (batch,n_rays,N) sample depths, or NULL */
   void* workspace;           /* >= c3d_workspace_bytes() */
   size_t workspace_bytes;
+  const c3d_gather_out* gather;  /* NULL, or (MODE_BF16, n_samples >= 8, no density-only pass): rgb_map / feature_map / mask / xyz
+                                  * go to the gathered tensors of every peer INSTEAD of the four pointers above (which may
+                                  * then be NULL; sdf and z_vals_out stay local) */
 } c3d_fwd_params;
 
 /* Cotangents in, gradients out. Any gradient pointer may be NULL (not computed). */

@@ -43,7 +43,8 @@ def test_struct_sizes_match_header(lib):
     import cips3dpp_b200 as c3d
     a = c3d._abi
     assert ctypes.sizeof(a.RawParams) == 8 + 6 * 16 * 8 + 11 * 8
-    assert ctypes.sizeof(a.FwdParams) == 10 * 4 + 18 * 8 + 8
+    assert ctypes.sizeof(a.FwdParams) == 10 * 4 + 18 * 8 + 8 + 8
+    assert ctypes.sizeof(a.GatherOut) == 8 + 4 * 16 * 8
     assert ctypes.sizeof(a.BwdParams) == ctypes.sizeof(a.FwdParams) + 12 * 8 + 8
     assert ctypes.sizeof(a.ParamGrads) == ctypes.sizeof(a.RawParams) - 8
     assert ctypes.sizeof(a.RaygenParams) == 4 * 4 + 9 * 8

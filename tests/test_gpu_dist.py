@@ -26,3 +26,7 @@ def test_gather_maps_and_grad_allreduce_nccl_world2():
     # summed partial losses and the shared latent follow the single-process run (north star: loss curves within 1 %)
     assert line["inv_loss_rel"] < 1e-2 and line["inv_w_rel"] < 2e-2
     assert line["last_loss"] < line["first_loss"]
+    # fused all-gather: the kernel stored every rank's maps into every rank's gathered tensors (peer memory over NVLink) --
+    # bit-identical to rendering all images on one GPU, with no collective launched
+    assert "fused_error" not in line, line.get("fused_error")
+    assert line["fused_all_ranks_ok"] and line["fused_feat_equal"] and line["fused_rgb_equal"] and line["fused_xyz_equal"]

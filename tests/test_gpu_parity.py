@@ -259,6 +259,13 @@ def test_channel_major_features_come_from_the_kernel(case, img_size, fwd):
     assert b["feature_map"].shape == (a["feature_map"].shape[0], 256, img_size * img_size)
     assert torch.equal(a["feature_map"].transpose(1, 2), b["feature_map"])
     assert torch.equal(a["rgb_map"], b["rgb_map"]) and la == lb
+    # the same hand-off in bfloat16 (half the bytes for the decoder / the all-gather): the fp32 value rounded to nearest
+    with torch.no_grad():
+        h = m.render(*args, features_nchw="bf16", **kw)
+    assert h["feature_map"].dtype == torch.bfloat16 and m.last_launch_count == la
+    assert torch.equal(h["feature_map"], b["feature_map"].to(torch.bfloat16))
+    with pytest.raises(RuntimeError):                                   # inference-only layout
+        m.render(args[0], args[1], args[2], args[3], args[4].clone().requires_grad_(True), features_nchw="bf16", **kw)
 
 
 def test_render_nchw_and_perturb_consistency():
