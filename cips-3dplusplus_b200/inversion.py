@@ -77,26 +77,36 @@ def thumb_mse(thumb, target):
 
 class FlipInversion:
     def __init__(self, renderer, img_size=64, N_samples=24, cam_cfg=None, lr_latent=0.02, lr_cam=0.01, num_steps=200,
-                 loss_fn=thumb_mse, clip=10.0, shared_latent=False, static_viewdirs=True, fused_update=True):
+                 loss_fn=thumb_mse, clip=10.0, shared_latent=False, static_viewdirs=True, fused_update=True,
+                 loss_on_features=False):
         self.renderer, self.img_size, self.N = renderer, img_size, N_samples
         self.cam_cfg = dict(fov_ang=6, dist_radius=0.12) if cam_cfg is None else dict(cam_cfg)
         self.lr_latent, self.lr_cam, self.num_steps = lr_latent, lr_cam, num_steps
         self.loss_fn, self.clip, self.shared_latent, self.static_viewdirs = loss_fn, clip, shared_latent, static_viewdirs
+        # the reference's loss sees the thumb AND the decoder's image, i.e. the 256-channel feature map (projector_v9.py:230-246,
+        # renderer_detach=False): with loss_on_features the loss is called as loss_fn(thumbs, targets, features) with features
+        # (n*2, 256, S, S) -- the decoder / VGG stay the caller's -- and its cotangent flows back through feature_map
+        self.loss_on_features = loss_on_features
         # clipping + both Adam updates as one kernel (CUDA tensors); False (or C3D_INV_FUSED=0, for A/B runs): torch.optim
         self.fused_update = fused_update and os.environ.get("C3D_INV_FUSED", "1") != "0"
         # stage 1 optimises latents and cameras only: with a frozen renderer the packed weights are built once
         if hasattr(renderer, "cache_packed") and not any(p.requires_grad for p in renderer.parameters()):
             renderer.cache_packed = True
 
-    def render_thumbs(self, w, azim, elev):
-        """w (n, D+1, 256); azim, elev (n, 2, 1) -> thumbs (n*2, 3, S, S), differentiable."""
+    def render_maps(self, w, azim, elev, features=False):
+        """w (n, D+1, 256); azim, elev (n, 2, 1) -> thumbs (n*2, 3, S, S) [and features (n*2, 256, S, S)], differentiable."""
         n, S = w.shape[0], self.img_size
         loc = torch.cat([azim.reshape(-1, 1), elev.reshape(-1, 1)], 1)
         pose, focal, near, far, _ = Camera.generate_camera_params(S, w.device, locations=loc, **self.cam_cfg)
         styles = w.repeat_interleave(2, dim=0)                        # image and flip share the latent
+        kw = dict(features_nchw=True) if features else {}
         out = self.renderer.render(pose, focal, near, far, styles, img_size=S, N_samples=self.N,
-                                   static_viewdirs=self.static_viewdirs)
-        return out["rgb_map"].reshape(n * 2, S, S, 3).permute(0, 3, 1, 2)
+                                   static_viewdirs=self.static_viewdirs, **kw)
+        thumbs = out["rgb_map"].reshape(n * 2, S, S, 3).permute(0, 3, 1, 2)
+        return (thumbs, out["feature_map"].reshape(n * 2, -1, S, S)) if features else thumbs
+
+    def render_thumbs(self, w, azim, elev):
+        return self.render_maps(w, azim, elev)
 
     def run(self, targets, w_init, azim_init=None, elev_init=None, callback=None, cuda_graph=False, host_targets=None):
         """targets (n, 3, S, S) in [-1, 1]; w_init (1 or n, D+1, 256).  Returns dict(w, azim, elev, losses, events); `events` is a
@@ -137,8 +147,12 @@ class FlipInversion:
                                 for s in range(self.num_steps)], dtype=torch.float32).to(dev)
 
         def one_step():
-            thumbs = self.render_thumbs(w.expand(n, -1, -1) if self.shared_latent else w, azim, elev)
-            loss = self.loss_fn(thumbs, tgt)
+            wn = w.expand(n, -1, -1) if self.shared_latent else w
+            if self.loss_on_features:
+                thumbs, feats = self.render_maps(wn, azim, elev, features=True)
+                loss = self.loss_fn(thumbs, tgt, feats)
+            else:
+                loss = self.loss_fn(self.render_maps(wn, azim, elev), tgt)
             w.grad = azim.grad = elev.grad = None
             loss.backward()
             if multi_rank:
