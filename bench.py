@@ -630,44 +630,64 @@ def main():
         ms_comm = maxr(comm_loop(args.steps))
         ms_serial = maxr(comm_loop(args.steps, overlap=False))
         del full_feat, full_small
-        # The product path: the FUSED all-gather -- the kernel's compositing epilogue stores the maps straight into the gathered
-        # tensors of every rank (symmetric memory: peer addresses over NVLink / NVSwitch), then one cross-rank barrier per
-        # step.  No collective kernel, no SMs taken from the render.  Two buffer sets alternate (a consumer may still read
-        # the previous step's maps).
-        ms_fused, fused_err = None, None
+        # Without a collective kernel: dist.GatheredMaps (symmetric memory: every rank's gathered tensors mapped into every
+        # process over NVLink / NVSwitch).  (a) "p2p": after the render, peer-to-peer copies of the rank's shard into every
+        # rank's tensors on a communication stream -- DMA engines, no SMs, so they run under the next step's persistent
+        # kernel; one cross-rank barrier per step.  (b) "fused": the kernel's compositing epilogue stores the maps into every
+        # rank's tensors itself.  Two buffer sets alternate (a consumer may still read the previous step's maps).
+        ms_fused = ms_p2p = None
+        sym_err = None
         try:
             gms = [c3d.dist.GatheredMaps(B, IMG * IMG, features="bf16") for _ in range(2)]
 
-            def fused_loop(steps):
+            def sym_loop(steps, fused):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 barrier()
                 e0.record(stream)
                 for i in range(steps):
                     flush.fill_(1)
-                    m.render(devt[0], devt[1], devt[2], devt[3], devt[4], img_size=IMG, N_samples=N, gather=gms[i & 1])
-                    gms[i & 1].barrier()
+                    gm = gms[i & 1]
+                    if fused:
+                        m.render(devt[0], devt[1], devt[2], devt[3], devt[4], img_size=IMG, N_samples=N, gather=gm)
+                        gm.barrier()
+                    else:
+                        out = m.render(devt[0], devt[1], devt[2], devt[3], devt[4], img_size=IMG, N_samples=N, features_nchw="bf16")
+                        done = torch.cuda.Event()
+                        done.record(stream)
+                        comm_stream.wait_event(done)
+                        for k in ("feature_map", "rgb_map", "mask", "xyz"):
+                            out[k].record_stream(comm_stream)
+                        gm.push(out, comm_stream)
+                        with torch.cuda.stream(comm_stream):
+                            gm.barrier()
+                stream.wait_stream(comm_stream)
                 e1.record(stream)
                 barrier()
                 return e0.elapsed_time(e1) / steps
-            fused_loop(3)
-            ms_fused = maxr(fused_loop(args.steps))
+            sym_loop(3, False)
+            ms_p2p = maxr(sym_loop(args.steps, False))
+            sym_loop(3, True)
+            ms_fused = maxr(sym_loop(args.steps, True))
         except Exception as ex:  # noqa: BLE001  (no symmetric memory on this box: the NCCL path is the fallback measurement)
-            fused_err = f"{type(ex).__name__}: {ex}"[:200]
+            sym_err = f"{type(ex).__name__}: {ex}"[:200]
         gbytes = (world * B) * (256 * IMG * IMG * 2 + IMG * IMG * 8 * 4)
         base = maxr(ms_step)
         comm = {"what": "every rank ends up with every rank's maps: bf16 (b,256,hw) feature maps + fp32 rgb/mask/xyz, every step",
                 "gathered_bytes_per_rank_per_step": int(gbytes), "ms_per_step_no_comm": base,
-                "fused": {"how": "epilogue stores into peer memory (symmetric memory over NVLink) + one cross-rank barrier per step",
-                          "ms_per_step": ms_fused, "exposed_ms": None if ms_fused is None else ms_fused - base, "error": fused_err},
+                "p2p": {"how": "peer-to-peer copies (DMA engines) of the rank's shard into every rank's symmetric-memory tensors on a "
+                               "communication stream under the next step's render + one cross-rank barrier per step",
+                        "ms_per_step": ms_p2p, "exposed_ms": None if ms_p2p is None else ms_p2p - base, "error": sym_err},
+                "fused": {"how": "the kernel's epilogue stores into every rank's tensors (peer memory) + one cross-rank barrier per step",
+                          "ms_per_step": ms_fused, "exposed_ms": None if ms_fused is None else ms_fused - base},
                 "nccl": {"how": "all_gather_into_tensor on a communication stream under the next step's render",
                          "ms_per_step": ms_comm, "exposed_ms": ms_comm - base, "ms_per_step_not_overlapped": ms_serial,
                          "gather_ms_alone": ms_serial - base, "algbw_GBps_alone": gbytes / max(ms_serial - base, 1e-6) / 1e6},
-                "headline_uses": "fused" if ms_fused is not None else "nccl"}
+                "headline_uses": min((v, k) for k, v in (("p2p", ms_p2p), ("fused", ms_fused), ("nccl", ms_comm)) if v is not None)[1]}
 
     ms_step, ms_e2e, ms_sp_m, ms_e2e_serial = maxr(ms_step), maxr(ms_e2e), maxr(ms_sp), maxr(ms_e2e_serial)
     ms_kernel_step = ms_step
     if comm is not None:                                      # the headline at N > 1 includes the gather of the maps
-        ms_step = comm["fused"]["ms_per_step"] if comm["fused"]["ms_per_step"] is not None else comm["nccl"]["ms_per_step"]
+        ms_step = comm[comm["headline_uses"]]["ms_per_step"]
     extras = {}
     if world == 1 and not args.no_extras:
         extras = side_measurements(m, params, devt, D, N, dev, timed)

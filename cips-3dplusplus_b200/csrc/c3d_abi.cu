@@ -98,8 +98,10 @@ static bool fwd_uses_pair(const c3d_fwd_params* p) {
   return options().fwd_pair && p->mode == C3D_MODE_BF16 && p->n_samples >= fused::MIN_SAMPLES;
 }
 
+constexpr int PAIR_MAX_GRID = 160;          // CTAs of the persistent CTA-pair kernel (one per SM: 148 on B200)
+constexpr int PAIR_MAX_UNIT_RAYS = 128;     // a unit holds at most 128 / gcd(N, 128) <= 128 rays once a batch shrinks it (forward_pair)
 struct FwdWs {
-  size_t film, first, view, wimg, kimg, chunk, total;
+  size_t film, first, view, wimg, kimg, scratch, chunk, total;
   int chunk_imgs;
   size_t c_feat, c_rgb, c_pts, c_rd, c_vd, c_z;   // offsets inside the fp32 chunk area
 };
@@ -110,10 +112,13 @@ static FwdWs fwd_ws(const c3d_fwd_params* p) {
   w.film = o;  o += align_up(b * (p->D + 1) * W * sizeof(float2), 256);
   w.first = o; o += align_up(b * W * sizeof(float4), 256);
   w.view = o;  o += align_up(b * W * sizeof(float4), 256);
-  w.wimg = w.kimg = 0;
+  w.wimg = w.kimg = w.scratch = 0;
   if (fwd_uses_pair(p)) {
     w.wimg = o; o += align_up(b * p->D * pairk::WIMG_LAYER_BYTES, 1024);
     w.kimg = o; o += align_up(b * (p->D + 1) * pairk::KIMG_LAYER_BYTES, 1024);
+    // channel-major feature_map: per slot one unit of rays in (ray, channel) order, transposed when the unit is complete
+    w.scratch = o;
+    if (p->feat_layout != C3D_FEAT_NHWC) o += align_up((size_t)2 * PAIR_MAX_GRID * PAIR_MAX_UNIT_RAYS * W * sizeof(float), 1024);
   }
   w.chunk = o;
   w.chunk_imgs = 0;
@@ -297,6 +302,8 @@ static int forward_pair(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
   a.unit_rays = ur;
   a.units_per_img = (p->n_rays + 2 * ur - 1) / (2 * ur);
   a.wimg = ws + w.wimg; a.kimg = ws + w.kimg;
+  a.feat_scratch = reinterpret_cast<float*>(ws + w.scratch);
+  C3D_CHECK_ARG(ur <= PAIR_MAX_UNIT_RAYS, "unit of %d rays exceeds the scratch layout", ur);
   film_weights_kernel<<<dim3(8, p->D, p->batch), 256, 0, st>>>(a.blob, a.L, a.film, ws + w.wimg);
   C3D_LAUNCH_CHECK();
   film_k16_kernel<<<dim3(p->D + 1, p->batch), 256, 0, st>>>(a.blob, a.L, a.film, ws + w.kimg);
@@ -305,6 +312,7 @@ static int forward_pair(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
   int grid = nsm & ~1;
   if ((long long)grid > ((total_pu + 1) & ~1ll)) grid = (int)((total_pu + 1) & ~1ll);
   if (options().grid > 0) grid = (options().grid + 1) & ~1;
+  if (grid > PAIR_MAX_GRID) grid = PAIR_MAX_GRID;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(pairk::NTHREADS); cfg.dynamicSmemBytes = pairk::SMEM_BYTES; cfg.stream = st;

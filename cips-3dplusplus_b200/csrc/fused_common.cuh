@@ -26,6 +26,7 @@ struct Args {
   // fused all-gather (c3d_gather_out): the maps of image `img` go to image `gather_off + img` of every peer's gathered tensors
   // (peer memory mapped over NVLink); n_peers == 0: the four pointers above
   int n_peers, gather_off;
+  float* feat_scratch;   // CTA-pair kernel, channel-major feature_map: [2 * grid slots][unit_rays][256] fp32, L2-resident
   void* peer_feat[C3D_MAX_PEERS]; float* peer_rgb[C3D_MAX_PEERS]; float* peer_mask[C3D_MAX_PEERS]; float* peer_xyz[C3D_MAX_PEERS];
   int sdf_only;  // density-only pass (coarse pass of the two-pass render): the tile ends after the sdf head -- no view layer,
                  // no rgb head, no compositing; only `sdf` (and `z_vals_out`) are written

@@ -401,6 +401,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
     float* sdfS = reinterpret_cast<float*>(smem + SM_SDFP) + s * TILE;
     float* rayacc = reinterpret_cast<float*>(smem + SM_RAYACC) + s * RAYS * 2 * 8;
     float* raypart = reinterpret_cast<float*>(smem + SM_PART) + s * RAYS * 4 * 8;
+    float* scratch = a.feat_scratch + (size_t)(2 * blockIdx.x + s) * a.unit_rays * W;   // channel-major outputs: this slot's unit
     const uint32_t tacc = tmem_base + (uint32_t)s * 256u + ((uint32_t)(quad * 32) << 16);
     const float* scal = reinterpret_cast<const float*>(a.blob + a.L.scal);
     const float bsig = scal[0], brgb0 = scal[1], brgb1 = scal[2], brgb2 = scal[3];
@@ -597,13 +598,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
             // thread = channel t + 128 hh, fv[jx] = ray slot jx.  (b, hw, 256): a warp writes 32 consecutive channels of a
             // ray (128 B); (b, 256, hw): a thread writes up to 16 consecutive rays of its channel (64 B)
             const int ray0 = min(r0 + rl0, a.n_rays - 1), ch = t + TILE * hh;
-            // destination(s): this rank's feature_map, or -- fused all-gather -- image gather_off + img of every peer's gathered
-            // tensor (peer memory over NVLink; plain stores, visible to the peers once the kernel has completed)
-            const int ndst = a.n_peers > 0 ? a.n_peers : 1;
+            // (b, hw, 256): straight to the destination(s) -- this rank's feature_map or, fused all-gather, every peer's gathered
+            // tensor.  Channel-major layouts: into this slot's L2-resident scratch [unit ray][channel] first; the unit is
+            // transposed with 16-byte stores when its last tile is done (below).  Either way a warp writes 32 consecutive
+            // channels of a ray (128 B).
+            const int ndst = (a.n_peers > 0 && !a.feat_nchw) ? a.n_peers : 1;
             const size_t gimg = (size_t)(a.n_peers > 0 ? a.gather_off : 0) + img;
-            const size_t foff = a.feat_nchw ? (gimg * W + ch) * a.n_rays + ray0 : (gimg * a.n_rays + ray0) * W + ch;
-            const size_t fstride = a.feat_nchw ? 1 : W;
-            const bool fbf16 = a.feat_nchw == 2;          // (b, 256, hw) bf16: the decoder hand-off at half the bytes
+            const size_t foff = a.feat_nchw ? (size_t)rl0 * W + ch : (gimg * a.n_rays + ray0) * W + ch;
 #pragma unroll
             for (int jx = 0; jx < RAYS; ++jx) {
               const int rbeg = (rl0 + jx) * N, rend = rbeg + N;      // point range of ray slot jx inside the unit
@@ -612,14 +613,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
                 if (jx == 0) fvv += carry_f[hh];
                 if (rend <= tile_end) {                               // ray complete
                   for (int pr = 0; pr < ndst; ++pr) {
-                    void* fb = a.n_peers > 0 ? a.peer_feat[pr] : (void*)a.feature_map;
-                    if (fbf16) reinterpret_cast<__nv_bfloat16*>(fb)[foff + jx] = __float2bfloat16_rn(fvv);
-                    else reinterpret_cast<float*>(fb)[foff + (size_t)jx * fstride] = fvv;
+                    float* fb = a.feat_nchw ? scratch : (a.n_peers > 0 ? reinterpret_cast<float*>(a.peer_feat[pr]) : a.feature_map);
+                    fb[foff + (size_t)jx * W] = fvv;
                   }
                 }
                 if (rend >= tile_end) carry_f[hh] = rend > tile_end ? fvv : 0.f;   // last slot of the tile
               }
             }
+          }
+          if (a.feat_nchw && tile == ntiles - 1) {
+            // ---- the unit's rays are complete: scratch [ray][channel] -> (b, 256, hw), thread = channel, 8 rays per 16-byte
+            // (bf16) / 2 x 16-byte (fp32) store; to every peer's gathered tensor when the all-gather is fused
+            __threadfence_block();
+            named_bar_sync(bar_id + 2u, 2 * TILE);
+            const int ndst = a.n_peers > 0 ? a.n_peers : 1;
+            const size_t gimg = (size_t)(a.n_peers > 0 ? a.gather_off : 0) + img;
+            const size_t obase = (gimg * W + te) * a.n_rays + r0;
+            const bool fbf16 = a.feat_nchw == 2;
+            const bool vec = ((a.n_rays | r0) & 7) == 0;            // 16-byte aligned runs of 8 rays
+            int ry = 0;
+            for (; vec && ry + 8 <= nr; ry += 8) {
+              float x[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] = __ldcg(scratch + (size_t)(ry + i) * W + te);
+              for (int pr = 0; pr < ndst; ++pr) {
+                void* fb = a.n_peers > 0 ? a.peer_feat[pr] : (void*)a.feature_map;
+                if (fbf16) {
+                  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(fb) + obase + ry) =
+                      make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+                } else {
+                  float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(fb) + obase + ry);
+                  o4[0] = make_float4(x[0], x[1], x[2], x[3]);
+                  o4[1] = make_float4(x[4], x[5], x[6], x[7]);
+                }
+              }
+            }
+            for (; ry < nr; ++ry) {                                  // ragged shapes: one ray at a time
+              const float x = __ldcg(scratch + (size_t)ry * W + te);
+              for (int pr = 0; pr < ndst; ++pr) {
+                void* fb = a.n_peers > 0 ? a.peer_feat[pr] : (void*)a.feature_map;
+                if (fbf16) reinterpret_cast<__nv_bfloat16*>(fb)[obase + ry] = __float2bfloat16_rn(x);
+                else reinterpret_cast<float*>(fb)[obase + ry] = x;
+              }
+            }
+            named_bar_sync(bar_id + 2u, 2 * TILE);                 // the scratch may be overwritten by the next unit
           }
           tmem_ld_wait();
           tc_fence_before();

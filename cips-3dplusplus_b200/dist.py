@@ -42,10 +42,23 @@ def allreduce_grads(tensors, group=None):
     return tensors
 
 
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 class GatheredMaps:
-    """Peer-mapped (symmetric-memory) destination of the FUSED all-gather of rendered maps: `NerfBranch.render(..., gather=gm)`
-    makes the kernel's compositing epilogue store every finished ray straight into these tensors ON EVERY RANK (plain stores
-    into peer memory over NVLink / NVSwitch), so no collective runs after the kernel and no SM is taken from the render.
+    """Peer-mapped (symmetric-memory) destination of the all-gather of rendered maps, filled over NVLink / NVSwitch without a
+    collective kernel.  Two ways to fill it:
+      * `push(maps, stream)`: peer-to-peer copies of this rank's shard into every rank's tensors (DMA engines; the way bench.py
+        gathers -- it overlaps with the next step's render, which leaves no SM for an NCCL kernel);
+      * `NerfBranch.render(..., gather=gm)`: FUSED -- the kernel's compositing epilogue stores every finished ray straight
+        into the tensors of every rank.  Bit-exact and launch-free, but the channel-major layout makes those stores 2-byte
+        scattered writes, which NVLink serves badly (measured 1.5x the render time at 2 GPUs): kept for the (b, hw, 256)
+        layout and small batches, not the default.
 
     One process per GPU, equal shards: rank r's images land at [r * batch_per_rank, (r + 1) * batch_per_rank).  After the
     launch, `barrier()` (cross-rank, on the current stream) makes every rank's stores visible before any rank reads; use two
@@ -78,13 +91,36 @@ class GatheredMaps:
         self._hdl = symm_mem.rendezvous(self._arena, group)
         base = [int(p) for p in self._hdl.buffer_ptrs]
         self._ptrs = {name: [b + offs[name] for b in base] for name, _, _ in spec}
+        self._elem_off = {}
         for name, shape, dt in spec:
             n = 1
             for d in shape:
                 n *= d
-            nbytes = n * torch.empty((), dtype=dt).element_size()
-            setattr(self, name, self._arena[offs[name]: offs[name] + nbytes].view(dt).view(shape))
+            esz = torch.empty((), dtype=dt).element_size()
+            self._elem_off[name] = offs[name] // esz                 # storage offset of the tensor in elements of its dtype
+            setattr(self, name, self._arena[offs[name]: offs[name] + n * esz].view(dt).view(shape))
         self.layout = {"nhwc": _abi.FEAT_NHWC, "nchw": _abi.FEAT_NCHW, "bf16": _abi.FEAT_NCHW_BF16}[features]
+
+    def push(self, maps, stream=None):
+        """Copy-engine all-gather: this rank's freshly rendered maps (dict with feature_map / rgb_map / mask / xyz, this rank's
+        images only) are copied into this rank's slot of EVERY rank's gathered tensors with peer-to-peer copies over NVLink
+        (cudaMemcpyAsync on mapped peer memory: DMA engines, no SMs -- so it runs under the next step's persistent render
+        kernel, which occupies every SM).  Enqueued on `stream` (default: current), which must already wait for the render."""
+        if not hasattr(self, "_peer_views"):
+            self._peer_views = []
+            for r in range(self.world):
+                views = {}
+                for name in ("feature_map", "rgb_map", "mask", "xyz"):
+                    t = getattr(self, name)
+                    views[name] = self._hdl.get_buffer(r, t.shape, t.dtype, self._elem_off[name])
+                self._peer_views.append(views)
+        s0 = self.rank * self.batch_per_rank
+        ctx = torch.cuda.stream(stream) if stream is not None else _NullCtx()
+        with ctx:
+            for k in range(self.world):
+                r = (self.rank + k) % self.world                      # start with the own copy, then ring order: spreads the links
+                for name in ("feature_map", "rgb_map", "mask", "xyz"):
+                    self._peer_views[r][name][s0: s0 + self.batch_per_rank].copy_(maps[name], non_blocking=True)
 
     def struct(self):
         from . import _abi

@@ -60,10 +60,19 @@ try:
                  fused_rgb_equal=bool(torch.equal(gm.rgb_map, full_f["rgb_map"])),
                  fused_mask_equal=bool(torch.equal(gm.mask, full_f["mask"])), fused_xyz_equal=bool(torch.equal(gm.xyz, full_f["xyz"])),
                  fused_launches=int(m.last_launch_count))
+    # the same tensors filled by peer-to-peer copies of the rank's shard (DMA engines)
+    gm2 = c3d.dist.GatheredMaps(Bf, 64 * 64, features="bf16")
+    with torch.no_grad():
+        mine_f = m.render(pose_f[sl], focal_f[sl], near_f[sl], far_f[sl], styles_f[sl], img_size=64, N_samples=24, features_nchw="bf16")
+    gm2.push(mine_f)
+    gm2.barrier()
+    torch.cuda.synchronize()
+    fused["p2p_equal"] = bool(torch.equal(gm2.feature_map, full_f["feature_map"]) and torch.equal(gm2.rgb_map, full_f["rgb_map"])
+                              and torch.equal(gm2.mask, full_f["mask"]) and torch.equal(gm2.xyz, full_f["xyz"]))
     ok = torch.tensor([int(all(v for k, v in fused.items() if k.endswith("equal")))], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)                  # every rank must have received every rank's maps
     fused["fused_all_ranks_ok"] = bool(ok.item())
-    del gm
+    del gm, gm2
 except Exception as ex:  # noqa: BLE001  (symmetric memory unavailable on this box: reported, the NCCL path still covers the gather)
     fused = dict(fused_error=f"{type(ex).__name__}: {ex}"[:300])
 

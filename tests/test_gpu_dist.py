@@ -30,3 +30,4 @@ def test_gather_maps_and_grad_allreduce_nccl_world2():
     # bit-identical to rendering all images on one GPU, with no collective launched
     assert "fused_error" not in line, line.get("fused_error")
     assert line["fused_all_ranks_ok"] and line["fused_feat_equal"] and line["fused_rgb_equal"] and line["fused_xyz_equal"]
+    assert line["p2p_equal"]                        # the copy-engine gather (GatheredMaps.push) fills the same tensors
