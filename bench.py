@@ -174,6 +174,11 @@ def run_inversion(args, cfg, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     D, N, n_t = cfg["D"], cfg["N"], cfg["latents"]
+    # --shared-latent (BASELINE configs[4] as written): the 16 targets are SHARDED over the ranks (strong scaling), one latent
+    # is shared by all of them, and every step all-reduces its gradient over NCCL / NVLink (projector_v9.py:1050)
+    shared = bool(args.shared_latent) and world > 1
+    if shared:
+        n_t = max(1, n_t // world)
     m = c3d.NerfBranch(D, precision=args.precision)
     m.load_state_dict({k: torch.from_numpy(v) for k, v in O.init_params(D, seed=0).items()}, strict=True)
     m = m.to(dev).eval().requires_grad_(False)
@@ -182,7 +187,7 @@ def run_inversion(args, cfg, rank, world, local_rank):
     host_t = (torch.rand(n_t, 3, IMG, IMG, generator=g) * 2 - 1).pin_memory()
     tgt = host_t.to(dev)
     w0 = torch.zeros(1, D + 1, 256, device=dev)
-    inv = c3d.FlipInversion(m, img_size=IMG, N_samples=N, num_steps=max(args.warmup, 3))
+    inv = c3d.FlipInversion(m, img_size=IMG, N_samples=N, num_steps=max(args.warmup, 3), shared_latent=shared)
     inv.run(tgt, w0)                                                  # warm-up (eager), then the graph path once
     inv.run(tgt, w0, cuda_graph=True)
     wq = torch.zeros(n_t, D + 1, 256, device=dev, requires_grad=True)       # count this library's launches of one step
@@ -222,9 +227,11 @@ def run_inversion(args, cfg, rank, world, local_rank):
         print(json.dumps({
             "metric": "nerf_branch_rays_per_s", "value": world * rays / (ms_step * 1e-3), "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "scaling": "strong" if shared else "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "images_per_s": world * imgs / (ms_step * 1e-3),
-            "config": {"workload": cfg["desc"], "images_per_gpu": imgs, "rays_per_image": IMG * IMG, "samples_per_ray": N,
+            "config": {"workload": cfg["desc"], "images_per_gpu": imgs,
+                       "collective": "all-reduce (NCCL, captured in the step's CUDA graph) of the shared latent's gradient every step"
+                                     if shared else "none (each rank fits its own targets)", "rays_per_image": IMG * IMG, "samples_per_ray": N,
                        "layers": D, "step": "forward + backward (styles, cameras) + clipping + Adam, CUDA-graph replay",
                        "l2": "not flushed: the step's working set (saved tiles, 0.3 GB per image) is far larger than L2",
                        "final_loss": float(r["losses"][-1])},
@@ -459,6 +466,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the compositing-kernel and torch-on-GPU side lines")
+    ap.add_argument("--shared-latent", action="store_true", help="c5, N > 1: shard the 16 targets over the ranks (strong scaling), "
+                    "one latent shared by all, gradient all-reduce every step")
     ap.add_argument("--no-gather", action="store_true", help="N > 1: leave the all-gather of the rendered maps out of the timed region")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]

@@ -115,8 +115,8 @@ class FlipInversion:
 
         `cuda_graph=True` captures one whole optimisation step (camera glue, forward, loss, backward, clipping,
         both Adam updates) into a CUDA graph and replays it `num_steps` times; only the two learning rates are
-        written from the host between replays.  It needs frozen renderer weights, a capturable `loss_fn`, and is
-        refused together with a cross-rank shared latent (the all-reduce stays outside graphs).
+        written from the host between replays.  It needs frozen renderer weights and a capturable `loss_fn`; with a latent
+        shared across ranks the NCCL all-reduce of its gradient is captured in the graph too.
 
         `host_targets` (pinned host tensor shaped like `targets`) makes every step end to end: the step's targets are
         copied host -> device before it and its loss is copied back to (pinned) host memory after it -- asynchronously on
@@ -128,8 +128,8 @@ class FlipInversion:
         azim = (torch.zeros(n, 2, 1, device=dev) if azim_init is None else azim_init.detach().clone()).requires_grad_(True)
         elev = (torch.zeros(n, 2, 1, device=dev) if elev_init is None else elev_init.detach().clone()).requires_grad_(True)
         multi_rank = self.shared_latent and torch.distributed.is_available() and torch.distributed.is_initialized()
-        if cuda_graph and multi_rank:
-            raise ValueError("cuda_graph=True cannot be combined with a latent shared across ranks")
+        # with a latent shared across ranks the gradient all-reduce (NCCL) is part of the step; it is captured into the CUDA
+        # graph like every other launch of the step (every rank captures and replays the same sequence)
         fused = self.fused_update and dev.type == "cuda"
         device_lr = fused or cuda_graph                              # learning rates live on the device
         if fused:
