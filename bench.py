@@ -123,32 +123,103 @@ def cpu_baseline(cfg, n_images, reps=1, seeds=(1, 2), keep=None):
     if keep is not None:
         keep.update(rgb_map=outs[0], feature_map=outs[1], sdf=outs[2], mask=outs[3], xyz=outs[4], z_vals=z)
     t = min(times[1:])
-    return dict(value=n_images * IMG * IMG / t, unit="rays/s", cores=nthr, kind="port",
-                sample=f"{n_images} of {c2w.shape[0]} images of the step ({t:.2f} s, best of {reps})",
-                images_per_s=n_images / t, host_cpus=os.cpu_count()), t
+    out = dict(value=n_images * IMG * IMG / t, unit="rays/s", cores=nthr, kind="port",
+               sample=f"{n_images} of {c2w.shape[0]} images of the step ({t:.2f} s, best of {reps})",
+               images_per_s=n_images / t, host_cpus=os.cpu_count())
+    live = live_reference_cpu(cfg, params, c2w[:2], focal[:2], near[:2], far[:2], styles[:2], nthr)
+    if live is not None:
+        out["reference_torch"] = live
+    return out, t
+
+
+def live_reference_cpu(cfg, params, c2w, focal, near, far, styles, nthr):
+    """The LIVE reference beside the port: the unmodified `VolumeFeatureRenderer` + `Render.prepare_nerf_inputs` (PyTorch, CPU,
+    all host threads) on two images of the step.  Available where oracle/make_ref.sh has placed the reference modules."""
+    try:
+        import torch
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import ref_stubs
+        if not ref_stubs.available():
+            return None
+        model_v3, nerf_utils = ref_stubs.import_model_v3()
+        from exp.cips3d.volume_renderer import VolumeFeatureRenderer
+        torch.set_num_threads(nthr)
+        r = VolumeFeatureRenderer(N_layers_renderer=cfg["D"], input_dim=3, hidden_dim=256, style_dim=256, view_dim=3,
+                                  with_sdf=True, output_features=True).eval()
+        r.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+        t_ = lambda x: torch.from_numpy(np.ascontiguousarray(x))
+        times = []
+        with torch.no_grad():
+            for _ in range(2):
+                t0 = time.perf_counter()
+                pts, rays_d, viewdirs, z_vals = nerf_utils.Render.prepare_nerf_inputs(
+                    focal=t_(focal).view(-1, 1, 1), img_size=IMG, cam_poses=t_(c2w), near=t_(near).view(-1, 1, 1),
+                    far=t_(far).view(-1, 1, 1), N_samples=cfg["N"], perturb=False)
+                r(pts=pts, rays_d=rays_d, viewdirs=viewdirs, z_vals=z_vals, near=t_(near).view(-1, 1, 1), far=t_(far).view(-1, 1, 1),
+                  styles=t_(styles))
+                times.append(time.perf_counter() - t0)
+        t = min(times)
+        return dict(value=2 * IMG * IMG / t, unit="rays/s", images_per_s=2 / t, cores=nthr, kind="reference",
+                    sample=f"2 images through the unmodified PyTorch VolumeFeatureRenderer on the host cores ({t:.2f} s)")
+    except Exception as ex:  # noqa: BLE001  (the port's number stands on its own)
+        return dict(error=f"{type(ex).__name__}: {ex}"[:200])
 
 
 def run_reference(args, cfg, rank, world):
+    """The reference arm: the reference's own implementation of the path on the box's host cores, all threads, on a bounded
+    sample of the workload per step.  Where oracle/make_ref.sh has placed the reference modules (oracle/_ref) this is the
+    LIVE reference -- the unmodified PyTorch `VolumeFeatureRenderer` + `Render.prepare_nerf_inputs` (kind "reference");
+    otherwise the C / OpenMP port of the same algorithm, oracle/nerf_oracle.c (kind "port", roughly 2x faster than PyTorch)."""
     if rank != 0:
         return
-    n_img = max(1, min(cfg["latents"] * cfg["sweep"], 4))
-    cb, _ = cpu_baseline(cfg, n_img, reps=1)                        # sizes the sample
-    times = []
     from oracle import c_oracle, nerf_oracle as O
     c2w, focal, near, far, styles = workload(cfg)
     params = O.init_params(cfg["D"], seed=0)
-    packed = c_oracle.pack_params(params)
+    nthr = host_threads()
+    n_img = max(1, min(cfg["latents"] * cfg["sweep"], 4))
     sl = slice(0, n_img)
+    live = None
+    try:
+        import torch
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import ref_stubs
+        if ref_stubs.available():
+            model_v3, nerf_utils = ref_stubs.import_model_v3()
+            from exp.cips3d.volume_renderer import VolumeFeatureRenderer
+            torch.set_num_threads(nthr)
+            live = VolumeFeatureRenderer(N_layers_renderer=cfg["D"], input_dim=3, hidden_dim=256, style_dim=256, view_dim=3,
+                                         with_sdf=True, output_features=True).eval()
+            live.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+            t_ = lambda x: torch.from_numpy(np.ascontiguousarray(x))
+            tin = dict(focal=t_(focal[sl]).view(-1, 1, 1), cam_poses=t_(c2w[sl]), near=t_(near[sl]).view(-1, 1, 1),
+                       far=t_(far[sl]).view(-1, 1, 1), styles=t_(styles[sl]))
+    except Exception:  # noqa: BLE001
+        live = None
+    packed = c_oracle.pack_params(params)
+
+    def step():
+        if live is not None:
+            with torch.no_grad():
+                pts, rays_d, viewdirs, z_vals = nerf_utils.Render.prepare_nerf_inputs(
+                    focal=tin["focal"], img_size=IMG, cam_poses=tin["cam_poses"], near=tin["near"], far=tin["far"],
+                    N_samples=cfg["N"], perturb=False)
+                live(pts=pts, rays_d=rays_d, viewdirs=viewdirs, z_vals=z_vals, near=tin["near"], far=tin["far"], styles=tin["styles"])
+        else:
+            pts, rd, vd, z = c_oracle.prepare_inputs(c2w[sl], focal[sl], near[sl], far[sl], IMG, cfg["N"])
+            c_oracle.renderer_forward(params, pts, rd, vd, z, near[sl], far[sl], styles[sl], nthreads=nthr, packed=packed)
+    times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        pts, rd, vd, z = c_oracle.prepare_inputs(c2w[sl], focal[sl], near[sl], far[sl], IMG, cfg["N"])
-        c_oracle.renderer_forward(params, pts, rd, vd, z, near[sl], far[sl], styles[sl], nthreads=host_threads(),
-                                  packed=packed)
+        step()
         if i >= args.warmup:
             times.append(time.perf_counter() - t0)
     t = float(np.mean(times))
     v = n_img * IMG * IMG / t
-    cb.update(value=v, sample=f"each step = {n_img} of {c2w.shape[0]} images of the workload")
+    kind = "reference" if live is not None else "port"
+    what = ("the unmodified PyTorch VolumeFeatureRenderer + Render.prepare_nerf_inputs (oracle/_ref)" if live is not None
+            else "oracle/nerf_oracle.c (C / OpenMP port of the reference algorithm)")
+    cb = dict(value=v, unit="rays/s", cores=nthr, kind=kind, images_per_s=n_img / t, host_cpus=os.cpu_count(),
+              sample=f"each step = {n_img} of {c2w.shape[0]} images of the workload through {what}")
     print(json.dumps({
         "impl": "reference", "metric": "nerf_branch_rays_per_s", "value": v, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,

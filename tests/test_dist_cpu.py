@@ -66,7 +66,8 @@ def test_reference_arm_under_torchrun_env():
     assert r0.returncode == 0, r0.stderr
     line = json.loads([l for l in r0.stdout.splitlines() if l.startswith("{")][-1])
     assert line["impl"] == "reference" and line["metric"] == "nerf_branch_rays_per_s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # "reference" where the live reference modules are available (build container, oracle/_ref on the GPU box), else the port
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["n_gpus"] == 2
 
 
