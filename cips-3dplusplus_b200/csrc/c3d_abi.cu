@@ -262,7 +262,7 @@ static int fused_launch(const fused::Args& a, int kind, cudaStream_t st) {
   if (grid < 1) grid = 1;
   if (cluster == 2) grid = (grid + 1) & ~1;
   if (options().grid > 0) { grid = options().grid; if (cluster == 2) grid = (grid + 1) & ~1; }
-  const int egw = (kind == 0 && options().egw == 8) ? 8 : 4;   // epilogue warps per slot (tuning knob; 4 measured best)
+  const int egw = (kind == 0 && options().egw == 8) ? 8 : 4;   // forward: epilogue warps per slot (tuning knob; 4 measured best)
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);

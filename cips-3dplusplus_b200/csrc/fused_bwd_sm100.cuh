@@ -33,7 +33,10 @@ using fused::ACT_PBLOCK;
 using fused::tmem_ld_32x16;
 using fused::st_v4;
 
-constexpr int NTHREADS = 384;
+constexpr int EGW = 8;                                            // epilogue warps per slot: a thread owns ONE channel
+constexpr int EG_THREADS = EGW * 32;
+constexpr int NTHREADS = 128 + 2 * EG_THREADS;                    // 4 role warps + two epilogue groups
+constexpr int PF = 2;                    // iterations (of 16 points) whose saved-row loads are in flight per thread (1..4 measured)
 constexpr int STAGE_BYTES = 16384;
 constexpr int NSTAGE = 4;
 constexpr int RAYS = 16;
@@ -70,7 +73,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_backward_kernel(const Args 
 
   if (threadIdx.x == 32) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&misc->full[i], 1); mbar_init(&misc->empty[i], kCluster); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&misc->a_ready[i], TILE); mbar_init(&misc->acc_full[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&misc->a_ready[i], EG_THREADS); mbar_init(&misc->acc_full[i], 1); }
     fence_mbar_init();
   }
   if (warp == 2) { tmem_alloc(&misc->tmem_base, 512); tmem_relinquish(); }
@@ -193,19 +196,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_backward_kernel(const Args 
    }
   } else if (warp >= 4) {
     // ============================================================ epilogue groups
-    const int s = (warp - 4) >> 2;
-    const int t = threadIdx.x - 128 - s * TILE;
+    const int s = (warp - 4) / EGW;
+    const int te = threadIdx.x - 128 - s * EG_THREADS;      // 0 .. EG_THREADS-1
+    const int t = te & (TILE - 1);                          // point of the tile (point role: te < TILE) / channel inside a half
     const int quad = warp & 3;
+    const bool point_role = te < TILE;
+    const int h = te >> 7, ch = te;                         // my channel half / channel
     const int slot = 2 * blockIdx.x + s;
     const uint32_t aux_u32 = smem_u32(smem + SM_AUX + s * 4096);
     const uint32_t act_u32 = smem_u32(smem + SM_ACT + s * ACT_BYTES);
     const uint32_t tacc = tmem_base + (uint32_t)s * 256u + ((uint32_t)(quad * 32) << 16);
+    const uint32_t tcol = tacc + (uint32_t)h * 128u;
+    const uint32_t row_u32 = act_u32 + (uint32_t)ch * 128u;
     const int c7 = t & 7;
     uint32_t jobcnt = 0;
     const int total_units = a.batch * a.units_per_img;
     // cycle counters of one epilogue thread (build with -DC3D_KERNEL_PROF, run with C3D_DEBUG=2), as in the forward kernel
 #ifdef C3D_KERNEL_PROF
-    const bool eprof = (a.debug & 2) != 0 && blockIdx.x == 0 && t == 0;
+    const bool eprof = (a.debug & 2) != 0 && blockIdx.x == 0 && te == 0;
     long long e_setup = 0, e_wait = 0, e_epi = 0, e_other = 0, e_mark = clock64(), e_begin = e_mark;
     int e_tiles = 0;
 #define C3D_BPROF(acc) do { if (eprof) { const long long now_ = clock64(); acc += now_ - e_mark; e_mark = now_; } } while (0)
@@ -234,31 +242,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_backward_kernel(const Args 
         const size_t gpt = gray * N + k;
         // ---- job-0 operands: (a) d rgb / d sdf tile of my point, (b) Wgt row of my point, (c) gF^T rows of my channels
         {
-          const float wv = valid ? a.w_pt[gpt] : 0.f;
-          float e[8];
-#pragma unroll
-          for (int jx = 0; jx < 3; ++jx) {
-            const float gr = valid ? a.g_rgb_pt[gpt * 3 + jx] : 0.f;
-            const float hi = __bfloat162float(__float2bfloat16_rn(gr));
-            e[jx] = hi; e[3 + jx] = gr - hi;
-          }
-          const float gs = valid ? a.g_sdf_pt[gpt] : 0.f;
-          e[6] = __bfloat162float(__float2bfloat16_rn(gs)); e[7] = gs - e[6];
           const uint32_t row = (uint32_t)((t >> 3) * 256 + (t & 7) * 16);
-          st_v4(aux_u32 + row, pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
-          st_v4(aux_u32 + row + 128, 0u, 0u, 0u, 0u);
-          // Wgt[point][ray slot] (K-major k16 tile at G^T + 8192)
-          const int myslot = rl - rl0;
-          uint32_t wr[8];
+          if (point_role) {
+            const float wv = valid ? a.w_pt[gpt] : 0.f;
+            float e[8];
 #pragma unroll
-          for (int jx = 0; jx < 8; ++jx)
-            wr[jx] = pack_bf16x2(2 * jx == myslot ? wv : 0.f, 2 * jx + 1 == myslot ? wv : 0.f);
-          st_v4(act_u32 + 8192 + row, wr[0], wr[1], wr[2], wr[3]);
-          st_v4(act_u32 + 8192 + row + 128, wr[4], wr[5], wr[6], wr[7]);
-          // gF^T[channel][ray slot] for channels t and t+128 (k16 image at G^T + 0 / + 4096)
+            for (int jx = 0; jx < 3; ++jx) {
+              const float gr = valid ? a.g_rgb_pt[gpt * 3 + jx] : 0.f;
+              const float hi = __bfloat162float(__float2bfloat16_rn(gr));
+              e[jx] = hi; e[3 + jx] = gr - hi;
+            }
+            const float gs = valid ? a.g_sdf_pt[gpt] : 0.f;
+            e[6] = __bfloat162float(__float2bfloat16_rn(gs)); e[7] = gs - e[6];
+            st_v4(aux_u32 + row, pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+            st_v4(aux_u32 + row + 128, 0u, 0u, 0u, 0u);
+            // Wgt[point][ray slot] (K-major k16 tile at G^T + 8192)
+            const int myslot = rl - rl0;
+            uint32_t wr[8];
+#pragma unroll
+            for (int jx = 0; jx < 8; ++jx)
+              wr[jx] = pack_bf16x2(2 * jx == myslot ? wv : 0.f, 2 * jx + 1 == myslot ? wv : 0.f);
+            st_v4(act_u32 + 8192 + row, wr[0], wr[1], wr[2], wr[3]);
+            st_v4(act_u32 + 8192 + row + 128, wr[4], wr[5], wr[6], wr[7]);
+          }
+          // gF^T[channel][ray slot] for my channel(s) (k16 image at G^T + 0 / + 4096)
           const int tile_end = min((tile + 1) * TILE, npts);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          {
             uint32_t gw[8];
 #pragma unroll
             for (int jx = 0; jx < 8; ++jx) {
@@ -281,45 +290,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_backward_kernel(const Args 
         // ---- layers D .. 0: cotangent through sin/FiLM, column sums, G^T tile for the next MMA job
         for (int l = D; l >= 0; --l) {
           C3D_BPROF(e_other);
+          // my channel's saved fp16 accumulator rows of this layer: 16 point groups of 16 bytes.  They do not depend on the
+          // MMAs, so the first PF iterations' loads are in flight while the accumulator is still being produced.
+          const float scale = film_img[l * W + ch].x, shift = film_img[l * W + ch].y;
+          const uint4* pacc = reinterpret_cast<const uint4*>(a.save_acc + (((size_t)l * a.n_tiles_g + tile_g) * 16 * W + ch) * 8);
+          uint4 ac[PF + 1][2];
+#pragma unroll
+          for (int i = 0; i < PF; ++i) {
+            ac[i][0] = __ldcs(pacc + (size_t)(2 * i) * W);
+            ac[i][1] = __ldcs(pacc + (size_t)(2 * i + 1) * W);
+          }
           mbar_wait(&misc->acc_full[s], jobcnt & 1u);
           C3D_BPROF(e_wait);
           jobcnt++;
           tc_fence_after();
-#pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-            const int ch = t + TILE * h;
-            const float scale = film_img[l * W + ch].x, shift = film_img[l * W + ch].y;
-            const uint32_t tcol = tacc + (uint32_t)h * 128u;
-            const uint32_t row_u32 = act_u32 + (uint32_t)ch * 128u;
-            const size_t so = (((size_t)l * a.n_tiles_g + tile_g) * 16 * W + ch) * 8;
-            const uint4* pacc = reinterpret_cast<const uint4*>(a.save_acc + so);
-            float G1 = 0.f, G2 = 0.f;
+          {
+            // two points per operation (FFMA2 / FMUL2 / FADD2): the pass is bound by issue slots, not by a pipe
+            const float2 scale2 = make_float2(scale, scale), shift2 = make_float2(shift, shift);
+            float2 G1v = make_float2(0.f, 0.f), G2v = G1v;
             uint32_t v[16];
-#pragma unroll 2
+#pragma unroll
             for (int cp = 0; cp < 8; ++cp) {               // 16 points per iteration = 2 point groups
               tmem_ld_32x16(tcol + cp * 16, v);
-              uint4 ac[2];
-#pragma unroll
-              for (int g = 0; g < 2; ++g) ac[g] = __ldcs(pacc + (size_t)(cp * 2 + g) * W);
+              if (cp + PF < 8) {
+                ac[(cp + PF) % (PF + 1)][0] = __ldcs(pacc + (size_t)(2 * (cp + PF)) * W);
+                ac[(cp + PF) % (PF + 1)][1] = __ldcs(pacc + (size_t)(2 * (cp + PF) + 1) * W);
+              }
               tmem_ld_wait();
 #pragma unroll
               for (int g = 0; g < 2; ++g) {
-                const uint32_t aw[4] = {ac[g].x, ac[g].y, ac[g].z, ac[g].w};
-                float o[8];
+                const uint4 aq = ac[cp % (PF + 1)][g];
+                const uint32_t aw[4] = {aq.x, aq.y, aq.z, aq.w};
+                uint32_t o[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const float2 acc2 = __half22float2(*reinterpret_cast<const __half2*>(&aw[i]));     // saved fp16 accumulators
-                  const float ga0 = __uint_as_float(v[g * 8 + 2 * i]) * __cosf(fmaf(acc2.x, scale, shift));
-                  const float ga1 = __uint_as_float(v[g * 8 + 2 * i + 1]) * __cosf(fmaf(acc2.y, scale, shift));
-                  G2 += ga0 + ga1;
-                  G1 = fmaf(ga0, acc2.x, fmaf(ga1, acc2.y, G1));
-                  o[2 * i] = ga0 * scale; o[2 * i + 1] = ga1 * scale;
+                  const float2 arg = fma2(acc2, scale2, shift2);
+                  const float2 gh = make_float2(__uint_as_float(v[g * 8 + 2 * i]), __uint_as_float(v[g * 8 + 2 * i + 1]));
+                  const float2 ga = mul2(gh, make_float2(__cosf(arg.x), __cosf(arg.y)));
+                  G2v = add2(G2v, ga);
+                  G1v = fma2(ga, acc2, G1v);
+                  const float2 og = mul2(ga, scale2);
+                  o[i] = pack_bf16x2(og.x, og.y);
                 }
                 const int unit = (cp & 3) * 2 + g;            // 16-byte unit inside the 64-point block
-                st_v4(row_u32 + (uint32_t)(cp >> 2) * ACT_PBLOCK + (uint32_t)((unit ^ c7) << 4), pack_bf16x2(o[0], o[1]),
-                      pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+                st_v4(row_u32 + (uint32_t)(cp >> 2) * ACT_PBLOCK + (uint32_t)((unit ^ c7) << 4), o[0], o[1], o[2], o[3]);
               }
             }
+            const float G1 = G1v.x + G1v.y, G2 = G2v.x + G2v.y;
             atomicAdd(gfilm_img + ((size_t)l * W + ch) * 2 + 0, G1);
             atomicAdd(gfilm_img + ((size_t)l * W + ch) * 2 + 1, G2);
           }
@@ -333,10 +351,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_backward_kernel(const Args 
             jobcnt++;
             tc_fence_after();
             uint32_t v4[4];
-            tmem_ld_32x4(tacc + 4, v4);
-            tmem_ld_wait();
+            if (point_role) { tmem_ld_32x4(tacc + 4, v4); tmem_ld_wait(); }
             tc_fence_before();
-            if (valid && a.g_viewdirs) {
+            if (point_role && valid && a.g_viewdirs) {
 #pragma unroll
               for (int jx = 0; jx < 3; ++jx) atomicAdd(a.g_viewdirs + gray * 3 + jx, __uint_as_float(v4[jx]));
             }
@@ -349,10 +366,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_backward_kernel(const Args 
           jobcnt++;
           tc_fence_after();
           uint32_t v4[4];
-          tmem_ld_32x4(tacc, v4);
-          tmem_ld_wait();
+          if (point_role) { tmem_ld_32x4(tacc, v4); tmem_ld_wait(); }
           tc_fence_before();
-          if (valid) {
+          if (point_role && valid) {
             float* gp = a.g_pts + gpt * 3;
 #pragma unroll
             for (int jx = 0; jx < 3; ++jx) gp[jx] += nscale * __uint_as_float(v4[jx]);

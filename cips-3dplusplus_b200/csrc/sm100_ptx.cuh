@@ -269,6 +269,34 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 -- one issue slot for two operations)
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

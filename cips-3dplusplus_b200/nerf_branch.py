@@ -96,6 +96,7 @@ class _NerfFn(torch.autograd.Function):
         else:
             outs, ctx.saved_ws = module._launch_forward(kind, meta, styles, a0, a1, a2, a3, near, far), None
         ctx.module, ctx.kind, ctx.meta = module, kind, meta
+        ctx.set_materialize_grads(False)             # an output the loss never touched has no cotangent (not a tensor of zeros)
         ctx.save_for_backward(styles, a0, a1, a2 if a2 is not None else styles.new_empty(0),
                               a3 if a3 is not None else styles.new_empty(0), near, far)
         ctx.has = (a2 is not None, a3 is not None)
