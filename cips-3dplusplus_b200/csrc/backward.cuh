@@ -81,11 +81,11 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(CompositeBwdArgs p) 
   __syncwarp();
   // ---- gw_k = dL/dw_k : feature dot products with lanes over channels
   const int C4 = p.n_feat >> 2;
-  for (int k = 0; k < N; ++k) {
-    float acc = 0.f;
-    if (p.gdot) {
-      acc = p.gdot[ray * N + k];
-    } else if (p.g_feature_map && p.features) {
+  if (p.gdot || !(p.g_feature_map && p.features)) {          // precomputed (tensor-core path) or no cotangent on feature_map
+    for (int k = lane; k < N; k += 32) GW[k] = p.gdot ? p.gdot[ray * N + k] : 0.f;
+  } else {
+    for (int k = 0; k < N; ++k) {
+      float acc = 0.f;
       const float4* f = reinterpret_cast<const float4*>(p.features) + ((size_t)ray * N + k) * C4;
       const float4* g = reinterpret_cast<const float4*>(p.g_feature_map) + (size_t)ray * C4;
       for (int c = lane; c < C4; c += 32) {
@@ -94,8 +94,8 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(CompositeBwdArgs p) 
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) GW[k] = acc;
     }
-    if (lane == 0) GW[k] = acc;
   }
   __syncwarp();
   float g_dn = 0.f, g_b = 0.f;
