@@ -9,6 +9,7 @@
 #include "fused_common.cuh"
 #include "fused_bf16_sm100.cuh"
 #include "fused_pair_sm100.cuh"
+#include "mlp_tc32_sm100.cuh"
 #include "backward.cuh"
 #include "param_grads.cuh"
 #include "eikonal.cuh"
@@ -35,16 +36,18 @@ int fail(int code, const char* fmt, ...) {
 //   grid      0 (default: one CTA per SM) | CTAs of the persistent kernels
 //   egw       4 (default) | 8   single-CTA forward: epilogue warps per slot
 //   bwd       "tc" (default) | "simt"   force the FP32-pipe backward
+//   fp32      "tc" (default: fp32-mode MLP on the tensor cores, 3-way bf16 split, mlp_tc32_sm100.cuh) | "simt" (FP32 pipe)
 //   resample  "auto" (default) | "warp" | "lane";  resample_rb  rays per block of the warp kernel (0 = auto)
 //   debug     bit mask for builds with -DC3D_KERNEL_PROF (ignored by release builds)
 // ------------------------------------------------------------------------------------------
-struct Options { int fwd_pair, cluster, grid, egw, bwd_simt, resample, resample_rb, debug; };
+struct Options { int fwd_pair, cluster, grid, egw, bwd_simt, resample, resample_rb, debug, fp32_simt; };
 static int parse_option(Options& o, const char* key, const char* val) {
   if (!key || !val) return -1;
   if (!strcmp(key, "fwd")) { if (!strcmp(val, "pair")) o.fwd_pair = 1; else if (!strcmp(val, "v3")) o.fwd_pair = 0; else return -1; }
   else if (!strcmp(key, "cluster")) { const int v = atoi(val); if (v != 1 && v != 2) return -1; o.cluster = v; }
   else if (!strcmp(key, "grid")) { const int v = atoi(val); if (v < 0) return -1; o.grid = v; }
   else if (!strcmp(key, "egw")) { const int v = atoi(val); if (v != 4 && v != 8) return -1; o.egw = v; }
+  else if (!strcmp(key, "fp32")) { if (!strcmp(val, "simt")) o.fp32_simt = 1; else if (!strcmp(val, "tc")) o.fp32_simt = 0; else return -1; }
   else if (!strcmp(key, "bwd")) { if (!strcmp(val, "simt")) o.bwd_simt = 1; else if (!strcmp(val, "tc")) o.bwd_simt = 0; else return -1; }
   else if (!strcmp(key, "resample")) {
     if (!strcmp(val, "auto")) o.resample = 0; else if (!strcmp(val, "warp")) o.resample = 1; else if (!strcmp(val, "lane")) o.resample = 2; else return -1;
@@ -56,9 +59,9 @@ static int parse_option(Options& o, const char* key, const char* val) {
 }
 static Options& options() {
   static Options o = [] {
-    Options d{1, 2, 0, 4, 0, 0, 0, 0};
+    Options d{1, 2, 0, 4, 0, 0, 0, 0, 0};
     const char* keys[][2] = {{"C3D_FWD", "fwd"}, {"C3D_CLUSTER", "cluster"}, {"C3D_GRID", "grid"}, {"C3D_EGW", "egw"}, {"C3D_BWD", "bwd"},
-                             {"C3D_RESAMPLE", "resample"}, {"C3D_RESAMPLE_RB", "resample_rb"}, {"C3D_DEBUG", "debug"}};
+                             {"C3D_FP32", "fp32"}, {"C3D_RESAMPLE", "resample"}, {"C3D_RESAMPLE_RB", "resample_rb"}, {"C3D_DEBUG", "debug"}};
     for (auto& k : keys) { const char* e = getenv(k[0]); if (e) parse_option(d, k[1], e); }
     return d;
   }();
@@ -338,11 +341,37 @@ static int forward_bf16(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
   return fused_launch(a, 0, st);
 }
 
+// the fp32-mode point MLP: tensor cores (3-way bf16 split, clusters of two CTAs) unless the option asks for the FP32 pipe
+static int launch_mlp_fp32(MlpF32Args& m, int n_imgs, cudaStream_t st) {
+  m.n_imgs = n_imgs;
+  if (options().fp32_simt) {
+    C3D_SMEM_ATTR(mlp_fp32_kernel, F32_SMEM, 0, 1);
+    mlp_fp32_kernel<<<(unsigned)(n_imgs * m.tiles_per_img), 256, F32_SMEM, st>>>(m);
+    C3D_LAUNCH_CHECK();
+    return C3D_OK;
+  }
+  const long long pair_tiles = (long long)n_imgs * ((m.pts_per_img + 2 * tc32::TILE - 1) / (2 * tc32::TILE));
+  int grid = device_sms() & ~1;
+  if (pair_tiles * 2 < grid) grid = (int)(pair_tiles * 2);
+  if (options().grid > 0) grid = (options().grid + 1) & ~1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc32::NTHREADS); cfg.dynamicSmemBytes = tc32::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  void (*kern)(const MlpF32Args) = tc32::mlp_tc32_kernel;
+  C3D_SMEM_ATTR(kern, tc32::SMEM_BYTES, 0, 1);
+  C3D_CUDA(cudaLaunchKernelEx(&cfg, kern, m));
+  C3D_LAUNCH_CHECK();
+  return C3D_OK;
+}
+
 static int forward_fp32(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st, float* feat_out) {
   uint8_t* ws = reinterpret_cast<uint8_t*>(p->workspace);
   uint8_t* ck = ws + w.chunk;
   const size_t P = (size_t)p->n_rays * p->n_samples, R = (size_t)p->n_rays;
-  C3D_SMEM_ATTR(mlp_fp32_kernel, F32_SMEM, 0, 1);
   for (int i0 = 0; i0 < p->batch; i0 += w.chunk_imgs) {
     const int ni = (p->batch - i0 < w.chunk_imgs) ? p->batch - i0 : w.chunk_imgs;
     const float *pts, *rays_d, *viewdirs, *z_vals;
@@ -375,8 +404,7 @@ static int forward_fp32(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
     m.feat = reinterpret_cast<float*>(ck + w.c_feat); m.rgb = reinterpret_cast<float*>(ck + w.c_rgb);
     m.sdf = p->sdf + (size_t)i0 * P;
     m.save_acc = nullptr; m.save_stride = 0;
-    mlp_fp32_kernel<<<(unsigned)(ni * m.tiles_per_img), 256, F32_SMEM, st>>>(m);
-    C3D_LAUNCH_CHECK();
+    { const int rc = launch_mlp_fp32(m, ni, st); if (rc != C3D_OK) return rc; }
     if (fwd_sdf_only(p)) continue;                 // density-only pass: no compositing
     c3d_composite_params c;
     memset(&c, 0, sizeof(c));
@@ -861,7 +889,7 @@ static int backward_simt(const c3d_bwd_params* bp, cudaStream_t st) {
     m.n_samples = p->n_samples; m.pts_per_img = (int)P; m.tiles_per_img = (int)((P + F32_TP - 1) / F32_TP);
     m.feat = reinterpret_cast<float*>(ck + w.c_feat); m.rgb = reinterpret_cast<float*>(ck + w.c_rgb);
     m.sdf = reinterpret_cast<float*>(ck + w.c_sdf);
-    m.save_acc = reinterpret_cast<float*>(ck + w.c_acc); m.save_stride = (size_t)ni * P * W;
+    m.save_acc = reinterpret_cast<float*>(ck + w.c_acc); m.save_stride = (size_t)ni * P * W; m.n_imgs = ni;
     mlp_fp32_kernel<<<(unsigned)(ni * m.tiles_per_img), 256, F32_SMEM, st>>>(m);
     C3D_LAUNCH_CHECK();
     // 2. compositing backward
@@ -1177,7 +1205,7 @@ int c3d_eikonal_backward(const c3d_bwd_params* bp, const float* g_eik, c3d_strea
     m.n_samples = p->n_samples; m.pts_per_img = (int)P; m.tiles_per_img = (int)((P + F32_TP - 1) / F32_TP);
     m.feat = reinterpret_cast<float*>(ck + w.c_feat); m.rgb = reinterpret_cast<float*>(ck + w.c_rgb);
     m.sdf = reinterpret_cast<float*>(ck + w.c_sdf);
-    m.save_acc = reinterpret_cast<float*>(ck + w.c_acc); m.save_stride = (size_t)ni * P * W;
+    m.save_acc = reinterpret_cast<float*>(ck + w.c_acc); m.save_stride = (size_t)ni * P * W; m.n_imgs = ni;
     mlp_fp32_kernel<<<(unsigned)(ni * m.tiles_per_img), 256, F32_SMEM, st>>>(m);
     C3D_LAUNCH_CHECK();
     // 2. tangent sweep along v, 3. reverse sweep over both chains

@@ -20,7 +20,7 @@ struct MlpF32Args {
   const float* pts;        // (imgs, pts_per_img, 3) world space
   const float* viewdirs;   // (imgs, n_rays, 3)
   const float* near; const float* far;  // (imgs)
-  int n_samples; int pts_per_img; int tiles_per_img;
+  int n_samples; int pts_per_img; int tiles_per_img; int n_imgs;
   float* feat;             // (imgs*pts_per_img, 256)
   float* rgb;              // (imgs*pts_per_img, 3)
   float* sdf;              // (imgs*pts_per_img)
