@@ -36,7 +36,7 @@ int fail(int code, const char* fmt, ...) {
 //   grid      0 (default: one CTA per SM) | CTAs of the persistent kernels
 //   egw       4 (default) | 8   single-CTA forward: epilogue warps per slot
 //   bwd       "tc" (default) | "simt"   force the FP32-pipe backward
-//   fp32      "tc" (default: fp32-mode MLP on the tensor cores, 3-way bf16 split, mlp_tc32_sm100.cuh) | "simt" (FP32 pipe)
+//   fp32      "tc" (default: fp32-mode MLP on the tensor cores, two-way fp16 split, mlp_tc32_sm100.cuh) | "simt" (FP32 pipe)
 //   resample  "auto" (default) | "warp" | "lane";  resample_rb  rays per block of the warp kernel (0 = auto)
 //   debug     bit mask for builds with -DC3D_KERNEL_PROF (ignored by release builds)
 // ------------------------------------------------------------------------------------------
@@ -341,7 +341,7 @@ static int forward_bf16(const c3d_fwd_params* p, const FwdWs& w, cudaStream_t st
   return fused_launch(a, 0, st);
 }
 
-// the fp32-mode point MLP: tensor cores (3-way bf16 split, clusters of two CTAs) unless the option asks for the FP32 pipe
+// the fp32-mode point MLP: tensor cores (two-way fp16 split, clusters of two CTAs) unless the option asks for the FP32 pipe
 static int launch_mlp_fp32(MlpF32Args& m, int n_imgs, cudaStream_t st) {
   m.n_imgs = n_imgs;
   if (options().fp32_simt) {

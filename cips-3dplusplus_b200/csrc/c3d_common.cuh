@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -43,11 +44,12 @@ constexpr int NCHUNK = W / KCHUNK;  // 4 K-chunks per layer
 //              [0] K16 image [256 c][16]: slots 0..2 and 3..5 = bf16(Wrgb[j][c]) (pair with hi / lo of g_rgb), rest zero
 //              [1] K16 image [256 k][16]: slots 6, 7 = bf16(sigma_linear.weight[k]) (pair with hi / lo of g_sdf), rest zero
 //              [2] heads image 4 chunks x [16 n][64 c] (sw128): rows 0..2 = W0[c][j], rows 4..6 = Wview[c][256+j]
-//   wbf16m/l : the wbf16 layout again for bf16(W - hi) and bf16(W - hi - mid): with wbf16 the three-way bf16 split of the fp32
-//              weights (24 bits of mantissa), operands of the fp32-mode tensor-core MLP (mlp_tc32_sm100.cuh)
+//   wf16h/l  : the wbf16 layout again in IEEE half precision: hi = fp16(W) and lo = fp16(2^11 (W - hi)) -- the two-way fp16
+//              split of the fp32 weights (22 bits of mantissa; the scaled low part stays in the normal range), operands of
+//              the fp32-mode tensor-core MLP (mlp_tc32_sm100.cuh)
 // ------------------------------------------------------------------------------------------
 struct PackedLayout {
-  size_t w0, wvdir, bias, wsig, wrgb, scal, film, wT32, w32, wbf16, rgb16, w0img, wbf16T, bwd16, wbf16m, wbf16l, total;
+  size_t w0, wvdir, bias, wsig, wrgb, scal, film, wT32, w32, wbf16, rgb16, w0img, wbf16T, bwd16, wf16h, wf16l, total;
   int D;
 };
 constexpr size_t FILM_LAYER_FLOATS = 2 * (size_t)W * W + 2 * W;
@@ -78,8 +80,8 @@ __host__ __device__ inline PackedLayout packed_layout(int D) {
   L.wbf16T = o; o += WBF16_LAYER_BYTES * (size_t)D;
   L.bwd16 = o; o += 3 * W0IMG_BYTES;
   o = align_up(o, 1024);
-  L.wbf16m = o; o += WBF16_LAYER_BYTES * (size_t)D;
-  L.wbf16l = o; o += WBF16_LAYER_BYTES * (size_t)D;
+  L.wf16h = o; o += WBF16_LAYER_BYTES * (size_t)D;
+  L.wf16l = o; o += WBF16_LAYER_BYTES * (size_t)D;
   L.total = align_up(o, 1024);
   return L;
 }

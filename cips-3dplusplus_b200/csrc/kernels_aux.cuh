@@ -109,18 +109,16 @@ __global__ void pack_matrix_kernel(c3d_raw_params raw, uint8_t* __restrict__ blo
       for (int i = threadIdx.y; i < 32; i += 8) dsn[(size_t)(r0 + i) * W + c0 + threadIdx.x] = tile[i][threadIdx.x];
       uint8_t* img = blob + L.wbf16 + (size_t)(l - 1) * WBF16_LAYER_BYTES;
       uint8_t* imgT = blob + L.wbf16T + (size_t)(l - 1) * WBF16_LAYER_BYTES;
-      uint8_t* imgM = blob + L.wbf16m + (size_t)(l - 1) * WBF16_LAYER_BYTES;
-      uint8_t* imgL = blob + L.wbf16l + (size_t)(l - 1) * WBF16_LAYER_BYTES;
+      uint8_t* imgH = blob + L.wf16h + (size_t)(l - 1) * WBF16_LAYER_BYTES;
+      uint8_t* imgL = blob + L.wf16l + (size_t)(l - 1) * WBF16_LAYER_BYTES;
       for (int i = threadIdx.y; i < 32; i += 8) {
         const int n = r0 + i, k = c0 + threadIdx.x;
         const size_t off = (size_t)(k >> 6) * WBF16_CHUNK_BYTES + sw128_offset(n, k & 63);
         const float wv = tile[i][threadIdx.x];
-        const __nv_bfloat16 hi = __float2bfloat16_rn(wv);
-        const float r1 = wv - __bfloat162float(hi);
-        const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
-        *reinterpret_cast<__nv_bfloat16*>(img + off) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(imgM + off) = mid;
-        *reinterpret_cast<__nv_bfloat16*>(imgL + off) = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+        *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(wv);
+        const __half hi = __float2half_rn(wv);                  // fp32-mode operands: fp16 hi + 2^11-scaled fp16 lo
+        *reinterpret_cast<__half*>(imgH + off) = hi;
+        *reinterpret_cast<__half*>(imgL + off) = __float2half_rn((wv - __half2float(hi)) * 2048.0f);
         // transposed image: row = input channel k, column = output channel n
         *reinterpret_cast<__nv_bfloat16*>(imgT + (size_t)(n >> 6) * WBF16_CHUNK_BYTES + sw128_offset(k, n & 63)) =
             __float2bfloat16_rn(tile[i][threadIdx.x]);

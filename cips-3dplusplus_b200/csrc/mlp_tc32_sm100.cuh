@@ -1,26 +1,31 @@
 // fp32 parity mode of the FiLM-SIREN point MLP (volume_renderer.py:133-160) on the tensor cores of sm_100a.
 //
-// The fp32 products W_l h are formed from bf16 operands split three ways (x = hi + mid + lo, each a bf16: 24 bits of
-// mantissa), six tcgen05 products per layer:
-//     Wh Ah (own accumulator)   +   Wh Am + Wm Ah + Wm Am + Wh Al + Wl Ah (second accumulator)
-// The dropped terms (Wm Al, Wl Am, Wl Al) are 2^-24 relative.  Measured on B200 (bench_tools/umma_accum_probe.py): a K = 256
-// chain in TMEM has an rms error of 1.2e-7 on |acc| ~ 0.6 -- the level of a CPU fp32 GEMM (1.7e-7); the five small products
-// go to a second accumulator so that the 16-step main chain is not lengthened (TMEM truncates when it accumulates).
-// Sines are sinf() on the FP32 pipe, FiLM is applied in the epilogue in fp32, layer 0 (K = 3), the view-direction columns and
-// both heads run on the FP32 pipe as in mlp_fp32_kernel.  Per-point outputs (features, raw rgb, sdf) go to HBM for
+// The fp32 products W_l h are formed from IEEE half-precision operands split two ways, x = hi + 2^-11 lo' with
+// hi = fp16(x) and lo' = fp16(2^11 (x - hi)) (22 bits of mantissa, the scaled low part stays in fp16's normal range),
+// three tcgen05 products per layer:
+//     acc0 = Wh Ah          acc1 = Wh Al' + Wl' Ah          W h = acc0 + 2^-11 acc1
+// The dropped term (Wl Al) is 2^-22 relative.  Measured on B200 (bench_tools/umma_accum_probe.py): a K = 256 chain in TMEM has
+// an rms error of 1.2e-7 on |acc| ~ 0.6 -- the level of a CPU fp32 GEMM (1.7e-7); the two small products go to a second
+// accumulator so that the 16-step main chain is not lengthened (TMEM truncates when it accumulates) and so that they can carry
+// their own scale.  Round 2's first version split three ways in bf16 (six products per layer, 257 ms per configs[1] step);
+// fp16's 11-bit mantissa needs half the tensor work for the same 2.4e-7.
+// Sines run on the FP32 pipe: Cody-Waite reduction by pi (two constants, FMA) and an odd degree-9 polynomial, max error 1.1e-7
+// on |x| <= 100 (sinf: 0.7e-7); FiLM is applied in the epilogue in fp32; layer 0 (K = 3), the view-direction columns and both
+// heads run on the FP32 pipe as in mlp_fp32_kernel.  Per-point outputs (features, raw rgb, sdf) go to HBM for
 // composite_fwd_kernel exactly as in the FP32-pipe kernel, whose argument struct this kernel shares.
 //
 // Structure: clusters of two CTAs, one pair-tile of 2 x 128 points at a time.  TMEM lanes are points (D[point][channel],
-// tcgen05.mma.cta_group::2, M = 256, N = 256), so every CTA keeps the three split tiles of ITS 128 points in shared memory
-// (3 x 64 KB, K-major SWIZZLE_128B, written in place by the epilogue) and stages only its 128 rows of each weight chunk
-// (16 KB stages, two of them: what is left of 227 KB).  Warp 0 streams the stages with cp.async.bulk in the order the
-// issuer consumes them -- per K-chunk: Wh (x Ah, Am, Al), Wm (x Ah, Am), Wl (x Ah) -- 24 MMAs of 128 cycles per K-chunk
-// against three 16 KB copies.  Warp 1 issues (leader CTA) or relays the peer's "stage landed" (follower), warp 2 owns TMEM,
-// warps 4..19 are the epilogue: warp (quad, grp) handles TMEM lanes 32 quad.. (points) x columns 64 grp.. (channels).
+// tcgen05.mma.cta_group::2, M = 256, N = 256), so every CTA keeps the two split tiles of ITS 128 points in shared memory
+// (2 x 64 KB, K-major SWIZZLE_128B, written in place by the epilogue) and stages only its 128 rows of each weight chunk
+// (16 KB stages, a ring of five).  Warp 0 streams the stages with cp.async.bulk in the order the issuer consumes them -- per
+// K-chunk: Wh (x Ah, Al'), Wl' (x Ah) -- 12 MMAs of 128 cycles per K-chunk against two 16 KB copies.  Warp 1 issues (leader
+// CTA) or relays the peer's "stage landed" (follower), warp 2 owns TMEM, warps 4..19 are the epilogue: warp (quad, grp) handles
+// TMEM lanes 32 quad.. (points) x columns 64 grp.. (channels).
 #pragma once
 #include "c3d_common.cuh"
 #include "sm100_ptx.cuh"
 #include "mlp_fp32.cuh"
+#include <type_traits>
 
 namespace c3d { namespace tc32 {
 
@@ -29,15 +34,17 @@ using namespace c3d::ptx;
 constexpr int TILE = 128;                       // points per CTA and tile
 constexpr int EPW = 16;                         // epilogue warps
 constexpr int NTHREADS = 128 + EPW * 32;        // 640
-constexpr int SPLIT_BYTES = 65536;              // one split tile: [4 K-chunks][128 points][64 k] bf16
+constexpr int SPLIT_BYTES = 65536;              // one split tile: [4 K-chunks][128 points][64 k] fp16
 constexpr int CHUNK_BYTES = 16384;
 constexpr int STAGE_BYTES = 16384;              // [128 weight rows of this CTA][64 k]
-constexpr int NSTAGE = 2;
-constexpr int SM_ACT = 0;                                   // hi, mid, lo
-constexpr int SM_STAGE = 3 * SPLIT_BYTES;                   // 196608
-constexpr int SM_RED = SM_STAGE + NSTAGE * STAGE_BYTES;     // 229376  [4 column groups][128] float: sdf partial sums
-constexpr int SM_MISC = SM_RED + 4 * TILE * 4;              // 231424
-constexpr int SMEM_BYTES = SM_MISC + 128;                   // 231552 (of 232448): no slack for re-alignment, see the trap below
+constexpr int NSTAGE = 5;
+constexpr int NSPLIT = 2;
+constexpr float LO_SCALE = 2048.0f, LO_UNSCALE = 1.0f / 2048.0f;
+constexpr int SM_ACT = 0;                                   // hi, lo'
+constexpr int SM_STAGE = NSPLIT * SPLIT_BYTES;              // 131072
+constexpr int SM_RED = SM_STAGE + NSTAGE * STAGE_BYTES;     // 212992  [4 column groups][128] float: sdf partial sums
+constexpr int SM_MISC = SM_RED + 4 * TILE * 4;              // 215040
+constexpr int SMEM_BYTES = SM_MISC + 128;                   // 215168: no slack for re-alignment, see the trap below
 
 struct Misc {
   uint64_t full[NSTAGE], empty[NSTAGE], a_ready, acc_full;
@@ -57,20 +64,48 @@ __device__ __forceinline__ void ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 
-// x[0..7] -> three 16-byte units (hi, mid, lo bf16 of 8 consecutive channels) at the same offset of the three split tiles
+// x[0..7] -> two 16-byte units (hi, scaled lo fp16 of 8 consecutive channels) at the same offset of the two split tiles
 __device__ __forceinline__ void split_store8(const float* x, uint32_t addr_hi) {
-  uint32_t h[4], m[4], l[4];
+  uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
-    const float r0 = x[2 * i] - __uint_as_float(h[i] << 16), r1 = x[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
-    m[i] = pack_bf16x2(r0, r1);
-    const float s0 = r0 - __uint_as_float(m[i] << 16), s1 = r1 - __uint_as_float(m[i] & 0xffff0000u);
-    l[i] = pack_bf16x2(s0, s1);
+    h[i] = pack_f16x2(x[2 * i], x[2 * i + 1]);
+    const float2 f = unpack_f16x2(h[i]);
+    l[i] = pack_f16x2((x[2 * i] - f.x) * LO_SCALE, (x[2 * i + 1] - f.y) * LO_SCALE);
   }
   st_v4(addr_hi, h[0], h[1], h[2], h[3]);
-  st_v4(addr_hi + SPLIT_BYTES, m[0], m[1], m[2], m[3]);
-  st_v4(addr_hi + 2 * SPLIT_BYTES, l[0], l[1], l[2], l[3]);
+  st_v4(addr_hi + SPLIT_BYTES, l[0], l[1], l[2], l[3]);
+}
+
+// sin(x) on the FP32 pipe: n = rint(x / pi) by the magic-number trick, r = x - n pi with pi = PI_HI + PI_LO (FMA: one rounding
+// each), sign from the parity of n, odd degree-9 minimax polynomial on [-pi/2, pi/2].  Max error 1.1e-7 for |x| <= 100
+// (bench_tools/sin_poly_fit.py).  Branch-free so that the 16 sines of a chunk interleave; beyond |x| = 8192 the reduction runs
+// out of bits and the whole chunk is redone by libdevice (never on the reference's value ranges).
+__device__ __forceinline__ float sin_poly(float x) {
+  const float t = fmaf(x, 0.318309886f, 12582912.0f);
+  const float n = t - 12582912.0f;
+  float r = fmaf(n, -3.14159274f, x);
+  r = fmaf(n, 8.742278e-8f, r);
+  r = __uint_as_float(__float_as_uint(r) ^ (__float_as_uint(t) << 31));
+  const float s = r * r;
+  float q = fmaf(2.5943759e-06f, s, -1.9804016e-04f);
+  q = fmaf(q, s, 8.3329808e-03f);
+  q = fmaf(q, s, -1.6666655e-01f);
+  return fmaf(r * s, q, r);
+}
+__device__ __noinline__ float sin_far(float x) { return sinf(x); }
+template <int N>
+__device__ __forceinline__ void sin_inplace(float (&x)[N]) {
+  float m = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) m = fmaxf(m, fabsf(x[i]));
+  if (__builtin_expect(m > 8192.0f, 0)) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = sin_far(x[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = sin_poly(x[i]);
+  }
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc32_kernel(const MlpF32Args a) {
@@ -102,13 +137,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc32_kernel(const MlpF32Args 
   if (warp == 0) {
     if (elect_one()) {
       // ============================================================ weight producer: this CTA's 128 rows of every chunk
-      const uint8_t* img[3] = {a.blob + a.L.wbf16, a.blob + a.L.wbf16m, a.blob + a.L.wbf16l};
+      const uint8_t* img[NSPLIT] = {a.blob + a.L.wf16h, a.blob + a.L.wf16l};
       uint32_t n = 0;
       for (int pt = cl; pt < total; pt += ncl)
         for (int l = 1; l <= D; ++l)
           for (int kc = 0; kc < NCHUNK; ++kc)
 #pragma unroll
-            for (int sp = 0; sp < 3; ++sp, ++n) {
+            for (int sp = 0; sp < NSPLIT; ++sp, ++n) {
               const uint32_t st = n % NSTAGE, ph = (n / NSTAGE) & 1u;
               mbar_wait(&misc->empty[st], ph ^ 1u);
               mbar_arrive_expect_tx(&misc->full[st], STAGE_BYTES);
@@ -123,7 +158,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc32_kernel(const MlpF32Args 
       const uint32_t r_full = mapa_u32(smem_u32(&misc->full[0]), 0u);
       uint32_t n = 0;
       for (int pt = cl; pt < total; pt += ncl)
-        for (int i = 0; i < D * NCHUNK * 3; ++i, ++n) {
+        for (int i = 0; i < D * NCHUNK * NSPLIT; ++i, ++n) {
           const uint32_t st = n % NSTAGE, ph = (n / NSTAGE) & 1u;
           mbar_wait(&misc->full[st], ph);
           mbar_arrive_remote(r_full + st * 8u);
@@ -132,7 +167,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc32_kernel(const MlpF32Args 
   } else if (warp == 1) {
     // ============================================================ MMA issuer (leader; whole warp runs the control flow)
     const bool issue = elect_one();
-    const uint32_t idesc = umma_idesc_bf16(256, 256, 0, 0);
+    const uint32_t idesc = umma_idesc_f16(256, 256);
     const uint32_t act_base = smem_u32(smem + SM_ACT), stage_base = smem_u32(smem + SM_STAGE);
     const uint32_t acc0 = tmem_base, acc1 = tmem_base + 256u;
     uint32_t n = 0, acnt = 0;
@@ -144,14 +179,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc32_kernel(const MlpF32Args 
 #pragma unroll 1
         for (int kc = 0; kc < NCHUNK; ++kc)
 #pragma unroll
-          for (int sp = 0; sp < 3; ++sp, ++n) {
+          for (int sp = 0; sp < NSPLIT; ++sp, ++n) {
             const uint32_t st = n % NSTAGE, ph = (n / NSTAGE) & 1u;
             mbar_wait_cluster(&misc->full[st], ph);
             tc_fence_after();
             if (issue) {
               const uint64_t bd = umma_desc_kmajor_sw128(stage_base + st * STAGE_BYTES);
 #pragma unroll
-              for (int asp = 0; asp < 3 - sp; ++asp) {            // Wh x (Ah, Am, Al), Wm x (Ah, Am), Wl x Ah
+              for (int asp = 0; asp < NSPLIT - sp; ++asp) {       // Wh x (Ah, Al'), Wl' x Ah
                 const uint64_t ad = umma_desc_kmajor_sw128(act_base + asp * SPLIT_BYTES + kc * CHUNK_BYTES);
                 const bool main_acc = sp == 0 && asp == 0;
                 const bool first = kc == 0 && sp == 0 && asp <= 1;      // first MMA into acc0 (asp 0) / acc1 (asp 1)
@@ -212,8 +247,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc32_kernel(const MlpF32Args 
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 t = __ldg(first + u * 8 + i);
-            x[i] = sinf(fmaf(t.x, px, fmaf(t.y, py, fmaf(t.z, pz, t.w))));
-            if (D == 1) sp = fmaf(__ldg(wsig + c0 + u * 8 + i), x[i], sp);
+            x[i] = fmaf(t.x, px, fmaf(t.y, py, fmaf(t.z, pz, t.w)));
+          }
+          sin_inplace(x);
+          if (D == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sp = fmaf(__ldg(wsig + c0 + u * 8 + i), x[i], sp);
           }
           split_store8(x, row_hi + (uint32_t)((u ^ r7) << 4));
         }
@@ -229,34 +268,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc32_kernel(const MlpF32Args 
         const float4* view = a.view + (size_t)img * W + c0;
         float* save = a.save_acc ? a.save_acc + (size_t)(l - 1) * a.save_stride + gp * W + c0 : nullptr;
         float sp = 0.f, rr = 0.f, rg = 0.f, rb = 0.f;
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {                         // 16 channels per iteration
+        // 16 channels per iteration; kind: 0 hidden layer, 1 last hidden layer (+ sdf head), 2 view layer (+ rgb head, features)
+        auto chunk = [&](int j, auto kind_tag) {
+          constexpr int kind = decltype(kind_tag)::value;
           uint32_t v0[16], v1[16];
           ld16(t0 + j * 16, v0);
           ld16(t1 + j * 16, v1);
           tmem_ld_wait();
           float x[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v0[i]) + __uint_as_float(v1[i]);
+          for (int i = 0; i < 16; ++i) x[i] = fmaf(__uint_as_float(v1[i]), LO_UNSCALE, __uint_as_float(v0[i]));
           if (save && valid) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               reinterpret_cast<float4*>(save + j * 16)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float2 f = __ldg(film + j * 16 + i);
-            float arg = fmaf(f.x, x[i], f.y);
-            if (l == D) {                                     // view layer: + gammaD * Wview[:, 256..258] . viewdir
-              const float4 tv = __ldg(view + j * 16 + i);
-              arg = fmaf(f.x, x[i], fmaf(tv.x, vx, fmaf(tv.y, vy, tv.z * vz)) + f.y);
+          for (int i = 0; i < 16; i += 2) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(film + j * 16 + i));     // (gamma, shift) of two channels
+            if (kind == 2) {                                  // view layer: + gammaD * Wview[:, 256..258] . viewdir
+              const float4 tv = __ldg(view + j * 16 + i), tw = __ldg(view + j * 16 + i + 1);
+              x[i] = fmaf(f.x, x[i], fmaf(tv.x, vx, fmaf(tv.y, vy, tv.z * vz)) + f.y);
+              x[i + 1] = fmaf(f.z, x[i + 1], fmaf(tw.x, vx, fmaf(tw.y, vy, tw.z * vz)) + f.w);
+            } else {
+              x[i] = fmaf(f.x, x[i], f.y);
+              x[i + 1] = fmaf(f.z, x[i + 1], f.w);
             }
-            x[i] = sinf(arg);
           }
-          if (l < D) {
-            if (l == D - 1) {
+          sin_inplace(x);
+          if (kind < 2) {
+            if (kind == 1) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) sp = fmaf(__ldg(wsig + c0 + j * 16 + i), x[i], sp);
+              for (int i = 0; i < 16; i += 4) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(wsig + c0 + j * 16 + i));
+                sp = fmaf(w.x, x[i], sp); sp = fmaf(w.y, x[i + 1], sp); sp = fmaf(w.z, x[i + 2], sp); sp = fmaf(w.w, x[i + 3], sp);
+              }
             }
             split_store8(x, row_hi + (uint32_t)(((2 * j) ^ r7) << 4));
             split_store8(x + 8, row_hi + (uint32_t)(((2 * j + 1) ^ r7) << 4));
@@ -272,6 +318,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc32_kernel(const MlpF32Args 
               for (int i = 0; i < 4; ++i) o[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
             }
           }
+        };
+        if (l == D) {
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) chunk(j, std::integral_constant<int, 2>{});
+        } else if (l == D - 1) {
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) chunk(j, std::integral_constant<int, 1>{});
+        } else {
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) chunk(j, std::integral_constant<int, 0>{});
         }
         if (l < D) {
           if (l == D - 1) sdf_out(sp, gp, valid);
