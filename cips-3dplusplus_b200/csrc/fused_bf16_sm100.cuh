@@ -60,9 +60,9 @@ __device__ __forceinline__ int job_layer(int j, int D) {
   return -1;
 }
 
-__device__ __forceinline__ void st_bf16(uint32_t smem_addr, float x) {
+__device__ __forceinline__ void st_f16(uint32_t smem_addr, float x) {
   uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(x));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(x));
   asm volatile("st.shared.b16 [%0], %1;" ::"r"(smem_addr), "h"((unsigned short)r) : "memory");
 }
 __device__ __forceinline__ void st_v4(uint32_t smem_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -78,7 +78,7 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
       : "r"(taddr)
       : "memory");
 }
-// sin(acc * scale + shift) for 16 consecutive points of one channel -> bf16 -> two 16-byte stores into H^T.
+// sin(acc * scale + shift) for 16 consecutive points of one channel -> fp16 -> two 16-byte stores into H^T.
 __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], float scale, float shift, uint32_t row_addr,
                                            int u0, int c7) {
 #pragma unroll
@@ -86,8 +86,8 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], float scale,
     float o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = __sinf(fmaf(__uint_as_float(v[g * 8 + i]), scale, shift));
-    st_v4(row_addr + (uint32_t)(((u0 + g) ^ c7) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-          pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    st_v4(row_addr + (uint32_t)(((u0 + g) ^ c7) << 4), pack_f16x2(o[0], o[1]), pack_f16x2(o[2], o[3]),
+          pack_f16x2(o[4], o[5]), pack_f16x2(o[6], o[7]));
   }
 }
 
@@ -96,11 +96,6 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], float scale,
 // cos(scale * acc + shift) (and, for the view layer, the output sin(...) itself) from it: |acc| < 2, so fp16's 11 significant
 // bits put the ~30 rad argument within 0.007 rad -- the accuracy a stored bf16 cosine has -- at a third of the bytes of storing
 // accumulator, cosine and output.
-__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
 __device__ __forceinline__ void epilogue16_save(const uint32_t (&v)[16], float scale, float shift, uint32_t row_addr,
                                                 int u0, int c7, __nv_bfloat16* sacc) {
 #pragma unroll
@@ -108,7 +103,7 @@ __device__ __forceinline__ void epilogue16_save(const uint32_t (&v)[16], float s
     float o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = __sinf(fmaf(__uint_as_float(v[g * 8 + i]), scale, shift));
-    const uint4 po = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    const uint4 po = make_uint4(pack_f16x2(o[0], o[1]), pack_f16x2(o[2], o[3]), pack_f16x2(o[4], o[5]), pack_f16x2(o[6], o[7]));
     st_v4(row_addr + (uint32_t)(((u0 + g) ^ c7) << 4), po.x, po.y, po.z, po.w);
     const size_t goff = (size_t)g * (W * 8);
     *reinterpret_cast<uint4*>(sacc + goff) =
@@ -170,7 +165,7 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
   if (warp == 0) {
    if (elect_one()) {
     // ============================================================ weight producer
-    const uint8_t* wsrc = a.blob + a.L.wbf16;
+    const uint8_t* wsrc = a.blob + a.L.wf16h;
     uint32_t n = 0;
     for (int g = 0; g < rounds; ++g) {
       const int layer = job_layer(g % JOBS, D);
@@ -199,9 +194,10 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
    if (elect_one()) {
     // ============================================================ MMA issuer
     const uint32_t idesc_kk = umma_idesc_bf16(128, 128, 0, 0);     // both K-major (K = 16 side products)
-    const uint32_t idesc_l = umma_idesc_bf16(128, 128, 0, 1);      // layers: A = weights K-major, B = H^T MN-major
-    const uint32_t idesc_h = umma_idesc_bf16(128, 16, 1, 0);       // heads : A = H^T MN-major (rows = points)
-    const uint32_t idesc_c = umma_idesc_bf16(128, 16, 0, 0);       // composite: A = feat^T K-major, B = Wgt K-major
+    // every product that reads the activation tile takes IEEE half operands (c3d_common.cuh: "16-bit operand formats")
+    const uint32_t idesc_l = umma_idesc_f16(128, 128, 0, 1);       // layers: A = weights K-major, B = H^T MN-major
+    const uint32_t idesc_h = umma_idesc_f16(128, 16, 1, 0);        // heads : A = H^T MN-major (rows = points)
+    const uint32_t idesc_c = umma_idesc_f16(128, 16, 0, 0);        // composite: A = feat^T K-major, B = Wgt K-major
     const uint32_t act_addr[2] = {smem_u32(smem + SM_ACT), smem_u32(smem + SM_ACT + ACT_BYTES)};
     const uint32_t stage_base = smem_u32(smem + SM_STAGE);
     const uint32_t aux_addr[2] = {smem_u32(smem + SM_AUX), smem_u32(smem + SM_AUX + AUX_BYTES)};
@@ -440,11 +436,11 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
           jobcnt++;
           tc_fence_after();
           if (l == D && pt_role) {
-            // the view-direction tile has been consumed: build Wgt[ray slot][point] (bf16, K-major SW128) in its place
+            // the view-direction tile has been consumed: build Wgt[ray slot][point] (fp16, K-major SW128) in its place
             const int myslot = rl - rl0;
 #pragma unroll
             for (int jx = 0; jx < RAYS; ++jx)
-              st_bf16(aux_u32 + (uint32_t)((t >> 6) * 2048) + sw128_offset(jx, t & 63), jx == myslot ? wgt : 0.f);
+              st_f16(aux_u32 + (uint32_t)((t >> 6) * 2048) + sw128_offset(jx, t & 63), jx == myslot ? wgt : 0.f);
           }
 #pragma unroll 1
           for (int hh = 0; hh < HPT; ++hh) {

@@ -3,10 +3,10 @@
 // Reference semantics: exp/cips3d/volume_renderer.py:133-160,192-283, exp/cips3d/nerf_utils.py:17-218,230-338.
 //
 // Structure (profiles/r02_fused.md and profiles/r02_micro.md have the measurements behind each choice)
-//   * FiLM is folded into the GEMM.  film_weights_kernel (kernels_aux.cuh) writes, per image, bf16(gamma_c * W_l[c][k]) in
+//   * FiLM is folded into the GEMM.  film_weights_kernel (kernels_aux.cuh) writes, per image, fp16(gamma_c * W_l[c][k]) in
 //     the stage layout plus a K = 16 side image holding the shift (gamma b + beta, hi/lo split, multiplied by two "ones"
 //     slots of the point tile), the layer-0 weights and the view-direction columns.  The accumulator is the SIREN argument
-//     itself, so the epilogue is sin -> bf16 -> store with no per-channel constants.
+//     itself, so the epilogue is sin -> fp16 -> store with no per-channel constants.
 //   * Orientation D[point][channel] = H * W'^T: TMEM lanes are points.  A thread owns one point of its tile in every
 //     stage (geometry, layer epilogues, sdf / transmittance, rgb) and writes its own rows of the K-major activation tile.
 //   * Two CTAs of a cluster form a pair and issue tcgen05.mma.cta_group::2 (M = 256 points = 128 per CTA, N = 256): every
@@ -116,9 +116,9 @@ __device__ __forceinline__ int job_kind(int j, int D) { return j == 0 ? 0 : (j =
 __device__ __forceinline__ int job_film_layer(int j, int D) { return j; }        // jobs 0..D: index into kimg
 __device__ __forceinline__ int job_w_layer(int j, int D) { return j - 1; }       // jobs 1..D: index into wimg
 
-__device__ __forceinline__ void st_bf16(uint32_t smem_addr, float x) {
+__device__ __forceinline__ void st_f16(uint32_t smem_addr, float x) {
   uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(x));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(x));
   asm volatile("st.shared.b16 [%0], %1;" ::"r"(smem_addr), "h"((unsigned short)r) : "memory");
 }
 __device__ __forceinline__ void st_v4(uint32_t smem_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -136,15 +136,15 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
 // descriptor of the same layout `bytes` further (start-address field, 16-byte units; no carry out of the field here)
 __device__ __forceinline__ uint64_t desc_at(uint64_t base, uint32_t bytes) { return base + (uint64_t)(bytes >> 4); }
 
-// sin of 16 consecutive channels of one point -> bf16 -> two 16-byte stores into the point's row (units u0, u0 + 1)
+// sin of 16 consecutive channels of one point -> fp16 -> two 16-byte stores into the point's row (units u0, u0 + 1)
 __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], uint32_t row_addr, int u0, int r7) {
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     float o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = __sinf(__uint_as_float(v[g * 8 + i]));
-    st_v4(row_addr + (uint32_t)(((u0 + g) ^ r7) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-          pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    st_v4(row_addr + (uint32_t)(((u0 + g) ^ r7) << 4), pack_f16x2(o[0], o[1]), pack_f16x2(o[2], o[3]),
+          pack_f16x2(o[4], o[5]), pack_f16x2(o[6], o[7]));
   }
 }
 
@@ -169,8 +169,8 @@ __device__ __forceinline__ void epilogue16_sdf(const uint32_t (&v)[16], uint32_t
     const float4 wa = wsig[2 * g], wb = wsig[2 * g + 1];
     acc[0] = fmaf(wa.x, o[0], acc[0]); acc[1] = fmaf(wa.y, o[1], acc[1]); acc[2] = fmaf(wa.z, o[2], acc[2]); acc[3] = fmaf(wa.w, o[3], acc[3]);
     acc[0] = fmaf(wb.x, o[4], acc[0]); acc[1] = fmaf(wb.y, o[5], acc[1]); acc[2] = fmaf(wb.z, o[6], acc[2]); acc[3] = fmaf(wb.w, o[7], acc[3]);
-    st_v4(row_addr + (uint32_t)(((u0 + g) ^ r7) << 4), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-          pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    st_v4(row_addr + (uint32_t)(((u0 + g) ^ r7) << 4), pack_f16x2(o[0], o[1]), pack_f16x2(o[2], o[3]),
+          pack_f16x2(o[4], o[5]), pack_f16x2(o[6], o[7]));
   }
 }
 
@@ -292,9 +292,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
     // operand is then uniform by data flow and lives in uniform registers.  (With the loop inside `if (elect_one())`
     // ptxas wrapped each UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall -- ~170 cycles per MMA.)
     const bool issue = elect_one();
-    const uint32_t idesc_l = umma_idesc_bf16(256, 256, 0, 0);      // layers and K16 side products: both K-major
-    const uint32_t idesc_h = umma_idesc_bf16(256, 16, 0, 0);       // heads: B = 8 rows of heads16 per CTA
-    const uint32_t idesc_c = umma_idesc_bf16(256, 32, 1, 0);       // compositing: A = feat^T (MN-major view), B = Wgt
+    // every product that reads the activation tile takes IEEE half operands (c3d_common.cuh: "16-bit operand formats");
+    // the K16 side products (point / view tile x kimg) stay bf16 x bf16 and add into the same fp32 accumulator
+    const uint32_t idesc_k = umma_idesc_bf16(256, 256, 0, 0);      // K16 side products: both K-major
+    const uint32_t idesc_l = umma_idesc_f16(256, 256, 0, 0);       // layers: both K-major
+    const uint32_t idesc_h = umma_idesc_f16(256, 16, 0, 0);        // heads: B = 8 rows of heads16 per CTA
+    const uint32_t idesc_c = umma_idesc_f16(256, 32, 1, 0);        // compositing: A = feat^T (MN-major view), B = Wgt
     const uint32_t act_base = smem_u32(smem + SM_ACT);
     const uint32_t stage_base = smem_u32(smem + SM_STAGE);
     const uint32_t aux_base = smem_u32(smem + SM_AUX);
@@ -330,7 +333,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
           const uint32_t n0 = reuse ? n_shared : n;
           const uint64_t auxd = umma_desc_kmajor_k16(aux_addr);
           if (issue) {
-            umma_bf16_ss_pair(tacc, auxd, umma_desc_kmajor_k16(k16_addr), idesc_l, 0u);
+            umma_bf16_ss_pair(tacc, auxd, umma_desc_kmajor_k16(k16_addr), idesc_k, 0u);
             umma_commit_pair(&misc->kempty[s], (uint16_t)0x3);
           }
           if (kind == 1) {
@@ -495,11 +498,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
               tc_fence_after();
               if (l == D && ptg) {
                 // all MMAs of the view layer are complete: the view tile has been consumed, build Wgt[ray slot][point]
-                // (bf16, K-major SW128) in its place
+                // (fp16, K-major SW128) in its place
                 const int myslot = rl - rl0;
 #pragma unroll
                 for (int jx = 0; jx < RAYS; ++jx)
-                  st_bf16(aux_u32 + (uint32_t)((t >> 6) * 2048) + sw128_offset(jx, t & 63), jx == myslot ? wgt : 0.f);
+                  st_f16(aux_u32 + (uint32_t)((t >> 6) * 2048) + sw128_offset(jx, t & 63), jx == myslot ? wgt : 0.f);
               }
             }
             C3D_PROF(h == 0 ? 1 : 3);

@@ -39,14 +39,14 @@ __global__ void pack_small_kernel(c3d_raw_params raw, uint8_t* __restrict__ blob
     f[2 * W * W + c] = gb[c];
     f[2 * W * W + W + c] = bb[c];
   }
-  // heads16 bf16 image: [16 n][64 k] x 4 chunks; rows 0..2 rgb head, rows 4/5 = hi/lo split of the sdf head
+  // heads16 fp16 image: [16 n][64 k] x 4 chunks; rows 0..2 rgb head, rows 4/5 = hi/lo split of the sdf head
   uint8_t* r16 = blob + L.rgb16;
   const float ws = raw.sigma_weight[c];
-  const float ws_hi = __bfloat162float(__float2bfloat16_rn(ws));
+  const float ws_hi = __half2float(__float2half_rn(ws));
   for (int n = 0; n < 16; ++n) {
     float v = n < 3 ? raw.rgb_weight[n * W + c] : (n == 4 ? ws_hi : (n == 5 ? ws - ws_hi : 0.f));
     const int ch = c >> 6, k = c & 63;
-    *reinterpret_cast<__nv_bfloat16*>(r16 + (size_t)ch * (16 * 128) + sw128_offset(n, k)) = __float2bfloat16_rn(v);
+    *reinterpret_cast<__half*>(r16 + (size_t)ch * (16 * 128) + sw128_offset(n, k)) = __float2half_rn(v);
   }
   // wk16 image (see c3d_common.cuh): W0 split in slots 0..11, view-direction weights in 12..14
   uint8_t* w0i = blob + L.w0img;
@@ -107,7 +107,6 @@ __global__ void pack_matrix_kernel(c3d_raw_params raw, uint8_t* __restrict__ blo
       for (int i = threadIdx.y; i < 32; i += 8) dst[(size_t)(c0 + i) * W + r0 + threadIdx.x] = tile[threadIdx.x][i];
       float* dsn = reinterpret_cast<float*>(blob + L.w32) + (size_t)(l - 1) * W * W;
       for (int i = threadIdx.y; i < 32; i += 8) dsn[(size_t)(r0 + i) * W + c0 + threadIdx.x] = tile[i][threadIdx.x];
-      uint8_t* img = blob + L.wbf16 + (size_t)(l - 1) * WBF16_LAYER_BYTES;
       uint8_t* imgT = blob + L.wbf16T + (size_t)(l - 1) * WBF16_LAYER_BYTES;
       uint8_t* imgH = blob + L.wf16h + (size_t)(l - 1) * WBF16_LAYER_BYTES;
       uint8_t* imgL = blob + L.wf16l + (size_t)(l - 1) * WBF16_LAYER_BYTES;
@@ -115,8 +114,7 @@ __global__ void pack_matrix_kernel(c3d_raw_params raw, uint8_t* __restrict__ blo
         const int n = r0 + i, k = c0 + threadIdx.x;
         const size_t off = (size_t)(k >> 6) * WBF16_CHUNK_BYTES + sw128_offset(n, k & 63);
         const float wv = tile[i][threadIdx.x];
-        *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(wv);
-        const __half hi = __float2half_rn(wv);                  // fp32-mode operands: fp16 hi + 2^11-scaled fp16 lo
+        const __half hi = __float2half_rn(wv);                  // fp16(W): forward operand; with the 2^11-scaled lo the fp32 mode's
         *reinterpret_cast<__half*>(imgH + off) = hi;
         *reinterpret_cast<__half*>(imgL + off) = __float2half_rn((wv - __half2float(hi)) * 2048.0f);
         // transposed image: row = input channel k, column = output channel n
@@ -197,8 +195,8 @@ __global__ void __launch_bounds__(SP_THREADS) style_prep_kernel(const uint8_t* _
 
 // ------------------------------------------------------------------------------------------
 // Per-image weight images of the CTA-pair forward kernel (fused_pair_sm100.cuh): FiLM folded into the GEMM operands.
-//   wimg[b][idx 0..D-1][kc 0..3][half 0..1] : 16 KB stage images [128 rows n][64 k] bf16, K-major SWIZZLE_128B,
-//                                             value bf16(gamma_{b,idx+1}[n] * W_{idx+1}[n][k]),  n = 128 half + row
+//   wimg[b][idx 0..D-1][kc 0..3][half 0..1] : 16 KB stage images [128 rows n][64 k] fp16, K-major SWIZZLE_128B,
+//                                             value fp16(gamma_{b,idx+1}[n] * W_{idx+1}[n][k]),  n = 128 half + row
 //   kimg[b][L 0..D][half 0..1]              : 4 KB K16 images [128 rows n][16 slots], UMMA K-major no-swizzle:
 //        L = 0     slots 4j..4j+3 = (hi, hi, lo, hi) of gamma W0[n][j]   (x point tile (hi, mid, hi, lo))
 //        L = D     slots j and 3+j = bf16(gamma Wview[n][256+j])         (x view tile (hi x3, lo x3))
@@ -217,8 +215,8 @@ __global__ void __launch_bounds__(256) film_weights_kernel(const uint8_t* __rest
   for (int u = 0; u < 4; ++u) {
     const float4 x = src[2 * u], y = src[2 * u + 1];
     uint4 o;
-    o.x = ptx::pack_bf16x2(gamma * x.x, gamma * x.y); o.y = ptx::pack_bf16x2(gamma * x.z, gamma * x.w);
-    o.z = ptx::pack_bf16x2(gamma * y.x, gamma * y.y); o.w = ptx::pack_bf16x2(gamma * y.z, gamma * y.w);
+    o.x = ptx::pack_f16x2(gamma * x.x, gamma * x.y); o.y = ptx::pack_f16x2(gamma * x.z, gamma * x.w);
+    o.z = ptx::pack_f16x2(gamma * y.x, gamma * y.y); o.w = ptx::pack_f16x2(gamma * y.z, gamma * y.w);
     *reinterpret_cast<uint4*>(dst + (((q * 4 + u) ^ (i & 7)) << 4)) = o;
   }
 }
