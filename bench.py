@@ -48,6 +48,16 @@ CONFIGS = {
 IMG = 64
 
 
+
+OPERANDS = ("tcgen05 kind::f16, fp32 accumulate: IEEE half operands wherever the hidden-layer activations are read (layers, heads, "
+            "compositing; same dense peak as bf16, 8x finer mantissa), bfloat16 K=16 side operands and backward")
+
+
+def _dtype(precision):
+    """Arithmetic type of the path: the 16-bit tensor-core mode (API name "bf16", BASELINE's bf16 mode) multiplies fp16 operands."""
+    return "f16" if precision == "bf16" else "f32"
+
+
 def workload(cfg, seed_latent=1, seed_pose=2):
     """Synthetic inputs of the configured shape (numpy, host): poses, focal, near, far, styles."""
     from oracle import nerf_oracle as O
@@ -298,7 +308,7 @@ def run_inversion(args, cfg, rank, world, local_rank):
         print(json.dumps({
             "metric": "nerf_branch_rays_per_s", "value": world * rays / (ms_step * 1e-3), "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong" if shared else "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "scaling": "strong" if shared else "weak", "vs_baseline": None, "dtype": _dtype(args.precision), "data": "synthetic",
             "images_per_s": world * imgs / (ms_step * 1e-3),
             "config": {"workload": cfg["desc"], "images_per_gpu": imgs,
                        "collective": "all-reduce (NCCL, captured in the step's CUDA graph) of the shared latent's gradient every step"
@@ -423,7 +433,7 @@ def run_full_render(args, cfg, rank, world, local_rank):
         line = {
             "metric": "nerf_branch_rays_per_s", "value": world * rays / (ms_step * 1e-3), "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "images_per_s": world * B / (ms_step * 1e-3),
+            "vs_baseline": None, "dtype": _dtype(args.precision), "data": "synthetic", "images_per_s": world * B / (ms_step * 1e-3),
             "config": {"workload": cfg["desc"], "images_per_gpu": B, "rays_per_image": IMG * IMG, "samples_per_ray": N, "layers": D,
                        "image_size": 1024, "weights": "random-init (reference constructors)",
                        "decoder": "reference modules, `op` CUDA extensions replaced by pure-torch stand-ins in every arm",
@@ -793,12 +803,14 @@ def main():
         line = {
             "metric": "nerf_branch_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "vs_baseline": None, "dtype": _dtype(args.precision), "data": "synthetic",
             "images_per_s": world * B / (ms_step * 1e-3), "ms_per_step_min": ms_min,
             "config": {"workload": cfg["desc"], "images_per_gpu": B, "rays_per_image": IMG * IMG, "samples_per_ray": N,
                        "layers": D, "weights": "random-init (reference distributions)", "sampling": "eval (unperturbed)",
                        "l2": "flushed (256 MiB write) between timed steps, outside the event pair",
-                       "d2h": "rgb_map+mask+xyz to pinned host (feature_map stays on device for the decoder)"},
+                       "d2h": "rgb_map+mask+xyz to pinned host (feature_map stays on device for the decoder)",
+                       "arithmetic": OPERANDS if args.precision == "bf16" else
+                       "fp32 mode: two-way fp16 split operands, three tcgen05 products per layer, FiLM / sines in fp32"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": ms_e2e, "ms_per_step_unpipelined": ms_e2e_serial,
                     "how": "pinned host -> device upload, render, device -> host download of rgb_map+mask+xyz every step; "
                            "downloads overlap the next step on a copy stream; one event pair around all steps "
@@ -808,7 +820,10 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf, "traffic": traffic,
-                         "kernel": "fused_forward_pair_kernel + its two per-image weight-image kernels (step minus style_prep)",
+                         "kernel": "fused_forward_pair_kernel + its two per-image weight-image kernels (step minus style_prep)"
+                         if args.precision == "bf16" else
+                         "raygen_kernel + mlp_tc32_kernel + composite_fwd_kernel per image chunk (algorithmic FLOPs; the tensor "
+                         "cores execute three fp16 products per hidden layer, i.e. ~3x these)",
                          "peak_source": peak_src, "kernel_ms": ms_kernel, "flops_per_launch": flops_launch,
                          "frac_of_nominal_2250": achieved / 2250.0,
                          "frac_of_burst": achieved / peaks.get("bf16_tflops", 1590.0)},
