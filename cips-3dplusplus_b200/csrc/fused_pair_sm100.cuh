@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
     uint32_t cnt = 0;                                    // completed phases of acc_full[s]
     Cursor cur;
     cur.init(a, ps0 + s, n_pairslots);
-    C3D_PROF_DECL(8);   // 0 other (geometry, point stages, post), 1 wait acc, 4 sines + stores first K-chunk, 5 second, 6 arrive
+    C3D_PROF_DECL(8);   // 0 post epilogue (+ Wgt build), 1 wait acc, 2 density stage, 4 sines + stores first K-chunk, 5 second, 6 arrive, 7 geometry
 
     for (; cur.valid(); ) {
       const int u = cur.pu;
@@ -483,6 +483,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
           st_v4(aux_row + 128, pack_bf16x2(e[8], e[9]), pack_bf16x2(e[10], e[11]), pack_bf16x2(1.0f, 1.0f), 0u);
         }
         arrive_ready();
+        C3D_PROF(7);
 
         float sdf = 0.f, wgt = 0.f;
         float sdfa[4] = {0.f, 0.f, 0.f, 0.f};                // partial sums of the sdf head over my channels
@@ -567,6 +568,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
               if (t == TILE - 1) misc->carry[s] = (k == N - 1) ? 1.0f : T * om;
             }
             sdfa[0] = sdfa[1] = sdfa[2] = sdfa[3] = 0.f;
+            C3D_PROF(2);
           } else {
             arrive_ready();
             C3D_PROF(6);
@@ -575,7 +577,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
 
         // ------------------------------------------------ post job: composited features (thread = channel) + rgb (thread = point)
         {
+          C3D_PROF(0);
           mbar_wait(&misc->acc_full[s], cnt & 1u);
+          C3D_PROF(1);
           cnt++;
           tc_fence_after();
           float rgbv[3] = {brgb0, brgb1, brgb2};         // raw rgb of my point: 4 partial sums
@@ -723,8 +727,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
 #ifdef C3D_KERNEL_PROF
     C3D_PROF(0);
     if (blockIdx.x < 2 && t == 0)
-      printf("c3d prof pair eg[blk %d slot %d grp %d]: total %lld  other %lld  wait acc %lld (%lld %lld)  sines chunk 0 %lld chunk 1 %lld  arrive %lld\n",
-             (int)blockIdx.x, s, grp, clock64() - prof_begin, prof_t[0], prof_t[1], prof_t[2], prof_t[3], prof_t[4], prof_t[5], prof_t[6]);
+      printf("c3d prof pair eg[blk %d slot %d grp %d]: total %lld  post epilogue (+ Wgt build) %lld  wait acc %lld  density stage %lld  (%lld)  sines chunk 0 %lld chunk 1 %lld  arrive %lld  geometry %lld\n",
+             (int)blockIdx.x, s, grp, clock64() - prof_begin, prof_t[0], prof_t[1], prof_t[2], prof_t[3], prof_t[4], prof_t[5], prof_t[6], prof_t[7]);
 #endif
   }
 

@@ -216,22 +216,35 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
-// arrive on a barrier that lives in another CTA of the cluster (address from mapa_u32)
+// Arrive on a barrier that lives in another CTA of the cluster (address from mapa_u32).  Default semantics (.release.cta), as
+// in CUTLASS's ClusterBarrier::arrive(cta_id): what the arrival publishes is this thread's shared-memory stores to its OWN CTA,
+// already fenced into the async proxy, for its own SM's tensor core to read -- nothing a thread of the other CTA loads.  With
+// .release.cluster the instruction became MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR, which also waits for every outstanding global
+// store of the thread (the feature rows after a post job: thousands of cycles on the chain of a tile).
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+#ifdef C3D_CLUSTER_SCOPE_BARRIERS
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
+#ifdef C3D_CLUSTER_SCOPE_BARRIERS
       "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+#else
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"     // .acquire.cluster costs a CCTL.IVALL (L1 flush) per wait
+#endif
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
 }
-// wait on a barrier that other CTAs of the cluster arrive on (acquire at cluster scope)
+// wait on a barrier that other CTAs of the cluster arrive on (the waiter -- the MMA issuer or the relay -- reads no memory
+// the arriving threads wrote: it issues tcgen05 instructions or forwards the arrival)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait_cluster(bar, parity)) return;
   const long long t0 = clock64();
