@@ -420,11 +420,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
       __syncwarp();
       if (lane == 0) { if (leader) mbar_arrive(&misc->a_ready[s]); else mbar_arrive_remote(ready_remote); }
     };
-    float carry_f[2] = {0.f, 0.f};                       // partial feature sums of a ray continuing into the next tile
+    float carry_f = 0.f;                                 // partial feature sum (my channel) of a ray continuing into the next tile
     uint32_t cnt = 0;                                    // completed phases of acc_full[s]
     Cursor cur;
     cur.init(a, ps0 + s, n_pairslots);
-    C3D_PROF_DECL(8);   // 0 post epilogue (+ Wgt build), 1 wait acc, 2 density stage, 4 sines + stores first K-chunk, 5 second, 6 arrive, 7 geometry
+    C3D_PROF_DECL(12);   // 8 post: TMEM read-out, 9 feature stores, 10 ray sums + outputs, 11 geometry compute; 0 post epilogue (+ Wgt build), 1 wait acc, 2 density stage, 4 sines + stores first K-chunk, 5 second, 6 arrive, 7 geometry
 
     for (; cur.valid(); ) {
       const int u = cur.pu;
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
       const int ntiles = cur.ntiles;
       const float near = a.near[img], far = a.far[img];
       const float nscale = 2.0f / (far - near);
-      carry_f[0] = carry_f[1] = 0.f;
+      carry_f = 0.f;
 
       for (int tile = 0; tile < ntiles; ++tile, cur.next_tile(a)) {
         // ------------------------------------------------ geometry of my point (nerf_utils.py:17-170)
@@ -482,6 +482,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
           st_v4(aux_row, pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
           st_v4(aux_row + 128, pack_bf16x2(e[8], e[9]), pack_bf16x2(e[10], e[11]), pack_bf16x2(1.0f, 1.0f), 0u);
         }
+        C3D_PROF(11);
         arrive_ready();
         C3D_PROF(7);
 
@@ -602,6 +603,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
             tmem_ld_wait();
 #pragma unroll
             for (int jx = 0; jx < 16; ++jx) fv[jx] = __float_as_uint(__uint_as_float(fv[jx]) + __uint_as_float(fw[jx]));
+            C3D_PROF(8);
             // thread = channel t + 128 hh, fv[jx] = ray slot jx.  (b, hw, 256): a warp writes 32 consecutive channels of a
             // ray (128 B); (b, 256, hw): a thread writes up to 16 consecutive rays of its channel (64 B)
             const int ray0 = min(r0 + rl0, a.n_rays - 1), ch = t + TILE * hh;
@@ -612,22 +614,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
             const int ndst = (a.n_peers > 0 && !a.feat_nchw) ? a.n_peers : 1;
             const size_t gimg = (size_t)(a.n_peers > 0 ? a.gather_off : 0) + img;
             const size_t foff = a.feat_nchw ? (size_t)rl0 * W + ch : (gimg * a.n_rays + ray0) * W + ch;
+            // ray slot jx covers the unit's points [(rl0 + jx) N, (rl0 + jx + 1) N): the first jdone slots end inside this tile
+            // (complete rays: stored), slot jdone -- if it has points here -- continues in the next tile (carried).  Kept to a
+            // few predicated instructions per slot: this block runs once per tile on the critical path of the slot's chain.
+            const int jdone = tile_end / N - rl0;
+            const bool partial = (rl0 + jdone) * N < tile_end;
+            fv[0] = __float_as_uint(__uint_as_float(fv[0]) + carry_f);
+            for (int pr = 0; pr < ndst; ++pr) {
+              float* dst = (a.feat_nchw ? scratch : (a.n_peers > 0 ? reinterpret_cast<float*>(a.peer_feat[pr]) : a.feature_map)) + foff;
 #pragma unroll
-            for (int jx = 0; jx < RAYS; ++jx) {
-              const int rbeg = (rl0 + jx) * N, rend = rbeg + N;      // point range of ray slot jx inside the unit
-              if (rbeg < tile_end) {                                  // uniform: the slot is in use
-                float fvv = __uint_as_float(fv[jx]);
-                if (jx == 0) fvv += carry_f[hh];
-                if (rend <= tile_end) {                               // ray complete
-                  for (int pr = 0; pr < ndst; ++pr) {
-                    float* fb = a.feat_nchw ? scratch : (a.n_peers > 0 ? reinterpret_cast<float*>(a.peer_feat[pr]) : a.feature_map);
-                    fb[foff + (size_t)jx * W] = fvv;
-                  }
-                }
-                if (rend >= tile_end) carry_f[hh] = rend > tile_end ? fvv : 0.f;   // last slot of the tile
-              }
+              for (int jx = 0; jx < RAYS; ++jx)
+                if (jx < jdone) dst[jx * W] = __uint_as_float(fv[jx]);
             }
+            float cnext = 0.f;
+#pragma unroll
+            for (int jx = 0; jx < RAYS; ++jx)
+              if (jx == jdone) cnext = __uint_as_float(fv[jx]);
+            carry_f = partial ? cnext : 0.f;
           }
+          C3D_PROF(9);
           if (a.feat_nchw && tile == ntiles - 1) {
             // ---- the unit's rays are complete: scratch [ray][channel] -> (b, 256, hw), thread = channel, 8 rays per 16-byte
             // (bf16) / 2 x 16-byte (fp32) store; to every peer's gathered tensor when the all-gather is fused
@@ -722,13 +727,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) fused_forward_pair_kernel(const A
           }
           }
         }
+        C3D_PROF(10);
       }  // tiles
     }    // pair-units
 #ifdef C3D_KERNEL_PROF
     C3D_PROF(0);
     if (blockIdx.x < 2 && t == 0)
-      printf("c3d prof pair eg[blk %d slot %d grp %d]: total %lld  post epilogue (+ Wgt build) %lld  wait acc %lld  density stage %lld  (%lld)  sines chunk 0 %lld chunk 1 %lld  arrive %lld  geometry %lld\n",
-             (int)blockIdx.x, s, grp, clock64() - prof_begin, prof_t[0], prof_t[1], prof_t[2], prof_t[3], prof_t[4], prof_t[5], prof_t[6], prof_t[7]);
+      printf("c3d prof pair eg[blk %d slot %d grp %d]: total %lld  post epilogue (+ Wgt build) %lld  wait acc %lld  density stage %lld  (%lld)  sines chunk 0 %lld chunk 1 %lld  arrive %lld  first arrive %lld | post: read-out %lld feature stores %lld ray sums %lld geometry %lld\n",
+             (int)blockIdx.x, s, grp, clock64() - prof_begin, prof_t[0], prof_t[1], prof_t[2], prof_t[3], prof_t[4], prof_t[5], prof_t[6], prof_t[7], prof_t[8], prof_t[9], prof_t[10], prof_t[11]);
 #endif
   }
 
