@@ -890,8 +890,7 @@ static int backward_simt(const c3d_bwd_params* bp, cudaStream_t st) {
     m.feat = reinterpret_cast<float*>(ck + w.c_feat); m.rgb = reinterpret_cast<float*>(ck + w.c_rgb);
     m.sdf = reinterpret_cast<float*>(ck + w.c_sdf);
     m.save_acc = reinterpret_cast<float*>(ck + w.c_acc); m.save_stride = (size_t)ni * P * W; m.n_imgs = ni;
-    mlp_fp32_kernel<<<(unsigned)(ni * m.tiles_per_img), 256, F32_SMEM, st>>>(m);
-    C3D_LAUNCH_CHECK();
+    { const int rc = launch_mlp_fp32(m, ni, st); if (rc != C3D_OK) return rc; }   // tensor cores unless fp32=simt
     // 2. compositing backward
     CompositeBwdArgs c;
     memset(&c, 0, sizeof(c));
@@ -1206,8 +1205,7 @@ int c3d_eikonal_backward(const c3d_bwd_params* bp, const float* g_eik, c3d_strea
     m.feat = reinterpret_cast<float*>(ck + w.c_feat); m.rgb = reinterpret_cast<float*>(ck + w.c_rgb);
     m.sdf = reinterpret_cast<float*>(ck + w.c_sdf);
     m.save_acc = reinterpret_cast<float*>(ck + w.c_acc); m.save_stride = (size_t)ni * P * W; m.n_imgs = ni;
-    mlp_fp32_kernel<<<(unsigned)(ni * m.tiles_per_img), 256, F32_SMEM, st>>>(m);
-    C3D_LAUNCH_CHECK();
+    { const int rc = launch_mlp_fp32(m, ni, st); if (rc != C3D_OK) return rc; }   // tensor cores unless fp32=simt
     // 2. tangent sweep along v, 3. reverse sweep over both chains
     EikArgs e;
     memset(&e, 0, sizeof(e));
