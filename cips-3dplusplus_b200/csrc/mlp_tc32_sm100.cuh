@@ -43,8 +43,9 @@ constexpr float LO_SCALE = 2048.0f, LO_UNSCALE = 1.0f / 2048.0f;
 constexpr int SM_ACT = 0;                                   // hi, lo'
 constexpr int SM_STAGE = NSPLIT * SPLIT_BYTES;              // 131072
 constexpr int SM_RED = SM_STAGE + NSTAGE * STAGE_BYTES;     // 212992  [4 column groups][128] float: sdf partial sums
-constexpr int SM_MISC = SM_RED + 4 * TILE * 4;              // 215040
-constexpr int SMEM_BYTES = SM_MISC + 128;                   // 215168: no slack for re-alignment, see the trap below
+constexpr int SM_SCR = SM_RED + 4 * TILE * 4;               // 215040  [4 column groups][128] float4: rgb partial sums
+constexpr int SM_MISC = SM_SCR + 4 * TILE * 16;             // 223232
+constexpr int SMEM_BYTES = SM_MISC + 128;                   // 223360: no slack for re-alignment, see the trap below
 
 struct Misc {
   uint64_t full[NSTAGE], empty[NSTAGE], a_ready, acc_full;
@@ -107,6 +108,15 @@ __device__ __forceinline__ void sin_inplace(float (&x)[N]) {
     for (int i = 0; i < N; ++i) x[i] = sin_poly(x[i]);
   }
 }
+
+// in-kernel cycle counters of one epilogue thread and of the issuer (development builds only: -DC3D_KERNEL_PROF)
+#ifdef C3D_KERNEL_PROF
+#define TC32_PROF_DECL(n) long long pt_[n] = {}; long long pm_ = clock64(); const long long pb_ = pm_
+#define TC32_PROF(i) do { const long long now_ = clock64(); pt_[i] += now_ - pm_; pm_ = now_; } while (0)
+#else
+#define TC32_PROF_DECL(n) do { } while (0)
+#define TC32_PROF(i) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc32_kernel(const MlpF32Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -171,9 +181,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc32_kernel(const MlpF32Args 
     const uint32_t act_base = smem_u32(smem + SM_ACT), stage_base = smem_u32(smem + SM_STAGE);
     const uint32_t acc0 = tmem_base, acc1 = tmem_base + 256u;
     uint32_t n = 0, acnt = 0;
+    TC32_PROF_DECL(4);                                   // 0 issue, 1 wait a_ready, 2 wait full
     for (int pt = cl; pt < total; pt += ncl)
       for (int l = 1; l <= D; ++l) {
+        TC32_PROF(0);
         mbar_wait_cluster(&misc->a_ready, acnt & 1u);
+        TC32_PROF(1);
         acnt++;
         tc_fence_after();
 #pragma unroll 1
@@ -181,7 +194,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc32_kernel(const MlpF32Args 
 #pragma unroll
           for (int sp = 0; sp < NSPLIT; ++sp, ++n) {
             const uint32_t st = n % NSTAGE, ph = (n / NSTAGE) & 1u;
+            TC32_PROF(0);
             mbar_wait_cluster(&misc->full[st], ph);
+            TC32_PROF(2);
             tc_fence_after();
             if (issue) {
               const uint64_t bd = umma_desc_kmajor_sw128(stage_base + st * STAGE_BYTES);
@@ -200,6 +215,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc32_kernel(const MlpF32Args 
         if (issue) umma_commit_pair(&misc->acc_full, (uint16_t)0x3);
         __syncwarp();
       }
+#ifdef C3D_KERNEL_PROF
+    TC32_PROF(0);
+    if (blockIdx.x == 0 && issue)
+      printf("tc32 prof mma: total %lld  issue %lld  wait a_ready %lld  wait full %lld\n", clock64() - pb_, pt_[0], pt_[1], pt_[2]);
+#endif
   } else if (warp >= 4) {
     // ============================================================ epilogue (both CTAs)
     const int e = warp - 4, quad = e & 3, grp = e >> 2;
@@ -207,6 +227,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc32_kernel(const MlpF32Args 
     const int c0 = grp * 64;                                   // my 64 channels = K-chunk grp of the next layer's operand
     const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, t1 = t0 + 256u;
     const uint32_t row_hi = smem_u32(smem + SM_ACT) + (uint32_t)grp * CHUNK_BYTES + (uint32_t)row * 128u;
+    // feature staging of the view layer: my warp's own 2 x 4 KB of the split tiles (its 32 rows of K-chunk grp, hi and lo tile)
+    // as [32 points][64 channels] fp32, rows 0..15 in the hi part, 16..31 in the lo part, 16-byte units XOR-swizzled with the row
+    const uint32_t stage_warp = smem_u32(smem + SM_ACT) + (uint32_t)grp * CHUNK_BYTES + (uint32_t)(quad * 32) * 128u;
+    const uint32_t stage_row = stage_warp + (uint32_t)((lane & 16) ? SPLIT_BYTES : 0) + (uint32_t)((lane & 15) * 256);
     const int r7 = row & 7;
     const uint32_t ready_remote = mapa_u32(smem_u32(&misc->a_ready), 0u);
     float* red = reinterpret_cast<float*>(smem + SM_RED);
@@ -215,6 +239,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc32_kernel(const MlpF32Args 
     const float* scal = reinterpret_cast<const float*>(a.blob + a.L.scal);
     const int n_rays = a.pts_per_img / a.n_samples;
     uint32_t cnt = 0;
+    TC32_PROF_DECL(4);                                   // 0 layer 0 (+ tile set-up), 1 wait acc, 2 epilogues, 3 view layer + heads
     auto arrive_ready = [&]() {
       fence_proxy_async_smem();
       tc_fence_before();
@@ -259,9 +284,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc32_kernel(const MlpF32Args 
         if (D == 1) sdf_out(sp, gp, valid);
       }
       arrive_ready();
+      TC32_PROF(0);
       // ---- layers 1 .. D
       for (int l = 1; l <= D; ++l) {
         mbar_wait(&misc->acc_full, cnt & 1u);
+        TC32_PROF(1);
         cnt++;
         tc_fence_after();
         const float2* film = a.film + ((size_t)img * (D + 1) + l) * W + c0;
@@ -312,16 +339,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc32_kernel(const MlpF32Args 
               const float4 w = __ldg(wrgb + c0 + j * 16 + i);
               rr = fmaf(w.x, x[i], rr); rg = fmaf(w.y, x[i], rg); rb = fmaf(w.z, x[i], rb);
             }
-            if (valid) {
-              float4* o = reinterpret_cast<float4*>(a.feat + gp * W + c0 + j * 16);
+            // features: staged in this warp's own (now dead) rows of the split tiles, written out row by row below -- a thread
+            // storing its own 64 B of a 1 KB row made every STG.128 touch 32 different lines (8.2 k LSU wavefronts per tile-layer)
 #pragma unroll
-              for (int i = 0; i < 4; ++i) o[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-            }
+            for (int i = 0; i < 4; ++i)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + (uint32_t)(((4 * j + i) ^ (lane & 15)) << 4)),
+                           "f"(x[4 * i]), "f"(x[4 * i + 1]), "f"(x[4 * i + 2]), "f"(x[4 * i + 3]) : "memory");
           }
         };
         if (l == D) {
 #pragma unroll 1
           for (int j = 0; j < 4; ++j) chunk(j, std::integral_constant<int, 2>{});
+          __syncwarp();
+          // my warp's [32 points][64 channels] block: 16 lanes per row (256 B contiguous), two rows per instruction
+          const int qw = (pt - img * ptpi) * 2 * TILE + (int)rank * TILE + quad * 32;      // first point of my warp
+#pragma unroll 4
+          for (int kk = 0; kk < 16; ++kk) {
+            const int rw = 2 * kk + (lane >> 4), u = lane & 15;
+            const uint32_t src = stage_warp + (uint32_t)((rw & 16) ? SPLIT_BYTES : 0) + (uint32_t)((rw & 15) * 256) +
+                                 (uint32_t)((u ^ (rw & 15)) << 4);
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src) : "memory");
+            if (qw + rw < a.pts_per_img)
+              *reinterpret_cast<float4*>(a.feat + ((size_t)img * a.pts_per_img + qw + rw) * W + c0 + u * 4) = v;
+          }
+          __syncwarp();
         } else if (l == D - 1) {
 #pragma unroll 1
           for (int j = 0; j < 4; ++j) chunk(j, std::integral_constant<int, 1>{});
@@ -332,10 +374,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc32_kernel(const MlpF32Args 
         if (l < D) {
           if (l == D - 1) sdf_out(sp, gp, valid);
           arrive_ready();
+          TC32_PROF(2);
         } else {
-          // rgb head: partial sums of the four column groups through the (now dead) first 8 KB of the hi tile's K-chunk 0,
-          // which only column group 0 writes again (layer 0 of the next tile): its 128 threads meet once more after the read
-          float4* scr = reinterpret_cast<float4*>(smem + SM_ACT);
+          // rgb head: partial sums of the four column groups
+          float4* scr = reinterpret_cast<float4*>(smem + SM_SCR);
           scr[grp * TILE + row] = make_float4(rr, rg, rb, 0.f);
           named_bar_sync(1, EPW * 32);
           if (grp == 0) {
@@ -347,10 +389,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_tc32_kernel(const MlpF32Args 
               o[2] = ((p0.z + p1.z) + (p2.z + p3.z)) + scal[3];
             }
           }
-          if (grp == 0) named_bar_sync(2, TILE);
+          TC32_PROF(3);
         }
       }
     }
+#ifdef C3D_KERNEL_PROF
+    if (blockIdx.x == 0 && threadIdx.x == 128)
+      printf("tc32 prof eg: total %lld  layer 0 %lld  wait acc %lld  epilogues %lld  view layer %lld\n", clock64() - pb_, pt_[0], pt_[1], pt_[2], pt_[3]);
+#endif
   }
 
   tc_fence_before();
