@@ -511,18 +511,26 @@ __global__ void __launch_bounds__(nthreads(kEgw), 1) fused_forward_kernel(const 
             __nv_bfloat16* hbase = reinterpret_cast<__nv_bfloat16*>(a.feature_map) + ((size_t)img * W + ch) * a.n_rays + r0 + rl0;
             const size_t fstride = a.feat_nchw ? 1 : W;
             const bool fbf16 = a.feat_nchw == 2;          // (b, 256, hw) bf16: the decoder hand-off at half the bytes
+            // ray slot jx covers the unit's points [(rl0 + jx) N, (rl0 + jx + 1) N): the first jdone slots end inside this tile
+            // (complete rays: stored), slot jdone -- if it has points here -- continues in the next tile (carried).  A few
+            // predicated instructions per slot (the first version spent ~460 instructions per warp and tile here).
+            const int jdone = tile_end / N - rl0;
+            const bool partial = (rl0 + jdone) * N < tile_end;
+            fv[0] = __float_as_uint(__uint_as_float(fv[0]) + carry_f[hh]);
+            if (fbf16) {
 #pragma unroll
-            for (int jx = 0; jx < RAYS; ++jx) {
-              const int rbeg = (rl0 + jx) * N, rend = rbeg + N;      // point range of ray slot jx inside the unit
-              if (rbeg < tile_end) {                                  // uniform: the slot is in use
-                float fvv = __uint_as_float(fv[jx]);
-                if (jx == 0) fvv += carry_f[hh];
-                if (rend <= tile_end) {                                       // ray complete
-                  if (fbf16) hbase[jx] = __float2bfloat16_rn(fvv); else fbase[(size_t)jx * fstride] = fvv;
-                }
-                if (rend >= tile_end) carry_f[hh] = rend > tile_end ? fvv : 0.f;   // last slot of the tile
-              }
+              for (int jx = 0; jx < RAYS; ++jx)
+                if (jx < jdone) hbase[jx] = __float2bfloat16_rn(__uint_as_float(fv[jx]));
+            } else {
+#pragma unroll
+              for (int jx = 0; jx < RAYS; ++jx)
+                if (jx < jdone) fbase[(size_t)jx * fstride] = __uint_as_float(fv[jx]);
             }
+            float cnext = 0.f;
+#pragma unroll
+            for (int jx = 0; jx < RAYS; ++jx)
+              if (jx == jdone) cnext = __uint_as_float(fv[jx]);
+            carry_f[hh] = partial ? cnext : 0.f;
           }
           tmem_ld_wait();
           tc_fence_before();
