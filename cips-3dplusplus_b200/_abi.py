@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("C3D_LIB") or os.path.join(HERE, "libc3dpp.so")   # C3D_LIB: A/B builds (bench_tools)
 SRC = os.path.join(HERE, "csrc", "c3d_abi.cu")
-ABI_VERSION = 10
+ABI_VERSION = 11
 MAX_LAYERS = 16
 MAX_PEERS = 16
 MIN_SAMPLES_BF16 = 8     # fused::MIN_SAMPLES (csrc/fused_common.cuh)

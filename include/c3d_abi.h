@@ -34,14 +34,17 @@
 extern "C" {
 #endif
 
-#define C3D_ABI_VERSION 10
+#define C3D_ABI_VERSION 11 /* 11: packed-blob layout 2 (fp16 weight images; a blob packed by an older library must be re-packed) */
 #define C3D_MAX_LAYERS 16
 #define C3D_W 256
 
 typedef struct CUstream_st* c3d_stream_t; /* == cudaStream_t */
 
 enum { C3D_OK = 0, C3D_ERR_ARG = -1, C3D_ERR_CUDA = -2, C3D_ERR_UNSUPPORTED = -3 };
-enum { C3D_MODE_FP32 = 0, C3D_MODE_BF16 = 1 };          /* arithmetic of the point MLP */
+/* Arithmetic of the point MLP.  C3D_MODE_FP32: fp32 parity mode (products formed on the tensor cores from two-way fp16 split
+ * operands, fp32-accurate; option fp32=simt selects the FP32-pipe kernel).  C3D_MODE_BF16: the 16-bit tensor-core mode (the
+ * reference's autocast counterpart; since ABI 11 its hidden-layer operands are IEEE half, not bfloat16: same rate, 8x finer). */
+enum { C3D_MODE_FP32 = 0, C3D_MODE_BF16 = 1 };
 enum { C3D_INPUT_POSES = 0, C3D_INPUT_POINTS = 1 };
 /* feature_map layout: (b,hw,256) fp32 as the reference's renderer returns it; (b,256,hw) fp32 as the decoder consumes it
  * (model_v3.py:1014); (b,256,hw) bf16 -- the same hand-off at half the bytes (inference only: MODE_BF16, no backward).  The
