@@ -52,4 +52,4 @@ def _default_kernel_options():
     yield
     import cips3dpp_b200 as c3d
     if c3d._abi._lib is not None:
-        c3d._abi.set_options(fwd="pair", cluster=2, grid=0, egw=4, bwd="tc", resample="auto", resample_rb=0, debug=0)
+        c3d._abi.set_options(fwd="pair", cluster=2, grid=0, egw=4, bwd="tc", fp32="tc", resample="auto", resample_rb=0, debug=0)

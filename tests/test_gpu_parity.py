@@ -187,8 +187,12 @@ def _run_points(case, precision):
     return c, [o.cpu().numpy() for o in out[:5]], m
 
 
+@pytest.mark.parametrize("kernel", ["tc", "simt"])
 @pytest.mark.parametrize("case", CASES)
-def test_forward_fp32_matches_reference_golden(case):
+def test_forward_fp32_matches_reference_golden(case, kernel):
+    """fp32 parity mode: the tensor-core MLP (two-way fp16 split products, default) and round 1's FP32-pipe kernel."""
+    import cips3dpp_b200 as c3d
+    c3d._abi.set_options(fp32=kernel)              # (the autouse fixture of conftest.py restores the defaults)
     c, (rgb_map, feat, sdf, mask, xyz), m = _run_points(case, "fp32")
     assert sdf.shape == c["sdf"].shape and feat.shape == c["feature_map"].shape
     assert rel_l2(feat, c["feature_map"]) < FP32_REL
